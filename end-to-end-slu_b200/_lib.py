@@ -1,0 +1,55 @@
+"""ctypes binding of the C-ABI shared library (include/slu_b200.h).  No CPU fallback: if the
+library is missing or a kernel launch fails this raises -- the CUDA path must fail loudly."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libslu_b200.so")
+_lib = None
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+SIGNATURES = {
+    # name: argtypes (all return int = cudaError_t, 0 on success)
+    "slu_sinc_filters_fwd": [_P, _P, _P, _P],
+    "slu_sinc_filters_bwd": [_P, _P, _P, _P, _P, _P],
+    "slu_sincconv_fwd_simt": [_P, _P, _I, _I, _P, _P, _P],
+    "slu_sincconv_bwd_simt": [_P, _P, _P, _I, _I, _P, _P],
+    "slu_gru_fwd_simt": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "slu_gru_bwd_simt": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "slu_tc_selftest": [_P, _P, _P, _I, _I, _P],
+}
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError("slu_b200: %s not built -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(nvcc, sm_100a).  There is no fallback path." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is missing: loud by design
+            fn.argtypes = argtypes
+            fn.restype = _I
+        _lib = lib
+    return _lib
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "slu_b200 kernels take contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    err = getattr(load(), name)(*args)
+    if err != 0:
+        raise RuntimeError("slu_b200: %s failed with cudaError %d" % (name, err))

@@ -1,0 +1,121 @@
+// Minimal hand-written tcgen05 / TMEM / mbarrier primitives for sm_100a (inline PTX).
+// Operand convention used by every tensor-core kernel in this library:
+//   * A and B tiles are K-major bf16 in shared memory, NO swizzle ("interleaved" canonical layout):
+//       core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes;
+//       byte(r, k) = (k/8)*LBO + (r/8)*SBO + (r%8)*16 + (k%8)*2
+//     We use the "k-chunk-major" tile: LBO = rows*16, SBO = 128, i.e. all rows of one 8-element
+//     k-chunk are contiguous.  Threads stage operands with 16-byte st.shared (conflict-free).
+//   * fp32 data is split on the fly into bf16 hi + bf16 lo; every product is issued as
+//     hi*hi + hi*lo + lo*hi (3 MMAs, fp32 accumulate in TMEM)  -> ~2^-17 relative error,
+//     which the 1e-3 logit tolerance needs (see oracle/precision_study.py).
+//   * D (accumulator) lives in TMEM: lane = M row (0..127), column = N index (fp32).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace tc05 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+
+// ---- fences ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM allocation (one full warp) ---------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- descriptors -----------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major, SWIZZLE_NONE, version 1 (Blackwell).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Instruction descriptor: kind::f16, A=B=bf16 (K-major), D=f32, dense.
+__host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- MMA issue / commit (single thread) ------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -> registers (warp w may only touch lanes 32*(w%4) .. +31) -------------------------------
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- fp32 -> (bf16 hi, bf16 lo) split helpers --------------------------------------------------------
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+// 8 consecutive-k fp32 values -> one 16-byte hi chunk and one 16-byte lo chunk
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y);
+  split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
+}
+// byte offset of the 16-byte chunk (row r, k-chunk kc) inside a k-chunk-major tile of `rows` rows
+__device__ __forceinline__ uint32_t chunk_off(int rows, int r, int kc) { return (uint32_t)(kc * rows + r) * 16u; }
+
+// D[tmem] (+)= A(hi,lo) . B(hi,lo)^T over `k16` K-steps of 16, 3-pass bf16 split.  Single thread.
+// a_hi/a_lo/b_hi/b_lo: shared-memory byte addresses of k-chunk-major tiles with a_rows / b_rows rows.
+__device__ __forceinline__ void mma_split3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_rows, uint32_t b_hi, uint32_t b_lo,
+                                           int b_rows, int k16, uint32_t idesc, bool accumulate_first) {
+  const uint32_t a_lbo = a_rows * 16, b_lbo = b_rows * 16;
+  uint32_t acc = accumulate_first ? 1u : 0u;
+  for (int kk = 0; kk < k16; ++kk) {
+    const uint64_t ah = smem_desc(a_hi + kk * 2 * a_lbo, a_lbo, 128), al = smem_desc(a_lo + kk * 2 * a_lbo, a_lbo, 128);
+    const uint64_t bh = smem_desc(b_hi + kk * 2 * b_lbo, b_lbo, 128), bl = smem_desc(b_lo + kk * 2 * b_lbo, b_lbo, 128);
+    mma_bf16(d_tmem, ah, bh, idesc, acc); acc = 1u;
+    mma_bf16(d_tmem, ah, bl, idesc, 1u);
+    mma_bf16(d_tmem, al, bh, idesc, 1u);
+  }
+}
+
+}  // namespace tc05

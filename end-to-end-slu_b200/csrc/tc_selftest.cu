@@ -1,0 +1,72 @@
+// Self-test of the tcgen05 primitives in tc05.cuh: C[128][N] = A[128][K] . B[N][K]^T with the
+// 3-pass bf16 split, one CTA.  Exercised by tests/test_gpu_kernels.py against an fp64 numpy product.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace {
+__global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                             float* __restrict__ C, int N, int K) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  using namespace tc05;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int kc_n = K / 8;
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = a_hi + 128 * K * 2;
+  uint8_t* b_hi = a_lo + 128 * K * 2;
+  uint8_t* b_lo = b_hi + N * K * 2;
+  for (int idx = tid; idx < 128 * kc_n; idx += 128) {
+    const int r = idx % 128, kc = idx / 128;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = A[(size_t)r * K + kc * 8 + i];
+    uint4 hi, lo; split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(a_hi + chunk_off(128, r, kc)) = hi;
+    *reinterpret_cast<uint4*>(a_lo + chunk_off(128, r, kc)) = lo;
+  }
+  for (int idx = tid; idx < N * kc_n; idx += 128) {
+    const int r = idx % N, kc = idx / N;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = Bm[(size_t)r * K + kc * 8 + i];
+    uint4 hi, lo; split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(b_hi + chunk_off(N, r, kc)) = hi;
+    *reinterpret_cast<uint4*>(b_lo + chunk_off(N, r, kc)) = lo;
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base, 256);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    mma_split3(tmem, smem_u32(a_hi), smem_u32(a_lo), 128, smem_u32(b_hi), smem_u32(b_lo), N, K / 16, idesc_bf16_f32(128, N), false);
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  fence_after_sync();
+  for (int n0 = 0; n0 < N; n0 += 16) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + n0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) C[(size_t)tid * N + n0 + i] = v[i];
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+}  // namespace
+
+extern "C" int slu_tc_selftest(const float* A, const float* B, float* C, int N, int K, void* stream) {
+  if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16 || K > 256) return (int)cudaErrorInvalidValue;
+  const size_t smem = (size_t)(128 + N) * K * 4;
+  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+  int e = slu_set_smem((const void*)tc_selftest_kernel, smem);
+  if (e) return e;
+  tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, C, N, K);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,59 @@
+/* slu_b200 -- C ABI of the Blackwell-native (sm_100a) speech-encoder hot path.
+ *
+ * Drop-in boundary: the reference (lorenlugosch/end-to-end-SLU) has no FFI; its hot path is a chain
+ * of PyTorch library calls inside models.py.  Each entry point below replaces the library calls cited
+ * beside it (reference models.py:<line>); the repo-root models.py mirrors the reference class surface
+ * and reaches these through ctypes (end-to-end-slu_b200/_lib.py).  See INTEGRATION.md.
+ *
+ * Conventions: plain device pointers + sizes, no torch types; every function enqueues work on `stream`
+ * (a cudaStream_t passed as void*), returns 0 or a cudaError_t, never synchronises, never allocates.
+ * All tensors are contiguous row-major fp32 unless stated.  H = 128 hidden units, gate order (r, z, n).
+ */
+#ifndef SLU_B200_H
+#define SLU_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Filter-bank synthesis W[80][401] from the fp64 cut-offs -- replaces the 80-iteration python loop
+ * models.py:82-106 (sinc() :17-24, flip() :7-14). */
+int slu_sinc_filters_fwd(const double* filt_b1, const double* filt_band, float* W, void* stream);
+/* Its analytic backward: dL/dW[80][401] -> dL/dfilt_b1[80], dL/dfilt_band[80] (fp64), including the
+ * max-normalisation (:103) and |.| (:88-89) -- replaces autograd over those ops. */
+int slu_sinc_filters_bwd(const double* filt_b1, const double* filt_band, const float* dW, double* d_b1, double* d_band,
+                         void* stream);
+
+/* conv1d(x[B][1][T], W, stride 80, pad 200) + Abs + MaxPool1d(2, ceil) -- replaces models.py:108, :163-168, :205
+ * (LeakyReLU :211 is the identity on the non-negative result, Dropout(0) :218 likewise).
+ * out[B][L1][80] (time-major), L0=(T-1)/80+1, L1=(L0+1)/2.  route[B][L1][80] (u8, may be NULL): bit0 = which
+ * frame of the pair won, bit1 = sign of the winner, bit2 = winner was exactly 0 (abs has zero gradient). */
+int slu_sincconv_fwd_simt(const float* x, const float* W, int B, int T, float* out, uint8_t* route, void* stream);
+/* dL/dW[80][401] from dL/dout -- replaces cuDNN's conv backward-filter + abs/max-pool autograd.  The waveform
+ * needs no gradient. */
+int slu_sincconv_bwd_simt(const float* x, const float* gy, const uint8_t* route, int B, int T, float* dW, void* stream);
+
+/* Persistent bidirectional GRU recurrence (h0 = 0) with fused gate non-linearities, Dropout mask multiply and
+ * Downsample -- replaces nn.GRU (_VF.gru / cuDNN RNN) at models.py:232/262/686 plus RNNSelect :138-149,
+ * Dropout :246/276/700 and Downsample :26-46.
+ *   gx    [B][T][768]  x.W_ih^T + b_ih for both directions, col = d*384 + g*128 + j
+ *   w_hh  [2][384][128], b_hh [2][384]
+ *   drop_mask [B][T][256] keep-mask scaled by 1/(1-p), or NULL (eval / p = 0)
+ *   ds    1 = Downsample("none",1), 2 = Downsample("avg",2) (ceil mode: an odd tail frame is kept as is)
+ *   y_full [B][T][256] raw hidden states (col = d*128 + j);  y_out [B][ceil(T/ds)][256]
+ *   stash [B][T][1024] (r, z, n, W_hn h + b_hn per direction) for the backward pass, or NULL for inference. */
+int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T, int ds,
+                     float* y_full, float* y_out, float* stash, void* stream);
+/* Backward through time -- replaces _cudnn_rnn_backward.  Emits dgx[B][T][768] (gradient wrt gx) and
+ * dhn[B][T][256] (gradient wrt the n-gate's recurrent pre-activation); the weight/input gradients are dense
+ * GEMMs over these. */
+int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
+                     const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, void* stream);
+
+/* tcgen05 self-test: C[128][N] = A[128][K] . B[N][K]^T (3-pass bf16 split, fp32 accumulate in TMEM). */
+int slu_tc_selftest(const float* A, const float* B, float* C, int N, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,117 @@
+"""GPU parity tests: every kernel is called through the C-ABI (ctypes) and compared with the CPU
+oracle (oracle/torch_ref.py, pinned to the real reference by test_oracle_golden.py).
+Tolerances: forward activations 1e-4 relative (max-abs / max-abs; the north-star bar on the logits is
+1e-3), gradients 2e-3 relative."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_ref as R
+from util import ckpt_params, golden, load_test_wav, rel_err
+
+pytestmark = pytest.mark.gpu
+FWD_TOL, GRAD_TOL = 1e-4, 2e-3
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    p = importlib.import_module("end-to-end-slu_b200")
+    p._lib.load()
+    return p
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+@pytest.mark.parametrize("N,K", [(16, 16), (16, 128), (32, 64), (80, 80), (128, 256), (240, 64), (256, 128)])
+def test_tcgen05_selftest(pkg, N, K):
+    rs = np.random.RandomState(N * 1000 + K)
+    A = rs.standard_normal((128, K)).astype(np.float32)
+    Bm = rs.standard_normal((N, K)).astype(np.float32)
+    C = torch.empty(128, N, device="cuda")
+    pkg._lib.call("slu_tc_selftest", dev(torch.from_numpy(A)).data_ptr(), dev(torch.from_numpy(Bm)).data_ptr(),
+                  C.data_ptr(), N, K, pkg._lib.stream())
+    torch.cuda.synchronize()
+    ref = A.astype(np.float64) @ Bm.astype(np.float64).T
+    err = np.abs(C.cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err < 2e-5, err          # 3-pass bf16 split ~ 2^-16; plain bf16 would be ~4e-3
+
+
+def test_sinc_filters_fwd_bwd(pkg):
+    for src in ("mel", "ckpt"):
+        if src == "mel":
+            p = R.synthetic_params()
+        else:
+            p = ckpt_params()
+        b1 = p[R.P + "phoneme_layers.0.filt_b1"].clone().requires_grad_(True)
+        band = p[R.P + "phoneme_layers.0.filt_band"].clone().requires_grad_(True)
+        W_ref = R.sinc_filters(b1, band)
+        W = pkg.ops.sinc_filters(b1.cuda(), band.cuda())
+        assert rel_err(W.cpu(), W_ref) < 1e-5
+        rs = np.random.RandomState(3)
+        dW = torch.from_numpy(rs.standard_normal((80, 401)).astype(np.float32))
+        W_ref.backward(dW)
+        d_b1 = torch.empty(80, device="cuda", dtype=torch.float64); d_band = torch.empty_like(d_b1)
+        pkg._lib.call("slu_sinc_filters_bwd", dev(b1.detach()).data_ptr(), dev(band.detach()).data_ptr(),
+                      dev(dW).data_ptr(), d_b1.data_ptr(), d_band.data_ptr(), pkg._lib.stream())
+        assert rel_err(d_b1.cpu(), b1.grad) < 1e-3 and rel_err(d_band.cpu(), band.grad) < 1e-3
+
+
+@pytest.mark.parametrize("B,T", [(1, 57585), (3, 8000), (2, 1234), (2, 81), (1, 1), (5, 64000)])
+def test_sinc_frontend_fwd_bwd(pkg, B, T):
+    p = ckpt_params() if T == 57585 else R.synthetic_params()
+    x = load_test_wav() if T == 57585 else R.synthetic_batch(B, T, seed=T)[0]
+    b1 = p[R.P + "phoneme_layers.0.filt_b1"].clone().requires_grad_(True)
+    band = p[R.P + "phoneme_layers.0.filt_band"].clone().requires_grad_(True)
+    ref = R.sinc_frontend(x, b1, band).transpose(1, 2)                      # NLC
+    b1g = b1.detach().cuda().requires_grad_(True); bandg = band.detach().cuda().requires_grad_(True)
+    out = pkg.ops.SincFrontend.apply(x.cuda(), b1g, bandg)
+    assert out.shape == ref.shape
+    assert rel_err(out.detach().cpu(), ref) < FWD_TOL
+    rs = np.random.RandomState(1)
+    gy = torch.from_numpy(rs.standard_normal(tuple(ref.shape)).astype(np.float32))
+    ref.backward(gy)
+    out.backward(gy.cuda())
+    assert b1g.grad.dtype == torch.float64
+    assert rel_err(b1g.grad.cpu(), b1.grad) < GRAD_TOL and rel_err(bandg.grad.cpu(), band.grad) < GRAD_TOL
+
+
+@pytest.mark.parametrize("B,T,I,ds,use_mask", [(3, 7, 60, 2, False), (4, 24, 256, 2, True), (5, 23, 256, 1, True),
+                                               (1, 1, 256, 2, False), (9, 50, 60, 2, False), (2, 360, 60, 2, False)])
+def test_bigru_fwd_bwd(pkg, B, T, I, ds, use_mask):
+    rs = np.random.RandomState(B * 100 + T)
+    gru = torch.nn.GRU(I, 128, batch_first=True, bidirectional=True)
+    with torch.no_grad():
+        for q in gru.parameters():
+            q.copy_(torch.from_numpy(rs.uniform(-0.15, 0.15, size=tuple(q.shape)).astype(np.float32)))
+    x = torch.from_numpy(rs.standard_normal((B, T, I)).astype(np.float32)).requires_grad_(True)
+    mask = torch.from_numpy((rs.uniform(size=(B, T, 256)) >= 0.5).astype(np.float32) * 2) if use_mask else None
+    params = {"g." + k: v for k, v in gru.named_parameters()}
+    y = R.bigru(x, params, "g")
+    y = R.downsample(R.apply_dropout(y, mask), "avg" if ds == 2 else "none", ds)
+    gy = torch.from_numpy(rs.standard_normal(tuple(y.shape)).astype(np.float32))
+    y.backward(gy)
+    g_ref = {k: v.grad.clone() for k, v in gru.named_parameters()}
+    gx_ref = x.grad.clone()
+    gru_c = torch.nn.GRU(I, 128, batch_first=True, bidirectional=True).cuda()
+    gru_c.load_state_dict(gru.state_dict())
+    xc = x.detach().cuda().requires_grad_(True)
+    yc = pkg.ops.bigru(xc, gru_c, None if mask is None else mask.cuda(), ds)
+    assert yc.shape == y.shape
+    assert rel_err(yc.detach().cpu(), y.detach()) < FWD_TOL
+    yc.backward(gy.cuda())
+    assert rel_err(xc.grad.cpu(), gx_ref) < GRAD_TOL
+    for k, v in gru_c.named_parameters():
+        assert rel_err(v.grad.cpu(), g_ref[k]) < GRAD_TOL, k
+
+
+def test_conv_block_nlc(pkg):
+    rs = np.random.RandomState(5)
+    x = torch.from_numpy(rs.standard_normal((3, 80, 37)).astype(np.float32))
+    w = torch.from_numpy(rs.uniform(-0.1, 0.1, (60, 80, 5)).astype(np.float32)); b = torch.from_numpy(rs.uniform(-0.1, 0.1, 60).astype(np.float32))
+    ref = R.conv_block(x, w, b).transpose(1, 2)
+    out = pkg.ops.conv_block_nlc(x.transpose(1, 2).contiguous().cuda(), w.cuda(), b.cuda())
+    assert rel_err(out.cpu(), ref) < FWD_TOL

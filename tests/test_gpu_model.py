@@ -1,0 +1,165 @@
+"""GPU parity of the whole drop-in surface (models.Model / PretrainedModel on cuda:0) against the
+golden vectors of the real reference and the CPU oracle.  North-star bar: intent logits within
+1e-3 relative (max-abs / max-abs) of the reference's CPU fp32 path."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+import models
+from oracle import torch_ref as R
+from util import ckpt_params, golden, load_test_wav, make_config, rel_err
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL = 1e-3      # north star; we assert 10x tighter where fp32 kernels are used
+GRAD_TOL = 5e-3
+
+
+def gpu_model(params=None, train=False):
+    m = models.Model(make_config())
+    assert next(m.parameters()).is_cuda
+    if params is not None:
+        sd = m.state_dict()
+        sd.update({k: v for k, v in params.items() if k in sd})
+        m.load_state_dict(sd)
+    return m.train() if train else m.eval()
+
+
+def test_native_library_is_loaded():
+    pkg = importlib.import_module("end-to-end-slu_b200")
+    pkg._lib.load()
+    maps = open("/proc/self/maps").read()
+    assert "libslu_b200.so" in maps
+
+
+def test_known_answer_testwav_on_gpu():
+    g = golden("golden_testwav.npz")
+    m = gpu_model(ckpt_params())
+    logits, pred = m.predict_intents(load_test_wav())
+    assert logits.is_cuda
+    err = rel_err(logits.detach().cpu(), g["logits"])
+    assert err < LOGIT_TOL / 10, err
+    assert pred.tolist() == [[1, 2, 1]]
+    assert m.decode_intents(load_test_wav().cuda()) == [["action_1", "object_2", "location_1"]]
+    feats = m.pretrained_model.compute_features(load_test_wav())
+    assert feats.shape == (1, 23, 256) and rel_err(feats.detach().cpu(), g["features"]) < LOGIT_TOL / 10
+
+
+@pytest.mark.parametrize("tag", ["small", "ragged", "odd"])
+def test_loss_logits_grads_match_reference_goldens(tag):
+    g = golden("golden_synth_%s.npz" % tag)
+    p = R.synthetic_params(seed=int(g["pseed"]))
+    m = gpu_model(p)
+    for q in m.parameters():
+        q.requires_grad = True
+    x, y = R.synthetic_batch(int(g["B"]), int(g["T"]), seed=int(g["bseed"]))
+    loss, acc = m(x, y)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-4 * float(g["loss"])
+    assert acc.item() == float(g["acc"])
+    logits, pred = m.predict_intents(x)
+    assert rel_err(logits.detach().cpu(), g["logits"]) < LOGIT_TOL / 10
+    assert np.array_equal(pred.cpu().numpy(), g["pred"])
+    named = dict(m.named_parameters())
+    checked = 0
+    for k in p:
+        if "g/" + k not in g.files:
+            continue
+        grad = named[k].grad
+        assert grad is not None and grad.dtype == named[k].dtype, k
+        flat = grad.flatten().cpu()
+        sub = flat if flat.numel() <= 30000 else flat[::7]
+        ref = torch.from_numpy(g["g/" + k])
+        if ref.abs().max() == 0:
+            assert sub.abs().max() < 1e-7, k
+        else:
+            assert rel_err(sub, ref) < GRAD_TOL, (k, rel_err(sub, ref))
+        checked += 1
+    assert checked == 48
+    # the unused ASR heads get no gradient, as in the reference
+    assert named["pretrained_model.word_linear.weight"].grad is None
+
+
+def test_train_mode_dropout_masks_follow_reference_order(monkeypatch):
+    g = golden("golden_synth_dropout.npz")
+    p = R.synthetic_params(seed=int(g["pseed"]))
+    m = gpu_model(p, train=True)
+    for q in m.parameters():
+        q.requires_grad = True
+    x, y = R.synthetic_batch(int(g["B"]), int(g["T"]), seed=int(g["bseed"]))
+    rs = np.random.RandomState(int(g["mask_seed"]))
+    eng = importlib.import_module("end-to-end-slu_b200").engine
+
+    def fake_mask(shape, p_, training, device):
+        assert training and p_ == 0.5
+        return torch.from_numpy((rs.uniform(size=shape) >= 0.5).astype(np.float32) * 2.0).to(device)
+    monkeypatch.setattr(eng, "_drop_mask", fake_mask)
+    loss, _ = m(x, y)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-4 * float(g["loss"])
+    named = dict(m.named_parameters())
+    for k in p:
+        if "gl2/" + k in g.files:
+            ref = float(g["gl2/" + k])
+            assert abs(named[k].grad.double().norm().item() - ref) < GRAD_TOL * ref + 1e-9, k
+
+
+def test_frozen_encoder_only_intent_module_gets_grads():
+    m = gpu_model(R.synthetic_params(seed=2), train=False)
+    m.freeze_all_layers()
+    x, y = R.synthetic_batch(4, 16000, seed=3)
+    loss, _ = m(x, y)
+    loss.backward()
+    named = dict(m.named_parameters())
+    assert named["intent_layers.0.weight_hh_l0"].grad is not None
+    assert named["pretrained_model.word_layers.4.weight_hh_l0"].grad is None
+
+
+def test_full_size_batch_rows_are_independent():
+    """BASELINE-size input (64 x 4 s): utterances are independent, so any row of the big batch must equal
+    the same row run alone through the oracle -- checks tiling / batch-tile boundaries at full size."""
+    p = R.synthetic_params(seed=4)
+    m = gpu_model(p)
+    x, _ = R.synthetic_batch(64, 64000, seed=5)
+    with torch.no_grad():
+        logits, _ = m.predict_intents(x)
+        rows = [0, 37, 63]
+        ref = R.intent_logits(x[rows], p)
+    assert rel_err(logits[rows].cpu(), ref) < LOGIT_TOL / 10
+    assert torch.isfinite(logits).all()
+
+
+def test_cpu_gpu_roundtrip_like_trainer_test():
+    """training.py:150/166 moves the model to the CPU for validation and back."""
+    p = R.synthetic_params(seed=6)
+    m = gpu_model(p)
+    x, y = R.synthetic_batch(2, 8000, seed=7)
+    l_gpu, _ = m(x, y)
+    m.cpu(); m.is_cuda = False
+    l_cpu, _ = m(x, y)
+    m.cuda(); m.is_cuda = True
+    l_gpu2, _ = m(x, y)
+    assert not l_cpu.is_cuda and l_gpu2.is_cuda
+    assert abs(l_gpu.item() - l_cpu.item()) < 1e-4 and abs(l_gpu.item() - l_gpu2.item()) < 1e-6
+
+
+def test_asr_pretraining_forward_on_gpu():
+    g = golden("golden_asr.npz")
+    cfg = make_config(pretraining_type=2)
+    pm = models.PretrainedModel(cfg).eval()
+    p = R.synthetic_params(seed=12, asr=True)
+    sd = pm.state_dict()
+    sd.update({k[len(R.P):]: v for k, v in p.items() if k.startswith(R.P)})
+    pm.load_state_dict(sd)
+    x, _ = R.synthetic_batch(int(g["B"]), int(g["T"]), seed=13)
+    pl, wl, pa, wa = pm(x, torch.from_numpy(g["y_phoneme"]), torch.from_numpy(g["y_word"]))
+    assert abs(pl.item() - float(g["phoneme_loss"])) < 1e-4 * float(g["phoneme_loss"])
+    assert abs(wl.item() - float(g["word_loss"])) < 1e-4 * float(g["word_loss"])
+    (pl + wl).backward()
+    for k, v in pm.named_parameters():
+        if "gl2/" + k in g.files:
+            ref = float(g["gl2/" + k])
+            assert abs(v.grad.double().norm().item() - ref) < GRAD_TOL * ref + 1e-9, k
+    ph, _ = pm.compute_posteriors(x)
+    assert rel_err(ph.detach().cpu(), g["phoneme_logits"]) < 1e-3

@@ -1,0 +1,187 @@
+"""Host-side drop-in surface (models.py) on CPU: state_dict layout, known answer, freeze schedule,
+config reader, C-ABI symbol table.  Where /root/reference exists (build container) the real
+reference is imported and compared directly; on the GPU box those cases skip."""
+import ctypes
+import importlib
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import models
+from util import ckpt_params, golden, load_test_wav, make_config, rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("SLU_REFERENCE", "/root/reference")
+has_ref = os.path.isfile(os.path.join(REF, "models.py"))
+
+
+def cpu_model(cfg=None):
+    m = models.Model(cfg or make_config())
+    m.cpu(); m.is_cuda = False
+    return m
+
+
+def load_ckpt(m):
+    sd = m.state_dict()
+    ck = ckpt_params()
+    missing = set(sd) - set(ck)
+    assert missing == {"pretrained_model.word_linear.weight", "pretrained_model.word_linear.bias"}
+    for k, v in ck.items():
+        assert sd[k].shape == v.shape and sd[k].dtype == v.dtype, k
+    sd.update(ck)
+    m.load_state_dict(sd, strict=True)
+
+
+def test_state_dict_layout_and_known_answer():
+    m = cpu_model().eval()
+    load_ckpt(m)
+    assert m.state_dict()["pretrained_model.phoneme_layers.0.filt_b1"].dtype == torch.float64
+    g = golden("golden_testwav.npz")
+    logits, pred = m.predict_intents(load_test_wav())
+    assert rel_err(logits, g["logits"]) < 2e-5
+    assert pred.tolist() == [[1, 2, 1]]
+    # decode_intents with an index-named table: README.md:42 {activate, lights, kitchen} = (1, 2, 1)
+    assert m.decode_intents(load_test_wav()) == [["action_1", "object_2", "location_1"]]
+    assert rel_err(m.pretrained_model.compute_features(load_test_wav()), g["features"]) < 2e-5
+
+
+def test_unfreeze_schedule_and_print(capsys):
+    cfg = make_config("unfreeze_all_layers", pretraining_type=2)
+    cfg.pretraining_type = 0          # no checkpoint on disk ...
+    m = cpu_model(cfg)
+    m.unfreezing_index = 1            # ... but exercise the pretraining_type=2 schedule
+    m.freeze_all_layers()
+    order = []
+    names = lambda: [l.name for l in list(m.pretrained_model.phoneme_layers) + list(m.pretrained_model.word_layers)
+                     if models.has_params(l) and not models.is_frozen(l)]
+    for _ in range(8):
+        m.unfreeze_one_layer()
+        order.append(set(names()))
+    seq = [sorted(order[0])] + [sorted(order[i] - order[i - 1]) for i in range(1, 8)]
+    assert seq == [["word_rnn1"], ["word_rnn0"], ["phone_rnn1"], ["phone_rnn0"], ["conv2"], ["conv1"], ["sinc0"], []]
+    m.print_frozen()
+    assert "sinc0: unfrozen" in capsys.readouterr().out
+    # unused ASR heads are never frozen
+    assert m.pretrained_model.word_linear.weight.requires_grad
+
+
+def test_config_reader_matches_cfg_semantics():
+    cfg = make_config("unfreeze_all_layers", pretraining_type=2)
+    assert cfg.cnn_N_filt == [80, 60, 60] and cfg.cnn_len_filt == [401, 5, 5] and cfg.cnn_stride == [80, 1, 1]
+    assert cfg.phone_downsample_factor == 640 and cfg.word_downsample_factor == 2560
+    assert cfg.unfreezing_type == 2 and cfg.seq2seq is False and cfg.train_wording_path is None
+    s2s = make_config("seq2seq")
+    assert s2s.seq2seq and s2s.intent_decoder_dim == 256 and s2s.num_intent_decoder_layers == 2
+
+
+def test_forward_loss_acc_matches_golden_on_cpu():
+    from oracle import torch_ref as R
+    g = golden("golden_synth_small.npz")
+    m = cpu_model().eval()
+    sd = m.state_dict()
+    sd.update({k: v for k, v in R.synthetic_params(seed=int(g["pseed"])).items() if k in sd})
+    m.load_state_dict(sd)
+    x, y = R.synthetic_batch(int(g["B"]), int(g["T"]), seed=int(g["bseed"]))
+    loss, acc = m(x, y)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * float(g["loss"])
+    assert acc.item() == float(g["acc"])
+    named = dict(m.named_parameters())
+    for k in ("pretrained_model.phoneme_layers.0.filt_b1", "pretrained_model.phoneme_layers.0.filt_band",
+              "pretrained_model.phoneme_layers.5.bias", "intent_layers.4.weight"):
+        assert rel_err(named[k].grad.flatten(), g["g/" + k]) < 1e-4, k
+        assert named[k].grad.dtype == named[k].dtype
+
+
+def test_cabi_library_exports_declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "slu_b200.h")).read()
+    declared = set(re.findall(r"\bint\s+(slu_\w+)\s*\(", hdr))
+    assert len(declared) >= 7
+    lib_mod = importlib.import_module("end-to-end-slu_b200._lib")
+    assert os.path.isfile(lib_mod.LIB_PATH), "build the library first: python __graft_entry__.py"
+    lib = ctypes.CDLL(lib_mod.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(lib_mod.SIGNATURES), declared ^ set(lib_mod.SIGNATURES)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    lib_mod = importlib.import_module("end-to-end-slu_b200._lib")
+    monkeypatch.setattr(lib_mod, "_lib", None)
+    monkeypatch.setattr(lib_mod, "LIB_PATH", "/nonexistent/libslu_b200.so")
+    with pytest.raises(RuntimeError, match="no fallback"):
+        lib_mod.load()
+
+
+# ---- direct comparison with the real reference (build container only) --------------------------------
+@pytest.fixture(scope="module")
+def reference():
+    if not has_ref:
+        pytest.skip("reference tree not present (GPU box)")
+    saved = {k: sys.modules.get(k) for k in ("models", "data", "soundfile", "textgrid")}
+    for m in ("soundfile", "textgrid"):
+        sys.modules[m] = types.ModuleType(m)
+    sys.path.insert(0, REF)
+    del sys.modules["models"]
+    sys.dont_write_bytecode = True
+    ref_models = importlib.import_module("models")
+    assert ref_models.__file__.startswith(REF)
+    sys.path.remove(REF)
+    sys.modules["ref_models"] = ref_models
+    sys.modules["models"] = saved["models"]
+    yield ref_models
+    for m in ("soundfile", "textgrid"):
+        sys.modules.pop(m, None)
+
+
+def test_same_seed_same_init_and_same_forward_as_reference(reference):
+    cfg = make_config()
+    torch.manual_seed(1234)
+    ref = reference.Model(cfg); ref.cpu(); ref.is_cuda = False
+    torch.manual_seed(1234)
+    new = cpu_model(cfg)
+    sd_r, sd_n = ref.state_dict(), new.state_dict()
+    assert list(sd_r) == list(sd_n)
+    for k in sd_r:
+        assert torch.equal(sd_r[k], sd_n[k]), k
+    x = 0.1 * torch.randn(2, 9000)
+    y = torch.tensor([[1, 2, 3], [0, 13, 0]])
+    ref.eval(); new.eval()
+    l_r, a_r = ref(x, y); l_n, a_n = new(x, y)
+    assert abs(l_r.item() - l_n.item()) < 1e-5 and a_r.item() == a_n.item()
+    lg_r, p_r = ref.predict_intents(x); lg_n, p_n = new.predict_intents(x)
+    assert rel_err(lg_n, lg_r) < 2e-5 and torch.equal(p_r, p_n)
+
+
+def test_unfreeze_matches_reference_for_all_types(reference):
+    for utype, start in ((1, 1), (2, 1), (2, 3), (0, 1)):
+        cfg = make_config(unfreezing_type=utype)
+        ref = reference.Model(cfg); new = models.Model(cfg)
+        for m in (ref, new):
+            m.unfreezing_index = start
+            m.freeze_all_layers()
+        for step in range(9):
+            ref.unfreeze_one_layer(); new.unfreeze_one_layer()
+            fr = [p.requires_grad for p in ref.parameters()]
+            fn = [p.requires_grad for p in new.parameters()]
+            assert fr == fn and ref.unfreezing_index == new.unfreezing_index, (utype, start, step)
+
+
+def test_asr_forward_matches_reference(reference):
+    cfg = make_config(pretraining_type=2)
+    torch.manual_seed(7)
+    ref = reference.PretrainedModel(cfg).cpu().eval()
+    torch.manual_seed(7)
+    new = models.PretrainedModel(cfg).cpu().eval()
+    x = 0.1 * torch.randn(2, 5120)
+    yp = torch.randint(-1, 42, (2, 8)); yw = torch.randint(-1, 10000, (2, 2))
+    out_r = ref(x, yp, yw); out_n = new(x, yp, yw)
+    for a, b in zip(out_r, out_n):
+        assert abs(a.item() - b.item()) < 1e-5
+    pr, wr = ref.compute_posteriors(x); pn, wn = new.compute_posteriors(x)
+    assert rel_err(pn, pr) < 2e-5 and rel_err(wn, wr) < 2e-5

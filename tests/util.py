@@ -22,3 +22,18 @@ def load_test_wav():
 def rel_err(a, b):
     a = torch.as_tensor(a).double(); b = torch.as_tensor(b).double()
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def make_config(name="no_unfreezing", pretraining_type=0, **over):
+    """Config for a random-init model (no checkpoint on disk): the shipped cfg with
+    pretraining_type overridden and the FSC slot table filled in."""
+    import importlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfgmod = importlib.import_module("end-to-end-slu_b200.config")
+    cfg = cfgmod.read_config(os.path.join(root, "configs", name + ".cfg"))
+    cfg.pretraining_type = pretraining_type
+    cfg.Sy_intent, cfg.values_per_slot = cfgmod.fsc_intent_table()
+    cfg.num_phonemes = 42
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return cfg
