@@ -19,7 +19,10 @@ SIGNATURES = {
     "slu_sincconv_bwd_simt": [_P, _P, _P, _I, _I, _P, _P],
     "slu_gru_fwd_simt": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_gru_bwd_simt": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "slu_gru_fwd_tc": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
     "slu_tc_selftest": [_P, _P, _P, _I, _I, _P],
+    "slu_tc_selftest_ts": [_P, _P, _P, _I, _I, _P],
 }
 
 
@@ -49,7 +52,33 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+stats = {"calls": 0}        # number of C-ABI kernel launches issued by this process
+_prof = None                # name -> [(start_event, end_event)] while profiling
+
+
 def call(name, *args):
+    stats["calls"] += 1
+    if _prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     err = getattr(load(), name)(*args)
     if err != 0:
         raise RuntimeError("slu_b200: %s failed with cudaError %d" % (name, err))
+    if _prof is not None:
+        e1.record()
+        _prof.setdefault(name, []).append((e0, e1))
+
+
+def profile_begin():
+    """Start recording CUDA events around every launch (on the current stream)."""
+    global _prof
+    _prof = {}
+
+
+def profile_end():
+    """-> {entry point: [device ms per launch]}"""
+    global _prof
+    torch.cuda.synchronize()
+    out = {k: [a.elapsed_time(b) for a, b in v] for k, v in _prof.items()}
+    _prof = None
+    return out

@@ -32,7 +32,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  // bounded spin: a protocol bug traps (launch failure) instead of hanging the GPU
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
 }
 
 // ---- fences ---------------------------------------------------------------------------------------
@@ -70,6 +74,22 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+// A operand from TMEM (weights-stationary): lane = M row, 32-bit column c holds elements k=2c (low half), 2c+1.
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ---- registers -> TMEM ------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- TMEM -> registers (warp w may only touch lanes 32*(w%4) .. +31) -------------------------------
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -116,6 +136,31 @@ __device__ __forceinline__ void mma_split3(uint32_t d_tmem, uint32_t a_hi, uint3
     mma_bf16(d_tmem, ah, bl, idesc, 1u);
     mma_bf16(d_tmem, al, bh, idesc, 1u);
   }
+}
+
+// Same with the A operand resident in TMEM: a_hi_t / a_lo_t are TMEM addresses of [128 x 16*k16] bf16 (packed pairs,
+// 8 columns per K-step).  B tile has byte strides b_lbo (between 8-element k-chunks) / 128 (between 8-row groups).
+__device__ __forceinline__ void mma_split3_ts(uint32_t d_tmem, uint32_t a_hi_t, uint32_t a_lo_t, uint32_t b_hi, uint32_t b_lo,
+                                              uint32_t b_lbo, int k16, uint32_t idesc, bool accumulate_first) {
+  uint32_t acc = accumulate_first ? 1u : 0u;
+  for (int kk = 0; kk < k16; ++kk) {
+    const uint64_t bh = smem_desc(b_hi + kk * 2 * b_lbo, b_lbo, 128), bl = smem_desc(b_lo + kk * 2 * b_lbo, b_lbo, 128);
+    mma_bf16_ts(d_tmem, a_hi_t + kk * 8, bh, idesc, acc); acc = 1u;
+    mma_bf16_ts(d_tmem, a_hi_t + kk * 8, bl, idesc, 1u);
+    mma_bf16_ts(d_tmem, a_lo_t + kk * 8, bh, idesc, 1u);
+  }
+}
+
+// Store one M-row (this thread's TMEM lane) of fp32 values as packed bf16 hi / lo A-operands: `n` values (multiple of 16).
+__device__ __forceinline__ void tmem_store_row_split(uint32_t t_hi, uint32_t t_lo, const float* row, int n) {
+  for (int c0 = 0; c0 < n; c0 += 16) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split2(row[c0 + 2 * i], row[c0 + 2 * i + 1], hi[i], lo[i]);
+    tmem_st8(t_hi + c0 / 2, hi);
+    tmem_st8(t_lo + c0 / 2, lo);
+  }
+  tmem_st_wait();
 }
 
 }  // namespace tc05

@@ -3,11 +3,16 @@
 Layouts are the library's own (time-major NLC everywhere):
   waveform [B,T] -> sinc frames [B,L1,80] -> conv blocks [B,L1,60] -> GRU stacks [B,T_l,256].
 """
+import os
+
 import torch
 
 from . import _lib
 
 H = 128
+# Which persistent-GRU kernel family runs the recurrence: "tc" = tcgen05 (weights stationary in TMEM),
+# "simt" = fp32 CUDA-core variant.  Both are sm_100a kernels of this library with identical contracts.
+GRU_IMPL = os.environ.get("SLU_GRU_IMPL", "simt")
 
 
 def _f32(t):
@@ -91,7 +96,7 @@ class BiGRU(torch.autograd.Function):
         y_out = torch.empty(B, T2, 256, device=dev, dtype=torch.float32) if (ds != 1 or mask is not None) else y_full
         need = any(ctx.needs_input_grad[:9])
         stash = torch.empty(B, T, 1024, device=dev, dtype=torch.float32) if need else None
-        _lib.call("slu_gru_fwd_simt", _lib.ptr(gx), _lib.ptr(w_hh_cat), _lib.ptr(b_hh_cat), _lib.ptr(mask), B, T, ds,
+        _lib.call("slu_gru_fwd_" + GRU_IMPL, _lib.ptr(gx), _lib.ptr(w_hh_cat), _lib.ptr(b_hh_cat), _lib.ptr(mask), B, T, ds,
                   _lib.ptr(y_full), _lib.ptr(y_out), _lib.ptr(stash), _lib.stream())
         if need:
             ctx.save_for_backward(x, w_ih_cat, w_hh_cat, y_full, stash, mask)
@@ -107,7 +112,7 @@ class BiGRU(torch.autograd.Function):
         gy = _f32(gy)
         dgx = torch.empty(B, T, 768, device=dev, dtype=torch.float32)
         dhn = torch.empty(B, T, 256, device=dev, dtype=torch.float32)
-        _lib.call("slu_gru_bwd_simt", _lib.ptr(gy), _lib.ptr(mask), _lib.ptr(y_full), _lib.ptr(stash), _lib.ptr(w_hh_cat),
+        _lib.call("slu_gru_bwd_" + GRU_IMPL, _lib.ptr(gy), _lib.ptr(mask), _lib.ptr(y_full), _lib.ptr(stash), _lib.ptr(w_hh_cat),
                   B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), _lib.stream())
         ni = ctx.needs_input_grad
         dgx2 = dgx.view(B * T, 768)

@@ -50,8 +50,17 @@ int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float* b_hh, cons
 int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
                      const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, void* stream);
 
+/* Same contracts as slu_gru_fwd_simt / slu_gru_bwd_simt, executed on tcgen05 tensor cores: W_hh (bf16 hi+lo) stationary
+ * in tensor memory, h / dG as the shared-memory B operand, 3-pass bf16 split with fp32 accumulation in TMEM. */
+int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T, int ds,
+                   float* y_full, float* y_out, float* stash, void* stream);
+int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
+                   const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, void* stream);
+
 /* tcgen05 self-test: C[128][N] = A[128][K] . B[N][K]^T (3-pass bf16 split, fp32 accumulate in TMEM). */
 int slu_tc_selftest(const float* A, const float* B, float* C, int N, int K, void* stream);
+/* Same, A operand resident in tensor memory (K <= 128), B tile with a padded leading-byte-offset. */
+int slu_tc_selftest_ts(const float* A, const float* B, float* C, int N, int K, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,18 +26,32 @@ def dev(t):
     return t.cuda().contiguous()
 
 
-@pytest.mark.parametrize("N,K", [(16, 16), (16, 128), (32, 64), (80, 80), (128, 256), (240, 64), (256, 128)])
+@pytest.mark.parametrize("N,K", [(16, 16), (16, 128), (32, 64), (80, 80), (128, 128), (240, 64), (256, 128)])
 def test_tcgen05_selftest(pkg, N, K):
     rs = np.random.RandomState(N * 1000 + K)
     A = rs.standard_normal((128, K)).astype(np.float32)
     Bm = rs.standard_normal((N, K)).astype(np.float32)
     C = torch.empty(128, N, device="cuda")
-    pkg._lib.call("slu_tc_selftest", dev(torch.from_numpy(A)).data_ptr(), dev(torch.from_numpy(Bm)).data_ptr(),
-                  C.data_ptr(), N, K, pkg._lib.stream())
+    Ad, Bd = dev(torch.from_numpy(A)), dev(torch.from_numpy(Bm))        # keep alive: raw pointers are passed
+    pkg._lib.call("slu_tc_selftest", Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), N, K, pkg._lib.stream())
     torch.cuda.synchronize()
     ref = A.astype(np.float64) @ Bm.astype(np.float64).T
     err = np.abs(C.cpu().numpy() - ref).max() / np.abs(ref).max()
     assert err < 2e-5, err          # 3-pass bf16 split ~ 2^-16; plain bf16 would be ~4e-3
+
+
+@pytest.mark.parametrize("N,K", [(16, 16), (16, 128), (32, 64), (64, 128), (256, 32)])
+def test_tcgen05_selftest_a_in_tmem(pkg, N, K):
+    rs = np.random.RandomState(N * 1000 + K + 1)
+    A = rs.standard_normal((128, K)).astype(np.float32)
+    Bm = rs.standard_normal((N, K)).astype(np.float32)
+    C = torch.empty(128, N, device="cuda")
+    Ad, Bd = dev(torch.from_numpy(A)), dev(torch.from_numpy(Bm))        # keep alive: raw pointers are passed
+    pkg._lib.call("slu_tc_selftest_ts", Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), N, K, pkg._lib.stream())
+    torch.cuda.synchronize()
+    ref = A.astype(np.float64) @ Bm.astype(np.float64).T
+    err = np.abs(C.cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err < 2e-5, err
 
 
 def test_sinc_filters_fwd_bwd(pkg):
@@ -55,9 +69,11 @@ def test_sinc_filters_fwd_bwd(pkg):
         dW = torch.from_numpy(rs.standard_normal((80, 401)).astype(np.float32))
         W_ref.backward(dW)
         d_b1 = torch.empty(80, device="cuda", dtype=torch.float64); d_band = torch.empty_like(d_b1)
-        pkg._lib.call("slu_sinc_filters_bwd", dev(b1.detach()).data_ptr(), dev(band.detach()).data_ptr(),
-                      dev(dW).data_ptr(), d_b1.data_ptr(), d_band.data_ptr(), pkg._lib.stream())
-        assert rel_err(d_b1.cpu(), b1.grad) < 1e-3 and rel_err(d_band.cpu(), band.grad) < 1e-3
+        b1d, bandd, dWd = dev(b1.detach()), dev(band.detach()), dev(dW)    # keep alive: raw pointers are passed
+        pkg._lib.call("slu_sinc_filters_bwd", b1d.data_ptr(), bandd.data_ptr(), dWd.data_ptr(), d_b1.data_ptr(),
+                      d_band.data_ptr(), pkg._lib.stream())
+        e1, e2 = rel_err(d_b1.cpu(), b1.grad), rel_err(d_band.cpu(), band.grad)
+        assert e1 < 1e-3 and e2 < 1e-3, (src, e1, e2)
 
 
 @pytest.mark.parametrize("B,T", [(1, 57585), (3, 8000), (2, 1234), (2, 81), (1, 1), (5, 64000)])
@@ -76,12 +92,16 @@ def test_sinc_frontend_fwd_bwd(pkg, B, T):
     ref.backward(gy)
     out.backward(gy.cuda())
     assert b1g.grad.dtype == torch.float64
-    assert rel_err(b1g.grad.cpu(), b1.grad) < GRAD_TOL and rel_err(bandg.grad.cpu(), band.grad) < GRAD_TOL
+    scale = max(b1.grad.abs().max().item(), band.grad.abs().max().item())
+    for got, ref_g in ((b1g.grad.cpu(), b1.grad), (bandg.grad.cpu(), band.grad)):
+        assert (got - ref_g).abs().max().item() < GRAD_TOL * scale + 1e-4, ((got - ref_g).abs().max().item(), scale)
 
 
-@pytest.mark.parametrize("B,T,I,ds,use_mask", [(3, 7, 60, 2, False), (4, 24, 256, 2, True), (5, 23, 256, 1, True),
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("B,T,I,ds,use_mask", [(3, 7, 60, 2, False), (17, 9, 256, 2, True), (40, 5, 60, 1, False), (4, 24, 256, 2, True), (5, 23, 256, 1, True),
                                                (1, 1, 256, 2, False), (9, 50, 60, 2, False), (2, 360, 60, 2, False)])
-def test_bigru_fwd_bwd(pkg, B, T, I, ds, use_mask):
+def test_bigru_fwd_bwd(pkg, monkeypatch, impl, B, T, I, ds, use_mask):
+    monkeypatch.setattr(pkg.ops, "GRU_IMPL", impl)
     rs = np.random.RandomState(B * 100 + T)
     gru = torch.nn.GRU(I, 128, batch_first=True, bidirectional=True)
     with torch.no_grad():
