@@ -11,6 +11,8 @@ _lib = None
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
+_L = ctypes.c_long
+_F = ctypes.c_float
 SIGNATURES = {
     # name: argtypes (all return int = cudaError_t, 0 on success)
     "slu_sinc_filters_fwd": [_P, _P, _P, _P],
@@ -21,6 +23,7 @@ SIGNATURES = {
     "slu_gru_bwd_simt": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
     "slu_gru_fwd_tc": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "slu_gemm_tc": [_P, _L, _L, _P, _L, _L, _L, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "slu_tc_selftest": [_P, _P, _P, _I, _I, _P],
     "slu_tc_selftest_ts": [_P, _P, _P, _I, _I, _P],
 }

@@ -51,14 +51,14 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   __shared__ __align__(128) uint8_t h_tile[2 * 16 * LBO];   // [hi | lo] x 16 k-chunks x (NB rows x 16 B + pad)
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int d = blockIdx.y, b0 = blockIdx.x * NB;
   const int j = (warp & 3) * 32 + lane;              // hidden unit == TMEM lane
   const int c0 = (warp >> 2) * NC;                   // first batch column of this thread
   uint8_t* h_hi = h_tile;
   uint8_t* h_lo = h_tile + 16 * LBO;
 
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 3); fence_mbar_init(); }   // 3 gate-issuer warps commit per step
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_base, 512);
   fence_before_sync();
@@ -89,7 +89,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   load_step(d ? T - 1 : 0, gxr, gxz, gxn, mk);
   const uint32_t idesc = idesc_bf16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
-  const uint32_t hs_hi = smem_u32(h_hi), hs_lo = smem_u32(h_lo);
+  const uint64_t bdesc_hi = smem_desc(smem_u32(h_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(h_lo), LBO, 128);
   // byte offset of element (k = j) inside a k-chunk-major row b: (j/8)*LBO + b*16 + (j%8)*2
   const uint32_t h_off = (uint32_t)(j >> 3) * LBO + (uint32_t)(j & 7) * 2;
 
@@ -147,12 +147,20 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       fence_async_smem();          // h tile (generic-proxy stores) -> visible to the tensor core (async proxy)
       fence_before_sync();         // order this thread's tcgen05.ld before the barrier
       __syncthreads();
-      if (tid == 0) {
-        fence_after_sync();
-#pragma unroll 1
-        for (int g = 0; g < 3; ++g)
-          mma_split3_ts(tmem + ACC_COL + g * NB, tmem + g * 64, tmem + 192 + g * 64, hs_hi, hs_lo, LBO, 8, idesc, false);
-        mma_commit(&bar);
+      if (warp < 3) {                 // warps 0,1,2 (three different SM sub-partitions) issue gate r, z, n concurrently
+        if (elect_one()) {
+          fence_after_sync();
+          const uint32_t dacc = tmem + ACC_COL + warp * NB, a_hi = tmem + warp * 64, a_lo = a_hi + 192;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t bh = desc_advance(bdesc_hi, kk * 2 * LBO), bl = desc_advance(bdesc_lo, kk * 2 * LBO);
+            mma_bf16_ts(dacc, a_hi + kk * 8, bh, idesc, kk > 0 ? 1u : 0u);
+            mma_bf16_ts(dacc, a_hi + kk * 8, bl, idesc, 1u);
+            mma_bf16_ts(dacc, a_lo + kk * 8, bh, idesc, 1u);
+          }
+          mma_commit(&bar);
+        }
+        __syncwarp();
       }
     }
   }
@@ -173,13 +181,13 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   __shared__ __align__(128) uint8_t g_tile[2 * 48 * LBO];   // [hi | lo] x 48 k-chunks (384 gate rows)
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int d = blockIdx.y, b0 = blockIdx.x * NB;
   const int j = (warp & 3) * 32 + lane;
   const int c0 = (warp >> 2) * NC;
   uint8_t* g_hi = g_tile;
   uint8_t* g_lo = g_tile + 48 * LBO;
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 3); fence_mbar_init(); }   // the K=384 reduction is issued as 3 chunks by 3 warps
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_base, 512);
   fence_before_sync();
@@ -217,7 +225,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   load_step(d ? 0 : T - 1, cur);
   const uint32_t idesc = idesc_bf16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
-  const uint32_t gs_hi = smem_u32(g_hi), gs_lo = smem_u32(g_lo);
+  const uint64_t bdesc_hi = smem_desc(smem_u32(g_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(g_lo), LBO, 128);
   const uint32_t g_off = (uint32_t)(j >> 3) * LBO + (uint32_t)(j & 7) * 2;     // + gate*16*LBO + b*16
   float dh_direct[NC];
 #pragma unroll
@@ -233,8 +241,12 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
     } else {
       mbar_wait(&bar, (uint32_t)((s - 1) & 1));
       fence_after_sync();
-      if (NC == 8) tmem_ld8(acc_addr, rec); else tmem_ld16(acc_addr, rec);
+      float r1[NC], r2[NC];                 // three partial accumulators (one per gate-row chunk / issuing warp)
+      if (NC == 8) { tmem_ld8(acc_addr, rec); tmem_ld8(acc_addr + NB, r1); tmem_ld8(acc_addr + 2 * NB, r2); }
+      else { tmem_ld16(acc_addr, rec); tmem_ld16(acc_addr + NB, r1); tmem_ld16(acc_addr + 2 * NB, r2); }
       tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < NC; ++c) rec[c] += r1[c] + r2[c];
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -267,10 +279,21 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
-        fence_after_sync();
-        mma_split3_ts(tmem + ACC_COL, tmem, tmem + 192, gs_hi, gs_lo, LBO, 24, idesc, false);
-        mma_commit(&bar);
+      if (warp < 3) {                 // warp g reduces gate-row chunk g (K steps 8g..8g+7) into its own accumulator
+        if (elect_one()) {
+          fence_after_sync();
+          const uint32_t dacc = tmem + ACC_COL + warp * NB, a_hi = tmem + warp * 64, a_lo = a_hi + 192;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t koff = (uint32_t)(warp * 8 + kk) * 2 * LBO;
+            const uint64_t bh = desc_advance(bdesc_hi, koff), bl = desc_advance(bdesc_lo, koff);
+            mma_bf16_ts(dacc, a_hi + kk * 8, bh, idesc, kk > 0 ? 1u : 0u);
+            mma_bf16_ts(dacc, a_hi + kk * 8, bl, idesc, 1u);
+            mma_bf16_ts(dacc, a_lo + kk * 8, bh, idesc, 1u);
+          }
+          mma_commit(&bar);
+        }
+        __syncwarp();
       }
     }
   }

@@ -17,6 +17,16 @@ namespace tc05 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- warp-uniform helpers ------------------------------------------------------------------------
+// Warp index as a value the compiler knows to be warp-uniform (so role branches are not "divergent").
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// One lane of a fully converged warp (elect.sync); tcgen05.mma / commit are issued under this predicate.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\n@px mov.s32 %0, 1;\n}" : "+r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -162,5 +172,8 @@ __device__ __forceinline__ void tmem_store_row_split(uint32_t t_hi, uint32_t t_l
   }
   tmem_st_wait();
 }
+
+// Descriptor arithmetic for unrolled issue loops: advance the start-address field (16-byte units) of a descriptor.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 
 }  // namespace tc05

@@ -96,7 +96,7 @@ def phoneme_features(pm, x):
     _require(plan.sinc is not None, "use_sincnet must be True")
     out = ops.SincFrontend.apply(x, plan.sinc.filt_b1, plan.sinc.filt_band)      # [B, L1, 80] (LeakyReLU is identity on >=0)
     for conv, slope in plan.convs:
-        out = ops.conv_block_nlc(out, conv.weight, conv.bias, slope)
+        out = ops.conv_block(out, conv.weight, conv.bias, slope)
     return _run_rnns(out, plan.phone, pm.training)
 
 

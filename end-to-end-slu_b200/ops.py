@@ -13,10 +13,108 @@ H = 128
 # Which persistent-GRU kernel family runs the recurrence: "tc" = tcgen05 (weights stationary in TMEM),
 # "simt" = fp32 CUDA-core variant.  Both are sm_100a kernels of this library with identical contracts.
 GRU_IMPL = os.environ.get("SLU_GRU_IMPL", "simt")
+# Dense contractions (x-projection, CNN tail, weight/input gradients): "tc" = this library's tcgen05 tap-GEMM,
+# "lib" = cuBLAS fp32 through torch (plain library GEMMs).
+GEMM_IMPL = os.environ.get("SLU_GEMM_IMPL", "lib")
 
 
 def _f32(t):
     return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def _eptr(t, off=0):
+    assert t.is_cuda and t.dtype == torch.float32
+    return t.data_ptr() + 4 * off
+
+
+def gemm_tc(A, a_off, a_sm, a_sk, Bm, b_off, b_sn, b_sk, M, N, K, out, c_off=0, ldc=None, bias=None, taps=1, tap_pad=0,
+            T=0, a_kshift=0, b_kshift=0, b_stap=0, split_k=1, act=0, slope=0.0):
+    """Raw strided call of slu_gemm_tc (see include/slu_b200.h).  `out` must be zero-filled when split_k > 1."""
+    _lib.call("slu_gemm_tc", _eptr(A, a_off), a_sm, a_sk, _eptr(Bm, b_off), b_sn, b_sk, b_stap,
+              None if bias is None else _eptr(bias), _eptr(out, c_off), N if ldc is None else ldc, M, N, K, taps, tap_pad, T,
+              a_kshift, b_kshift, split_k, act, float(slope), _lib.stream())
+    return out
+
+
+def _split_k(M, N, K, taps=1):
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
+    kb = taps * ((K + 31) // 32)
+    return max(1, min(kb, 296 // max(1, tiles)))
+
+
+def linear_nt(x2, w, bias=None):
+    """x2 [M,K] @ w[N,K]^T + bias -> [M,N]."""
+    M, K = x2.shape
+    N = w.shape[0]
+    if GEMM_IMPL != "tc":
+        return torch.addmm(bias, x2, w.t()) if bias is not None else x2 @ w.t()
+    out = torch.empty(M, N, device=x2.device, dtype=torch.float32)
+    return gemm_tc(x2, 0, K, 1, w, 0, K, 1, M, N, K, out, bias=bias)
+
+
+def matmul_nn(a2, w):
+    """a2 [M,K] @ w[K,N] -> [M,N]  (w row-major, i.e. the 'transposed weight' operand of an input gradient)."""
+    M, K = a2.shape
+    N = w.shape[1]
+    if GEMM_IMPL != "tc":
+        return a2 @ w
+    out = torch.empty(M, N, device=a2.device, dtype=torch.float32)
+    return gemm_tc(a2, 0, K, 1, w, 0, 1, N, M, N, K, out)
+
+
+def matmul_tn(g2, x2):
+    """g2[R,M]^T @ x2[R,N] -> [M,N]: weight gradient, reduction over the R frames (split-K + fp32 atomics)."""
+    R, M = g2.shape
+    N = x2.shape[1]
+    if GEMM_IMPL != "tc":
+        return g2.t() @ x2
+    out = torch.zeros(M, N, device=g2.device, dtype=torch.float32)
+    return gemm_tc(g2, 0, 1, M, x2, 0, 1, N, M, N, R, out, split_k=_split_k(M, N, R))
+
+
+class ConvBlock(torch.autograd.Function):
+    """Conv1d(k odd, pad k//2) + bias + LeakyReLU on NLC activations as an accumulating tap-GEMM (models.py:200-220)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, slope):
+        x = _f32(x)
+        B, T, Cin = x.shape
+        Cout, _, k = weight.shape
+        w = weight.detach().contiguous()
+        out = torch.empty(B, T, Cout, device=x.device, dtype=torch.float32)
+        gemm_tc(x, 0, Cin, 1, w, 0, Cin * k, k, B * T, Cout, Cin, out, bias=bias.detach(), taps=k, tap_pad=k // 2, T=T,
+                b_stap=1, act=1, slope=slope)
+        ctx.save_for_backward(x, w, out)
+        ctx.slope = slope
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, out = ctx.saved_tensors
+        B, T, Cin = x.shape
+        Cout, _, k = w.shape
+        dpre = torch.where(out > 0, gy, gy * ctx.slope).contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, T, Cin, device=x.device, dtype=torch.float32)
+            # dX[b,t,ci] = sum_d sum_co dpre[b,t-(d-k//2),co] W[co,ci,d]; tap' = k-1-d walks the kernel backwards
+            gemm_tc(dpre, 0, Cout, 1, w, k - 1, k, Cin * k, B * T, Cin, Cout, dx, taps=k, tap_pad=k // 2, T=T, b_stap=-1)
+        if ctx.needs_input_grad[1]:
+            dwt = torch.zeros(k, Cout, Cin, device=x.device, dtype=torch.float32)
+            sk = _split_k(Cout, Cin, B * T)
+            for d in range(k):
+                gemm_tc(dpre, 0, 1, Cout, x, 0, 1, Cin, Cout, Cin, B * T, dwt, c_off=d * Cout * Cin, T=T, b_kshift=d - k // 2,
+                        split_k=sk)
+            dw = dwt.permute(1, 2, 0).contiguous()
+        if ctx.needs_input_grad[2]:
+            db = dpre.sum((0, 1))
+        return dx, dw, db, None
+
+
+def conv_block(x, weight, bias, slope):
+    if GEMM_IMPL == "tc":
+        return ConvBlock.apply(x, weight, bias, slope)
+    return conv_block_nlc(x, weight, bias, slope)
 
 
 class SincFrontend(torch.autograd.Function):
@@ -90,7 +188,7 @@ class BiGRU(torch.autograd.Function):
         b_ih_cat = torch.cat([b_ih, b_ih_r], 0).detach()
         w_hh_cat = torch.stack([w_hh, w_hh_r], 0).detach().contiguous()       # [2,384,128]
         b_hh_cat = torch.stack([b_hh, b_hh_r], 0).detach().contiguous()
-        gx = torch.addmm(b_ih_cat, x.view(B * T, I), w_ih_cat.t())            # x-projection, both directions
+        gx = linear_nt(x.view(B * T, I), w_ih_cat.contiguous(), b_ih_cat)       # x-projection, both directions
         T2 = (T + ds - 1) // ds
         y_full = torch.empty(B, T, 256, device=dev, dtype=torch.float32)
         y_out = torch.empty(B, T2, 256, device=dev, dtype=torch.float32) if (ds != 1 or mask is not None) else y_full
@@ -116,19 +214,33 @@ class BiGRU(torch.autograd.Function):
                   B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), _lib.stream())
         ni = ctx.needs_input_grad
         dgx2 = dgx.view(B * T, 768)
-        dx = (dgx2 @ w_ih_cat).view(B, T, I) if ni[0] else None
+        dx = matmul_nn(dgx2, w_ih_cat.contiguous()).view(B, T, I) if ni[0] else None
         grads = [None] * 8
         if any(ni[1:9]):
             x2 = x.view(B * T, I)
-            dw_ih = dgx2.t() @ x2                                               # [768, I]
+            dw_ih = matmul_tn(dgx2, x2)                                         # [768, I]
             db_ih = dgx2.sum(0)
+            db_hn = dhn.view(B * T, 256).sum(0)
+            if GEMM_IMPL == "tc":
+                R = B * T
+                dw_hh_cat = torch.zeros(2, 384, H, device=dev, dtype=torch.float32)
+                sk = _split_k(256, H, R)
+                for d in range(2):      # dW_hh[d] = [dr,dz | dhn]^T . h_{t-1}  (h_{t+1} for the reverse direction)
+                    sh = 1 if d else -1
+                    gemm_tc(dgx, d * 384, 1, 768, y_full, d * H, 1, 256, 256, H, R, dw_hh_cat, c_off=d * 384 * H, T=T,
+                            b_kshift=sh, split_k=sk)
+                    gemm_tc(dhn, d * H, 1, 256, y_full, d * H, 1, 256, H, H, R, dw_hh_cat, c_off=(d * 384 + 256) * H, T=T,
+                            b_kshift=sh, split_k=sk)
             zero = torch.zeros(B, 1, H, device=dev, dtype=torch.float32)
             for d in range(2):
-                hd = y_full[:, :, d * H:(d + 1) * H]
-                hprev = torch.cat([zero, hd[:, :-1]], 1) if d == 0 else torch.cat([hd[:, 1:], zero], 1)
-                gd = torch.cat([dgx[:, :, d * 384:d * 384 + 256], dhn[:, :, d * H:(d + 1) * H]], 2).reshape(B * T, 384)
-                dw_hh = gd.t() @ hprev.reshape(B * T, H)
-                db_hh = gd.sum(0)
+                if GEMM_IMPL == "tc":
+                    dw_hh = dw_hh_cat[d]
+                else:
+                    hd = y_full[:, :, d * H:(d + 1) * H]
+                    hprev = torch.cat([zero, hd[:, :-1]], 1) if d == 0 else torch.cat([hd[:, 1:], zero], 1)
+                    gd = torch.cat([dgx[:, :, d * 384:d * 384 + 256], dhn[:, :, d * H:(d + 1) * H]], 2).reshape(B * T, 384)
+                    dw_hh = gd.t() @ hprev.reshape(B * T, H)
+                db_hh = torch.cat([db_ih[d * 384:d * 384 + 256], db_hn[d * H:(d + 1) * H]])
                 grads[4 * d + 0] = dw_ih[d * 384:(d + 1) * 384]
                 grads[4 * d + 1] = dw_hh
                 grads[4 * d + 2] = db_ih[d * 384:(d + 1) * 384]

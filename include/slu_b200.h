@@ -57,6 +57,17 @@ int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const 
 int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
                    const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, void* stream);
 
+/* Dense "tap-GEMM" on tcgen05 (fp32 in/out, 3-pass bf16 split, fp32 accumulate in TMEM) -- replaces the cuBLAS / cuDNN
+ * calls behind nn.GRU's input projection (models.py:232/262/686), nn.Conv1d (models.py:200) and their autograd:
+ *   C[m][n] (+)= sum_tap sum_k A(m,tap,k) * B(n,tap,k) (+ bias[n]) (LeakyReLU if act==1)
+ *   A(m,tap,k) = A[(m + tap - tap_pad)*a_sm + k*a_sk]   (a_sk==1; rows leaving their T-frame utterance read as 0), or,
+ *                when a_sk != 1 (reduction over frames): A[m*a_sm + (k + a_kshift)*a_sk], 0 if frame k%T + a_kshift leaves [0,T)
+ *   B(n,tap,k) = B[n*b_sn + k*b_sk + tap*b_stap]        (b_sk != 1: frame-shifted by b_kshift like A)
+ * split_k > 1 accumulates with fp32 atomics into a caller-zeroed C. */
+int slu_gemm_tc(const float* A, long a_sm, long a_sk, const float* B, long b_sn, long b_sk, long b_stap, const float* bias,
+                float* C, long ldc, int M, int N, int K, int taps, int tap_pad, int T, int a_kshift, int b_kshift,
+                int split_k, int act, float slope, void* stream);
+
 /* tcgen05 self-test: C[128][N] = A[128][K] . B[N][K]^T (3-pass bf16 split, fp32 accumulate in TMEM). */
 int slu_tc_selftest(const float* A, const float* B, float* C, int N, int K, void* stream);
 /* Same, A operand resident in tensor memory (K <= 128), B tile with a padded leading-byte-offset. */

@@ -97,11 +97,13 @@ def test_sinc_frontend_fwd_bwd(pkg, B, T):
         assert (got - ref_g).abs().max().item() < GRAD_TOL * scale + 1e-4, ((got - ref_g).abs().max().item(), scale)
 
 
+@pytest.mark.parametrize("gemm", ["lib", "tc"])
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("B,T,I,ds,use_mask", [(3, 7, 60, 2, False), (17, 9, 256, 2, True), (40, 5, 60, 1, False), (4, 24, 256, 2, True), (5, 23, 256, 1, True),
                                                (1, 1, 256, 2, False), (9, 50, 60, 2, False), (2, 360, 60, 2, False)])
-def test_bigru_fwd_bwd(pkg, monkeypatch, impl, B, T, I, ds, use_mask):
+def test_bigru_fwd_bwd(pkg, monkeypatch, gemm, impl, B, T, I, ds, use_mask):
     monkeypatch.setattr(pkg.ops, "GRU_IMPL", impl)
+    monkeypatch.setattr(pkg.ops, "GEMM_IMPL", gemm)
     rs = np.random.RandomState(B * 100 + T)
     gru = torch.nn.GRU(I, 128, batch_first=True, bidirectional=True)
     with torch.no_grad():
@@ -126,6 +128,48 @@ def test_bigru_fwd_bwd(pkg, monkeypatch, impl, B, T, I, ds, use_mask):
     assert rel_err(xc.grad.cpu(), gx_ref) < GRAD_TOL
     for k, v in gru_c.named_parameters():
         assert rel_err(v.grad.cpu(), g_ref[k]) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("M,K,N", [(300, 60, 768), (257, 256, 768), (128, 256, 24), (1000, 768, 60), (130, 768, 256)])
+def test_gemm_tc_linear_and_input_grad(pkg, monkeypatch, M, K, N):
+    monkeypatch.setattr(pkg.ops, "GEMM_IMPL", "tc")
+    rs = np.random.RandomState(M + K + N)
+    x = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).cuda()
+    w = torch.from_numpy(rs.standard_normal((N, K)).astype(np.float32)).cuda()
+    b = torch.from_numpy(rs.standard_normal(N).astype(np.float32)).cuda()
+    ref = x.double() @ w.double().t() + b.double()
+    assert rel_err(pkg.ops.linear_nt(x, w, b).cpu(), ref.cpu()) < 2e-5
+    wk = torch.from_numpy(rs.standard_normal((K, N)).astype(np.float32)).cuda()
+    assert rel_err(pkg.ops.matmul_nn(x, wk).cpu(), (x.double() @ wk.double()).cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("R,M,N", [(1000, 768, 60), (5000, 768, 256), (333, 60, 80), (4096, 256, 128)])
+def test_gemm_tc_weight_grad_splitk(pkg, monkeypatch, R, M, N):
+    monkeypatch.setattr(pkg.ops, "GEMM_IMPL", "tc")
+    rs = np.random.RandomState(R + M + N)
+    g = torch.from_numpy(rs.standard_normal((R, M)).astype(np.float32)).cuda()
+    x = torch.from_numpy(rs.standard_normal((R, N)).astype(np.float32)).cuda()
+    ref = g.double().t() @ x.double()
+    assert rel_err(pkg.ops.matmul_tn(g, x).cpu(), ref.cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("B,T,Cin,Cout", [(3, 37, 80, 60), (2, 1, 60, 60), (5, 400, 60, 60), (1, 130, 80, 60)])
+def test_conv_block_tc_fwd_bwd(pkg, monkeypatch, B, T, Cin, Cout):
+    monkeypatch.setattr(pkg.ops, "GEMM_IMPL", "tc")
+    rs = np.random.RandomState(B * 1000 + T)
+    x = torch.from_numpy(rs.standard_normal((B, Cin, T)).astype(np.float32)).requires_grad_(True)
+    w = torch.from_numpy(rs.uniform(-0.1, 0.1, (Cout, Cin, 5)).astype(np.float32)).requires_grad_(True)
+    b = torch.from_numpy(rs.uniform(-0.1, 0.1, Cout).astype(np.float32)).requires_grad_(True)
+    ref = R.conv_block(x, w, b).transpose(1, 2)
+    gy = torch.from_numpy(rs.standard_normal(tuple(ref.shape)).astype(np.float32))
+    ref.backward(gy)
+    xc = x.detach().transpose(1, 2).contiguous().cuda().requires_grad_(True)
+    wc = w.detach().cuda().requires_grad_(True); bc = b.detach().cuda().requires_grad_(True)
+    out = pkg.ops.conv_block(xc, wc, bc, 0.2)
+    assert rel_err(out.detach().cpu(), ref.detach()) < FWD_TOL
+    out.backward(gy.cuda())
+    assert rel_err(xc.grad.cpu(), x.grad.transpose(1, 2)) < GRAD_TOL
+    assert rel_err(wc.grad.cpu(), w.grad) < GRAD_TOL and rel_err(bc.grad.cpu(), b.grad) < GRAD_TOL
 
 
 def test_conv_block_nlc(pkg):
