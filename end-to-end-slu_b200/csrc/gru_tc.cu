@@ -20,12 +20,6 @@ using namespace tc05;
 constexpr int TC_THREADS = 256;       // 8 warps: warp w owns TMEM lanes 32*(w%4).., batch columns (w/4)*NB/2 ..
 constexpr uint32_t ACC_COL = 384;     // accumulators start after the 384 weight columns
 
-__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
-__device__ __forceinline__ float fast_tanh(float v) {
-  // tanh(v) = 2*sigmoid(2v) - 1, ex2-based (rel err ~2^-22), saturates cleanly for |v| large
-  return __fdividef(2.0f, 1.0f + __expf(-2.0f * v)) - 1.0f;
-}
-
 // Load W rows (this thread's lane) into TMEM as split bf16 A-operands.  src: 3 blocks of [128][128] fp32 with
 // element (row j, k) at src[g*block_stride + j*row_stride + k*k_stride].
 __device__ __forceinline__ void load_weights_to_tmem(uint32_t tmem, uint32_t lane_base, const float* src, size_t block_stride,
@@ -40,6 +34,11 @@ __device__ __forceinline__ void load_weights_to_tmem(uint32_t tmem, uint32_t lan
     tmem_store_row_split(t_hi, t_hi + 192, row, 64);
   }
 }
+
+// ex2 / rcp based gate math (MUFU): rel. error ~2^-22, far inside the parity budget.
+__device__ __forceinline__ float ex2_approx(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float rcp_approx(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+constexpr float kLog2e = 1.4426950408889634f;
 
 template <int NB, bool STASH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -70,35 +69,42 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
 
   const float bhr = b_hh[d * SLU_G3 + j], bhz = b_hh[d * SLU_G3 + 128 + j], bhn = b_hh[d * SLU_G3 + 256 + j];
   const int T2 = (T + ds - 1) / ds;
-  float hprev[NC], pend[NC];
-  float gxr[NC], gxz[NC], gxn[NC], mk[NC];
+  // Per-column addressing: rows beyond B are clamped for loads (results unused) and predicated off for stores.
+  int row256[NC];                                    // (clamped b) * T * 256 ; gx = 3x, stash = 4x
+  uint32_t vmask = 0;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) { hprev[c] = 0.f; pend[c] = 0.f; gxr[c] = gxz[c] = gxn[c] = 0.f; mk[c] = 1.f; }
+  for (int c = 0; c < NC; ++c) {
+    const int b = b0 + c0 + c;
+    if (b < B) vmask |= 1u << c;
+    row256[c] = min(b, B - 1) * T * 256;
+  }
+  const float* gx_j = gx + d * SLU_G3 + j;
+  const float* mask_j = mask ? mask + d * SLU_H + j : nullptr;
+  float* yf_j = y_full + d * SLU_H + j;
+  float* yo_j = y_out + d * SLU_H + j;
+  float* st_j = STASH ? stash + d * 512 + j : nullptr;
 
-  auto load_step = [&](int t, float* r_, float* z_, float* n_, float* m_) {
+  float hprev[NC], pend[NC], gxr[NC], gxz[NC], gxn[NC], mk[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { hprev[c] = 0.f; pend[c] = 0.f; mk[c] = 1.f; }
+  {
+    const int t = d ? T - 1 : 0;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const int b = b0 + c0 + c;
-      if (b < B) {
-        const float* p = gx + ((size_t)b * T + t) * 768 + d * SLU_G3 + j;
-        r_[c] = __ldg(p); z_[c] = __ldg(p + 128); n_[c] = __ldg(p + 256);
-        m_[c] = mask ? __ldg(mask + ((size_t)b * T + t) * 256 + d * SLU_H + j) : 1.f;
-      }
+      const float* p = gx_j + (size_t)3 * row256[c] + (size_t)t * 768;
+      gxr[c] = __ldg(p); gxz[c] = __ldg(p + 128); gxn[c] = __ldg(p + 256);
+      if (mask_j) mk[c] = __ldg(mask_j + (size_t)row256[c] + (size_t)t * 256);
     }
-  };
-  load_step(d ? T - 1 : 0, gxr, gxz, gxn, mk);
+  }
   const uint32_t idesc = idesc_bf16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
   const uint64_t bdesc_hi = smem_desc(smem_u32(h_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(h_lo), LBO, 128);
   // byte offset of element (k = j) inside a k-chunk-major row b: (j/8)*LBO + b*16 + (j%8)*2
-  const uint32_t h_off = (uint32_t)(j >> 3) * LBO + (uint32_t)(j & 7) * 2;
+  uint8_t* h_hi_j = h_hi + (uint32_t)(j >> 3) * LBO + (uint32_t)(j & 7) * 2 + c0 * 16;
+  uint8_t* h_lo_j = h_hi_j + 16 * LBO;
 
   for (int s = 0; s < T; ++s) {
     const int t = d ? T - 1 - s : s;
-    float nr[NC], nz[NC], nn[NC], nm[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) { nr[c] = nz[c] = nn[c] = 0.f; nm[c] = 1.f; }
-    if (s + 1 < T) load_step(d ? t - 1 : t + 1, nr, nz, nn, nm);
     float ar[NC], az[NC], an[NC];
     if (s == 0) {
 #pragma unroll
@@ -110,44 +116,47 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       else { tmem_ld16(acc_addr, ar); tmem_ld16(acc_addr + NB, az); tmem_ld16(acc_addr + 2 * NB, an); }
       tmem_ld_wait();
     }
+    const bool tail = (ds == 2) && ((t & 1) == 0) && (t == T - 1);       // odd tail frame: divisor 1 (ceil_mode)
+    const bool first = (ds == 2) && !tail && ((t & 1) == (d ? 1 : 0));   // first visited frame of its pair
+    const size_t t256 = (size_t)t * 256, to256 = (size_t)(ds == 2 ? (t >> 1) : t) * 256;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const int b = b0 + c0 + c;
-      const float r = fast_sigmoid(gxr[c] + (ar[c] + bhr));
-      const float z = fast_sigmoid(gxz[c] + (az[c] + bhz));
+      // r, z share one reciprocal:  r = (1+v)/((1+u)(1+v)), z = (1+u)/((1+u)(1+v)),  u = e^-pr, v = e^-pz
+      const float pr = fminf(fmaxf(gxr[c] + (ar[c] + bhr), -40.f), 40.f);
+      const float pz = fminf(fmaxf(gxz[c] + (az[c] + bhz), -40.f), 40.f);
+      const float su = 1.f + ex2_approx(-kLog2e * pr), sv = 1.f + ex2_approx(-kLog2e * pz);
+      const float w = rcp_approx(su * sv);
+      const float r = w * sv, z = w * su;
       const float hn = an[c] + bhn;
-      const float n = fast_tanh(gxn[c] + r * hn);
-      const float hnew = (1.f - z) * n + z * hprev[c];
+      const float pn = fminf(fmaxf(gxn[c] + r * hn, -40.f), 40.f);
+      const float n = 2.f * rcp_approx(1.f + ex2_approx(-2.f * kLog2e * pn)) - 1.f;
+      const float hnew = n + z * (hprev[c] - n);
       hprev[c] = hnew;
-      // MMA operand copy of h_t: bf16 hi + lo
       const __nv_bfloat16 hh = __float2bfloat16_rn(hnew);
       const __nv_bfloat16 hl = __float2bfloat16_rn(hnew - __bfloat162float(hh));
-      *reinterpret_cast<__nv_bfloat16*>(h_hi + h_off + (c0 + c) * 16) = hh;
-      *reinterpret_cast<__nv_bfloat16*>(h_lo + h_off + (c0 + c) * 16) = hl;
-      if (b < B) {
-        const size_t bt = (size_t)b * T + t;
-        y_full[bt * 256 + d * SLU_H + j] = hnew;
+      *reinterpret_cast<__nv_bfloat16*>(h_hi_j + c * 16) = hh;
+      *reinterpret_cast<__nv_bfloat16*>(h_lo_j + c * 16) = hl;
+      if (vmask & (1u << c)) {
+        yf_j[(size_t)row256[c] + t256] = hnew;
         if (STASH) {
-          float* sp = stash + bt * 1024 + d * 512 + j;
+          float* sp = st_j + (size_t)4 * row256[c] + 4 * t256;
           sp[0] = r; sp[128] = z; sp[256] = n; sp[384] = hn;
         }
         const float val = hnew * mk[c];
-        if (ds == 1) {
-          y_out[bt * 256 + d * SLU_H + j] = val;
-        } else {
-          float* yo = y_out + ((size_t)b * T2 + (t >> 1)) * 256 + d * SLU_H + j;
-          if ((t & 1) == 0 && t == T - 1) *yo = val;
-          else if ((t & 1) == (d ? 1 : 0)) pend[c] = val;
+        if (ds == 1) yo_j[(size_t)row256[c] + t256] = val;
+        else {
+          float* yo = yo_j + (size_t)(b0 + c0 + c) * T2 * 256 + to256;
+          if (tail) *yo = val;
+          else if (first) pend[c] = val;
           else *yo = 0.5f * (pend[c] + val);
         }
       }
-      gxr[c] = nr[c]; gxz[c] = nz[c]; gxn[c] = nn[c]; mk[c] = nm[c];
     }
     if (s + 1 < T) {
       fence_async_smem();          // h tile (generic-proxy stores) -> visible to the tensor core (async proxy)
       fence_before_sync();         // order this thread's tcgen05.ld before the barrier
       __syncthreads();
-      if (warp < 3) {                 // warps 0,1,2 (three different SM sub-partitions) issue gate r, z, n concurrently
+      if (warp < 3) {              // warps 0,1,2 (three different SM sub-partitions) issue gate r, z, n concurrently
         if (elect_one()) {
           fence_after_sync();
           const uint32_t dacc = tmem + ACC_COL + warp * NB, a_hi = tmem + warp * 64, a_lo = a_hi + 192;
@@ -161,6 +170,14 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
           mma_commit(&bar);
         }
         __syncwarp();
+      }
+      // next step's inputs: issued now, they land while the tensor core works (consumed after the mbarrier wait)
+      const int tn = d ? t - 1 : t + 1;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float* p = gx_j + (size_t)3 * row256[c] + (size_t)tn * 768;
+        gxr[c] = __ldg(p); gxz[c] = __ldg(p + 128); gxn[c] = __ldg(p + 256);
+        if (mask_j) mk[c] = __ldg(mask_j + (size_t)row256[c] + (size_t)tn * 256);
       }
     }
   }
@@ -199,41 +216,49 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   load_weights_to_tmem(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, 1, SLU_H, j, warp >> 2);
 
   const int T2 = (T + ds - 1) / ds;
-  struct In { float r, z, n, hn, hp, dy; };
-  In cur[NC], nxt[NC];
-  auto load_step = [&](int t, In* v) {
+  int row256[NC];
+  uint32_t vmask = 0;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int b = b0 + c0 + c;
+    if (b < B) vmask |= 1u << c;
+    row256[c] = min(b, B - 1) * T * 256;
+  }
+  const float* st_j = stash + d * 512 + j;
+  const float* yf_j = y_full + d * SLU_H + j;
+  const float* dy_j = dy_out + d * SLU_H + j;
+  const float* mask_j = mask ? mask + d * SLU_H + j : nullptr;
+  float* dgx_j = dgx + d * SLU_G3 + j;
+  float* dhn_j = dhn_out + d * SLU_H + j;
+
+  // raw step inputs (no arithmetic at load time, so the loads stay in flight across the tensor-core phase)
+  float in_r[NC], in_z[NC], in_n[NC], in_hn[NC], in_hp[NC], in_dy[NC], in_mk[NC];
+  auto issue_loads = [&](int t) {
+    const int tp = d ? t + 1 : t - 1;
+    const bool has_prev = tp >= 0 && tp < T;
+    const size_t t256 = (size_t)t * 256, tp256 = (size_t)(has_prev ? tp : t) * 256;
+    const size_t to256 = (size_t)(ds == 2 ? (t >> 1) : t) * 256;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      v[c].r = v[c].z = v[c].n = v[c].hn = v[c].hp = v[c].dy = 0.f;
-      const int b = b0 + c0 + c;
-      if (b >= B) continue;
-      const size_t bt = (size_t)b * T + t;
-      const float* sp = stash + bt * 1024 + d * 512 + j;
-      v[c].r = __ldg(sp); v[c].z = __ldg(sp + 128); v[c].n = __ldg(sp + 256); v[c].hn = __ldg(sp + 384);
-      const int tp = d ? t + 1 : t - 1;
-      if (tp >= 0 && tp < T) v[c].hp = __ldg(y_full + ((size_t)b * T + tp) * 256 + d * SLU_H + j);
-      float g;
-      if (ds == 1) g = __ldg(dy_out + bt * 256 + d * SLU_H + j);
-      else {
-        g = __ldg(dy_out + ((size_t)b * T2 + (t >> 1)) * 256 + d * SLU_H + j);
-        if (!((t & 1) == 0 && t == T - 1)) g *= 0.5f;
-      }
-      if (mask) g *= __ldg(mask + bt * 256 + d * SLU_H + j);
-      v[c].dy = g;
+      const float* sp = st_j + (size_t)4 * row256[c] + 4 * t256;
+      in_r[c] = __ldg(sp); in_z[c] = __ldg(sp + 128); in_n[c] = __ldg(sp + 256); in_hn[c] = __ldg(sp + 384);
+      in_hp[c] = __ldg(yf_j + (size_t)row256[c] + tp256);
+      in_dy[c] = __ldg(dy_j + (ds == 2 ? (size_t)min(b0 + c0 + c, B - 1) * T2 * 256 : (size_t)row256[c]) + to256);
+      in_mk[c] = mask_j ? __ldg(mask_j + (size_t)row256[c] + t256) : 1.f;
     }
   };
-  load_step(d ? 0 : T - 1, cur);
+  issue_loads(d ? 0 : T - 1);
   const uint32_t idesc = idesc_bf16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
   const uint64_t bdesc_hi = smem_desc(smem_u32(g_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(g_lo), LBO, 128);
-  const uint32_t g_off = (uint32_t)(j >> 3) * LBO + (uint32_t)(j & 7) * 2;     // + gate*16*LBO + b*16
+  uint8_t* g_hi_j = g_hi + (uint32_t)(j >> 3) * LBO + (uint32_t)(j & 7) * 2 + c0 * 16;     // + gate*16*LBO + c*16
+  uint8_t* g_lo_j = g_hi_j + 48 * LBO;
   float dh_direct[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) dh_direct[c] = 0.f;
 
   for (int s = 0; s < T; ++s) {
     const int t = d ? s : T - 1 - s;
-    if (s + 1 < T) load_step(d ? t + 1 : t - 1, nxt);
     float rec[NC];
     if (s == 0) {
 #pragma unroll
@@ -248,32 +273,32 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
 #pragma unroll
       for (int c = 0; c < NC; ++c) rec[c] += r1[c] + r2[c];
     }
+    const int tp = d ? t + 1 : t - 1;
+    const float hp_on = (tp >= 0 && tp < T) ? 1.f : 0.f;
+    const float dscale = (ds == 2 && !((t & 1) == 0 && t == T - 1)) ? 0.5f : 1.f;
+    const size_t t256 = (size_t)t * 256;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const int b = b0 + c0 + c;
-      const float dh = rec[c] + dh_direct[c] + cur[c].dy;
-      const float r = cur[c].r, z = cur[c].z, n = cur[c].n;
+      const float dh = rec[c] + dh_direct[c] + in_dy[c] * (dscale * in_mk[c]);
+      const float r = in_r[c], z = in_z[c], n = in_n[c];
       const float dn_pre = dh * (1.f - z) * (1.f - n * n);
-      const float dz_pre = dh * (cur[c].hp - n) * z * (1.f - z);
+      const float dz_pre = dh * (in_hp[c] * hp_on - n) * z * (1.f - z);
       const float dhn = dn_pre * r;
-      const float dr_pre = dn_pre * cur[c].hn * r * (1.f - r);
+      const float dr_pre = dn_pre * in_hn[c] * r * (1.f - r);
       dh_direct[c] = dh * z;
       const float gv[3] = {dr_pre, dz_pre, dhn};
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
         const __nv_bfloat16 hh = __float2bfloat16_rn(gv[g]);
         const __nv_bfloat16 hl = __float2bfloat16_rn(gv[g] - __bfloat162float(hh));
-        const uint32_t off = g_off + (uint32_t)g * 16 * LBO + (c0 + c) * 16;
-        *reinterpret_cast<__nv_bfloat16*>(g_hi + off) = hh;
-        *reinterpret_cast<__nv_bfloat16*>(g_lo + off) = hl;
+        *reinterpret_cast<__nv_bfloat16*>(g_hi_j + (uint32_t)g * 16 * LBO + c * 16) = hh;
+        *reinterpret_cast<__nv_bfloat16*>(g_lo_j + (uint32_t)g * 16 * LBO + c * 16) = hl;
       }
-      if (b < B) {
-        const size_t bt = (size_t)b * T + t;
-        float* p = dgx + bt * 768 + d * SLU_G3 + j;
+      if (vmask & (1u << c)) {
+        float* p = dgx_j + (size_t)3 * row256[c] + 3 * t256;
         p[0] = dr_pre; p[128] = dz_pre; p[256] = dn_pre;
-        dhn_out[bt * 256 + d * SLU_H + j] = dhn;
+        dhn_j[(size_t)row256[c] + t256] = dhn;
       }
-      cur[c] = nxt[c];
     }
     if (s + 1 < T) {
       fence_async_smem();
@@ -295,6 +320,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
         }
         __syncwarp();
       }
+      issue_loads(d ? t + 1 : t - 1);     // land during the tensor-core phase
     }
   }
   fence_before_sync();

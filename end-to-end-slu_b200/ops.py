@@ -28,12 +28,21 @@ def _eptr(t, off=0):
 
 
 def gemm_tc(A, a_off, a_sm, a_sk, Bm, b_off, b_sn, b_sk, M, N, K, out, c_off=0, ldc=None, bias=None, taps=1, tap_pad=0,
-            T=0, a_kshift=0, b_kshift=0, b_stap=0, split_k=1, act=0, slope=0.0):
+            T=0, a_kshift=0, b_kshift=0, b_stap=0, split_k=1, act=0, slope=0.0, b_img=None):
     """Raw strided call of slu_gemm_tc (see include/slu_b200.h).  `out` must be zero-filled when split_k > 1."""
-    _lib.call("slu_gemm_tc", _eptr(A, a_off), a_sm, a_sk, _eptr(Bm, b_off), b_sn, b_sk, b_stap,
-              None if bias is None else _eptr(bias), _eptr(out, c_off), N if ldc is None else ldc, M, N, K, taps, tap_pad, T,
-              a_kshift, b_kshift, split_k, act, float(slope), _lib.stream())
+    _lib.call("slu_gemm_tc", _eptr(A, a_off), a_sm, a_sk, None if Bm is None else _eptr(Bm, b_off), b_sn, b_sk, b_stap,
+              None if b_img is None else b_img.data_ptr(), None if bias is None else _eptr(bias), _eptr(out, c_off),
+              N if ldc is None else ldc, M, N, K, taps, tap_pad, T, a_kshift, b_kshift, split_k, act, float(slope),
+              _lib.stream())
     return out
+
+
+def presplit(W, w_off, sn, sk, stap, taps, N, K):
+    """Weights -> bf16 hi/lo operand image for gemm_tc's B side (slu_presplit_bf16)."""
+    Kp = (K + 31) // 32 * 32
+    img = torch.empty(2 * taps * N * Kp, device=W.device, dtype=torch.bfloat16)
+    _lib.call("slu_presplit_bf16", _eptr(W, w_off), sn, sk, stap, taps, N, K, img.data_ptr(), _lib.stream())
+    return img
 
 
 def _split_k(M, N, K, taps=1):
@@ -49,7 +58,7 @@ def linear_nt(x2, w, bias=None):
     if GEMM_IMPL != "tc":
         return torch.addmm(bias, x2, w.t()) if bias is not None else x2 @ w.t()
     out = torch.empty(M, N, device=x2.device, dtype=torch.float32)
-    return gemm_tc(x2, 0, K, 1, w, 0, K, 1, M, N, K, out, bias=bias)
+    return gemm_tc(x2, 0, K, 1, None, 0, 0, 0, M, N, K, out, bias=bias, b_img=presplit(w, 0, K, 1, 0, 1, N, K))
 
 
 def matmul_nn(a2, w):
@@ -59,7 +68,7 @@ def matmul_nn(a2, w):
     if GEMM_IMPL != "tc":
         return a2 @ w
     out = torch.empty(M, N, device=a2.device, dtype=torch.float32)
-    return gemm_tc(a2, 0, K, 1, w, 0, 1, N, M, N, K, out)
+    return gemm_tc(a2, 0, K, 1, None, 0, 0, 0, M, N, K, out, b_img=presplit(w, 0, 1, N, 0, 1, N, K))
 
 
 def matmul_tn(g2, x2):
@@ -82,8 +91,8 @@ class ConvBlock(torch.autograd.Function):
         Cout, _, k = weight.shape
         w = weight.detach().contiguous()
         out = torch.empty(B, T, Cout, device=x.device, dtype=torch.float32)
-        gemm_tc(x, 0, Cin, 1, w, 0, Cin * k, k, B * T, Cout, Cin, out, bias=bias.detach(), taps=k, tap_pad=k // 2, T=T,
-                b_stap=1, act=1, slope=slope)
+        gemm_tc(x, 0, Cin, 1, None, 0, 0, 0, B * T, Cout, Cin, out, bias=bias.detach(), taps=k, tap_pad=k // 2, T=T,
+                act=1, slope=slope, b_img=presplit(w, 0, Cin * k, k, 1, k, Cout, Cin))
         ctx.save_for_backward(x, w, out)
         ctx.slope = slope
         return out
@@ -98,7 +107,8 @@ class ConvBlock(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, Cin, device=x.device, dtype=torch.float32)
             # dX[b,t,ci] = sum_d sum_co dpre[b,t-(d-k//2),co] W[co,ci,d]; tap' = k-1-d walks the kernel backwards
-            gemm_tc(dpre, 0, Cout, 1, w, k - 1, k, Cin * k, B * T, Cin, Cout, dx, taps=k, tap_pad=k // 2, T=T, b_stap=-1)
+            gemm_tc(dpre, 0, Cout, 1, None, 0, 0, 0, B * T, Cin, Cout, dx, taps=k, tap_pad=k // 2, T=T,
+                    b_img=presplit(w, k - 1, k, Cin * k, -1, k, Cin, Cout))
         if ctx.needs_input_grad[1]:
             dwt = torch.zeros(k, Cout, Cin, device=x.device, dtype=torch.float32)
             sk = _split_k(Cout, Cin, B * T)

@@ -63,10 +63,13 @@ int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_f
  *   A(m,tap,k) = A[(m + tap - tap_pad)*a_sm + k*a_sk]   (a_sk==1; rows leaving their T-frame utterance read as 0), or,
  *                when a_sk != 1 (reduction over frames): A[m*a_sm + (k + a_kshift)*a_sk], 0 if frame k%T + a_kshift leaves [0,T)
  *   B(n,tap,k) = B[n*b_sn + k*b_sk + tap*b_stap]        (b_sk != 1: frame-shifted by b_kshift like A)
+ * b_img (optional): the B operand pre-split by slu_presplit_bf16 (then B/b_s* are ignored).
  * split_k > 1 accumulates with fp32 atomics into a caller-zeroed C. */
-int slu_gemm_tc(const float* A, long a_sm, long a_sk, const float* B, long b_sn, long b_sk, long b_stap, const float* bias,
-                float* C, long ldc, int M, int N, int K, int taps, int tap_pad, int T, int a_kshift, int b_kshift,
-                int split_k, int act, float slope, void* stream);
+int slu_gemm_tc(const float* A, long a_sm, long a_sk, const float* B, long b_sn, long b_sk, long b_stap, const void* b_img,
+                const float* bias, float* C, long ldc, int M, int N, int K, int taps, int tap_pad, int T, int a_kshift,
+                int b_kshift, int split_k, int act, float slope, void* stream);
+/* Weights (any strides) -> bf16 hi/lo image [2][taps][N][Kp], Kp = K rounded up to 32 (img: 2*taps*N*Kp bf16 values). */
+int slu_presplit_bf16(const float* W, long sn, long sk, long stap, int taps, int N, int K, void* img, void* stream);
 
 /* tcgen05 self-test: C[128][N] = A[128][K] . B[N][K]^T (3-pass bf16 split, fp32 accumulate in TMEM). */
 int slu_tc_selftest(const float* A, const float* B, float* C, int N, int K, void* stream);
