@@ -40,10 +40,14 @@ __device__ __forceinline__ float ex2_approx(float v) { float r; asm("ex2.approx.
 __device__ __forceinline__ float rcp_approx(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 constexpr float kLog2e = 1.4426950408889634f;
 
-template <int NB, bool STASH>
+// Addressing scheme of both kernels: every per-(b,t) array is indexed through ONE 32-bit element offset per batch
+// column, off[c] = (b*T + t) * 256, advanced by +-256 per step; gx = base + 3*off, stash = base + 4*off, ... so each
+// access costs a single IMAD.WIDE.  FULL = all NB rows of this CTA exist (stores unpredicated); the ragged last tile
+// is launched separately with FULL = false.
+template <int NB, bool STASH, bool FULL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
-                  const float* __restrict__ mask, int B, int T, int ds, float* __restrict__ y_full,
+                  const float* __restrict__ mask, int B, int T, int ds, int tile0, float* __restrict__ y_full,
                   float* __restrict__ y_out, float* __restrict__ stash) {
   constexpr int NC = NB / 2;                         // batch columns per thread
   constexpr uint32_t LBO = NB * 16 + 16;             // padded: conflict-free 2-byte operand stores
@@ -51,7 +55,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
-  const int d = blockIdx.y, b0 = blockIdx.x * NB;
+  const int d = blockIdx.y, b0 = (tile0 + blockIdx.x) * NB;
   const int j = (warp & 3) * 32 + lane;              // hidden unit == TMEM lane
   const int c0 = (warp >> 2) * NC;                   // first batch column of this thread
   uint8_t* h_hi = h_tile;
@@ -69,14 +73,16 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
 
   const float bhr = b_hh[d * SLU_G3 + j], bhz = b_hh[d * SLU_G3 + 128 + j], bhn = b_hh[d * SLU_G3 + 256 + j];
   const int T2 = (T + ds - 1) / ds;
-  // Per-column addressing: rows beyond B are clamped for loads (results unused) and predicated off for stores.
-  int row256[NC];                                    // (clamped b) * T * 256 ; gx = 3x, stash = 4x
-  uint32_t vmask = 0;
+  const int t_first = d ? T - 1 : 0, dt = d ? -1 : 1;
+  int off[NC], offo[NC];                             // (b*T + t)*256 ; (b*T2 + t/ds)*256   (rows >= B clamped)
+  bool ok[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int b = b0 + c0 + c;
-    if (b < B) vmask |= 1u << c;
-    row256[c] = min(b, B - 1) * T * 256;
+    ok[c] = FULL || b < B;
+    const int bc = FULL ? b : min(b, B - 1);
+    off[c] = (bc * T + t_first) * 256;
+    offo[c] = bc * T2 * 256;
   }
   const float* gx_j = gx + d * SLU_G3 + j;
   const float* mask_j = mask ? mask + d * SLU_H + j : nullptr;
@@ -86,15 +92,11 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
 
   float hprev[NC], pend[NC], gxr[NC], gxz[NC], gxn[NC], mk[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) { hprev[c] = 0.f; pend[c] = 0.f; mk[c] = 1.f; }
-  {
-    const int t = d ? T - 1 : 0;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const float* p = gx_j + (size_t)3 * row256[c] + (size_t)t * 768;
-      gxr[c] = __ldg(p); gxz[c] = __ldg(p + 128); gxn[c] = __ldg(p + 256);
-      if (mask_j) mk[c] = __ldg(mask_j + (size_t)row256[c] + (size_t)t * 256);
-    }
+  for (int c = 0; c < NC; ++c) {
+    hprev[c] = 0.f; pend[c] = 0.f; mk[c] = 1.f;
+    const float* p = gx_j + 3 * (long)off[c];
+    gxr[c] = __ldg(p); gxz[c] = __ldg(p + 128); gxn[c] = __ldg(p + 256);
+    if (mask_j) mk[c] = __ldg(mask_j + off[c]);
   }
   const uint32_t idesc = idesc_bf16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
@@ -104,7 +106,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   uint8_t* h_lo_j = h_hi_j + 16 * LBO;
 
   for (int s = 0; s < T; ++s) {
-    const int t = d ? T - 1 - s : s;
+    const int t = t_first + dt * s;
     float ar[NC], az[NC], an[NC];
     if (s == 0) {
 #pragma unroll
@@ -116,41 +118,39 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       else { tmem_ld16(acc_addr, ar); tmem_ld16(acc_addr + NB, az); tmem_ld16(acc_addr + 2 * NB, an); }
       tmem_ld_wait();
     }
-    const bool tail = (ds == 2) && ((t & 1) == 0) && (t == T - 1);       // odd tail frame: divisor 1 (ceil_mode)
-    const bool first = (ds == 2) && !tail && ((t & 1) == (d ? 1 : 0));   // first visited frame of its pair
-    const size_t t256 = (size_t)t * 256, to256 = (size_t)(ds == 2 ? (t >> 1) : t) * 256;
+    // Downsample(avg,2) bookkeeping, uniform per step: `single` = odd tail frame (divisor 1, ceil_mode),
+    // `first` = first visited frame of its pair (value parked in `pend`), otherwise the pair is completed.
+    const bool single = (ds == 1) || (((t & 1) == 0) && (t == T - 1));
+    const bool first = !single && ((t & 1) == (d ? 1 : 0));
+    const int to = (ds == 2 ? (t >> 1) : t) * 256;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       // r, z share one reciprocal:  r = (1+v)/((1+u)(1+v)), z = (1+u)/((1+u)(1+v)),  u = e^-pr, v = e^-pz
-      const float pr = fminf(fmaxf(gxr[c] + (ar[c] + bhr), -40.f), 40.f);
-      const float pz = fminf(fmaxf(gxz[c] + (az[c] + bhz), -40.f), 40.f);
+      const float pr = fmaxf(gxr[c] + (ar[c] + bhr), -40.f);           // lower clamp keeps (1+u)(1+v) finite
+      const float pz = fmaxf(gxz[c] + (az[c] + bhz), -40.f);
       const float su = 1.f + ex2_approx(-kLog2e * pr), sv = 1.f + ex2_approx(-kLog2e * pz);
       const float w = rcp_approx(su * sv);
       const float r = w * sv, z = w * su;
       const float hn = an[c] + bhn;
-      const float pn = fminf(fmaxf(gxn[c] + r * hn, -40.f), 40.f);
-      const float n = 2.f * rcp_approx(1.f + ex2_approx(-2.f * kLog2e * pn)) - 1.f;
+      const float n = 2.f * rcp_approx(1.f + ex2_approx(-2.f * kLog2e * (gxn[c] + r * hn))) - 1.f;   // tanh; inf-safe
       const float hnew = n + z * (hprev[c] - n);
       hprev[c] = hnew;
       const __nv_bfloat16 hh = __float2bfloat16_rn(hnew);
       const __nv_bfloat16 hl = __float2bfloat16_rn(hnew - __bfloat162float(hh));
       *reinterpret_cast<__nv_bfloat16*>(h_hi_j + c * 16) = hh;
       *reinterpret_cast<__nv_bfloat16*>(h_lo_j + c * 16) = hl;
-      if (vmask & (1u << c)) {
-        yf_j[(size_t)row256[c] + t256] = hnew;
+      const float val = hnew * mk[c];
+      const float outv = single ? val : 0.5f * (pend[c] + val);
+      pend[c] = val;
+      if (ok[c]) {
+        yf_j[off[c]] = hnew;
         if (STASH) {
-          float* sp = st_j + (size_t)4 * row256[c] + 4 * t256;
+          float* sp = st_j + 4 * (long)off[c];
           sp[0] = r; sp[128] = z; sp[256] = n; sp[384] = hn;
         }
-        const float val = hnew * mk[c];
-        if (ds == 1) yo_j[(size_t)row256[c] + t256] = val;
-        else {
-          float* yo = yo_j + (size_t)(b0 + c0 + c) * T2 * 256 + to256;
-          if (tail) *yo = val;
-          else if (first) pend[c] = val;
-          else *yo = 0.5f * (pend[c] + val);
-        }
+        if (!first) yo_j[offo[c] + to] = outv;
       }
+      off[c] += dt * 256;
     }
     if (s + 1 < T) {
       fence_async_smem();          // h tile (generic-proxy stores) -> visible to the tensor core (async proxy)
@@ -172,12 +172,11 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
         __syncwarp();
       }
       // next step's inputs: issued now, they land while the tensor core works (consumed after the mbarrier wait)
-      const int tn = d ? t - 1 : t + 1;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        const float* p = gx_j + (size_t)3 * row256[c] + (size_t)tn * 768;
+        const float* p = gx_j + 3 * (long)off[c];
         gxr[c] = __ldg(p); gxz[c] = __ldg(p + 128); gxn[c] = __ldg(p + 256);
-        if (mask_j) mk[c] = __ldg(mask_j + (size_t)row256[c] + (size_t)tn * 256);
+        if (mask_j) mk[c] = __ldg(mask_j + off[c]);
       }
     }
   }
@@ -188,10 +187,10 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
 
 // Backward through time on tensor cores.  dh_{t-1}[k] += sum_row W_hh[row][k] * dG[row]:  M = 128 (k), K = 384 (gate rows),
 // N = NB.  W_hh^T (hi/lo) is stationary in TMEM (2 x 192 columns); dG = (dr, dz, dhn) is the shared-memory B tile.
-template <int NB>
+template <int NB, bool FULL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, const float* __restrict__ y_full,
-                  const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds,
+                  const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds, int tile0,
                   float* __restrict__ dgx, float* __restrict__ dhn_out) {
   constexpr int NC = NB / 2;
   constexpr uint32_t LBO = NB * 16 + 16;
@@ -199,7 +198,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
-  const int d = blockIdx.y, b0 = blockIdx.x * NB;
+  const int d = blockIdx.y, b0 = (tile0 + blockIdx.x) * NB;
   const int j = (warp & 3) * 32 + lane;
   const int c0 = (warp >> 2) * NC;
   uint8_t* g_hi = g_tile;
@@ -216,13 +215,16 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   load_weights_to_tmem(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, 1, SLU_H, j, warp >> 2);
 
   const int T2 = (T + ds - 1) / ds;
-  int row256[NC];
-  uint32_t vmask = 0;
+  const int t_first = d ? 0 : T - 1, dt = d ? 1 : -1;       // walk time against the forward direction
+  int off[NC], offo[NC];
+  bool ok[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int b = b0 + c0 + c;
-    if (b < B) vmask |= 1u << c;
-    row256[c] = min(b, B - 1) * T * 256;
+    ok[c] = FULL || b < B;
+    const int bc = FULL ? b : min(b, B - 1);
+    off[c] = (bc * T + t_first) * 256;
+    offo[c] = bc * T2 * 256;
   }
   const float* st_j = stash + d * 512 + j;
   const float* yf_j = y_full + d * SLU_H + j;
@@ -234,20 +236,19 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   // raw step inputs (no arithmetic at load time, so the loads stay in flight across the tensor-core phase)
   float in_r[NC], in_z[NC], in_n[NC], in_hn[NC], in_hp[NC], in_dy[NC], in_mk[NC];
   auto issue_loads = [&](int t) {
-    const int tp = d ? t + 1 : t - 1;
-    const bool has_prev = tp >= 0 && tp < T;
-    const size_t t256 = (size_t)t * 256, tp256 = (size_t)(has_prev ? tp : t) * 256;
-    const size_t to256 = (size_t)(ds == 2 ? (t >> 1) : t) * 256;
+    const int tp = t + dt;                                   // the step the forward pass took before t
+    const int hp_shift = (tp >= 0 && tp < T) ? dt * 256 : 0;
+    const int to = (ds == 2 ? (t >> 1) : t) * 256;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const float* sp = st_j + (size_t)4 * row256[c] + 4 * t256;
+      const float* sp = st_j + 4 * (long)off[c];
       in_r[c] = __ldg(sp); in_z[c] = __ldg(sp + 128); in_n[c] = __ldg(sp + 256); in_hn[c] = __ldg(sp + 384);
-      in_hp[c] = __ldg(yf_j + (size_t)row256[c] + tp256);
-      in_dy[c] = __ldg(dy_j + (ds == 2 ? (size_t)min(b0 + c0 + c, B - 1) * T2 * 256 : (size_t)row256[c]) + to256);
-      in_mk[c] = mask_j ? __ldg(mask_j + (size_t)row256[c] + t256) : 1.f;
+      in_hp[c] = __ldg(yf_j + off[c] + hp_shift);
+      in_dy[c] = __ldg(dy_j + offo[c] + to);
+      in_mk[c] = mask_j ? __ldg(mask_j + off[c]) : 1.f;
     }
   };
-  issue_loads(d ? 0 : T - 1);
+  issue_loads(t_first);
   const uint32_t idesc = idesc_bf16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
   const uint64_t bdesc_hi = smem_desc(smem_u32(g_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(g_lo), LBO, 128);
@@ -258,7 +259,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   for (int c = 0; c < NC; ++c) dh_direct[c] = 0.f;
 
   for (int s = 0; s < T; ++s) {
-    const int t = d ? s : T - 1 - s;
+    const int t = t_first + dt * s;
     float rec[NC];
     if (s == 0) {
 #pragma unroll
@@ -273,10 +274,9 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
 #pragma unroll
       for (int c = 0; c < NC; ++c) rec[c] += r1[c] + r2[c];
     }
-    const int tp = d ? t + 1 : t - 1;
+    const int tp = t + dt;
     const float hp_on = (tp >= 0 && tp < T) ? 1.f : 0.f;
     const float dscale = (ds == 2 && !((t & 1) == 0 && t == T - 1)) ? 0.5f : 1.f;
-    const size_t t256 = (size_t)t * 256;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const float dh = rec[c] + dh_direct[c] + in_dy[c] * (dscale * in_mk[c]);
@@ -294,11 +294,12 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
         *reinterpret_cast<__nv_bfloat16*>(g_hi_j + (uint32_t)g * 16 * LBO + c * 16) = hh;
         *reinterpret_cast<__nv_bfloat16*>(g_lo_j + (uint32_t)g * 16 * LBO + c * 16) = hl;
       }
-      if (vmask & (1u << c)) {
-        float* p = dgx_j + (size_t)3 * row256[c] + 3 * t256;
+      if (ok[c]) {
+        float* p = dgx_j + 3 * (long)off[c];
         p[0] = dr_pre; p[128] = dz_pre; p[256] = dn_pre;
-        dhn_j[(size_t)row256[c] + t256] = dhn;
+        dhn_j[off[c]] = dhn;
       }
+      off[c] += dt * 256;
     }
     if (s + 1 < T) {
       fence_async_smem();
@@ -320,7 +321,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
         }
         __syncwarp();
       }
-      issue_loads(d ? t + 1 : t - 1);     // land during the tensor-core phase
+      issue_loads(t + dt);            // land during the tensor-core phase
     }
   }
   fence_before_sync();
@@ -332,21 +333,32 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
 
 extern "C" int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T,
                               int ds, float* y_full, float* y_out, float* stash, void* stream) {
-  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2)) return (int)cudaErrorInvalidValue;
+  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (long)B * T * 1024 >= (1L << 31)) return (int)cudaErrorInvalidValue;
   constexpr int NB = 16;
-  dim3 grid((B + NB - 1) / NB, 2);
-  if (stash) gru_fwd_tc_kernel<NB, true><<<grid, TC_THREADS, 0, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, stash);
-  else gru_fwd_tc_kernel<NB, false><<<grid, TC_THREADS, 0, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int full = B / NB, rem = B % NB;
+  if (full) {
+    dim3 grid(full, 2);
+    if (stash) gru_fwd_tc_kernel<NB, true, true><<<grid, TC_THREADS, 0, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, stash);
+    else gru_fwd_tc_kernel<NB, false, true><<<grid, TC_THREADS, 0, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, nullptr);
+  }
+  if (rem) {                          // ragged last tile: predicated stores
+    dim3 grid(1, 2);
+    if (stash) gru_fwd_tc_kernel<NB, true, false><<<grid, TC_THREADS, 0, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, stash);
+    else gru_fwd_tc_kernel<NB, false, false><<<grid, TC_THREADS, 0, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, nullptr);
+  }
   SLU_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
                               const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, void* stream) {
-  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2)) return (int)cudaErrorInvalidValue;
+  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (long)B * T * 1024 >= (1L << 31)) return (int)cudaErrorInvalidValue;
   constexpr int NB = 16;
-  dim3 grid((B + NB - 1) / NB, 2);
-  gru_bwd_tc_kernel<NB><<<grid, TC_THREADS, 0, (cudaStream_t)stream>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int full = B / NB, rem = B % NB;
+  if (full) gru_bwd_tc_kernel<NB, true><<<dim3(full, 2), TC_THREADS, 0, st>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn);
+  if (rem) gru_bwd_tc_kernel<NB, false><<<dim3(1, 2), TC_THREADS, 0, st>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn);
   SLU_CHECK_LAUNCH();
   return 0;
 }
