@@ -128,16 +128,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     if (A_KC) { a_kc[u] = c & 3; a_r[u] = c >> 2; } else { a_r[u] = c % BM; a_kc[u] = c / BM; }
   }
 
-  for (int i = 0; i < nkb; ++i) {
-    const int s = i % STAGES;
-    if (i >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((i / STAGES) - 1) & 1));
+  // Register-prefetch pipeline: the global loads of k-block i+1 are issued right after k-block i has been
+  // converted into its shared-memory stage, so their latency hides behind the fence / barrier / MMA issue.
+  float va[A_CH][8];
+  float vb[(BMODE == 2) ? 1 : B_CH][8];
+  uint4 ib_hi[(BMODE == 2) ? B_CH : 1], ib_lo[(BMODE == 2) ? B_CH : 1];
+  auto prefetch = [&](int i) {
     const int kb = kb_begin + i;
     const int tap = kb / kb_per_tap, k0 = (kb % kb_per_tap) * BK;
-    uint8_t* st = smem + s * S::STAGE;
-    uint8_t* a_hi = st; uint8_t* a_lo = st + S::A_PART;
-    uint8_t* b_hi = st + 2 * S::A_PART; uint8_t* b_lo = b_hi + S::B_PART;
-    // ---- issue the global loads of this k-block's A chunks first (consumed after the B tile is staged)
-    float va[A_CH][8];
 #pragma unroll
     for (int u = 0; u < A_CH; ++u) {
       const int m = m0 + a_r[u];
@@ -155,57 +153,37 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         load8_strided(p.A + (long)m * p.a_sm, p.a_sk, k0 + a_kc[u] * 8, p.K, p.T ? p.T : 1, p.a_kshift, m < p.M, va[u]);
       }
     }
-    if (BMODE == 2) {
-      uint4 bh[B_CH], bl[B_CH];
 #pragma unroll
-      for (int u = 0; u < B_CH; ++u) {
-        const int c = tid + u * THREADS;
+    for (int u = 0; u < B_CH; ++u) {
+      const int c = tid + u * THREADS;
+      if (BMODE == 2) {
         const int kc = c & 3, r = c >> 2, n = n0 + r;
-        bh[u] = make_uint4(0, 0, 0, 0); bl[u] = bh[u];
+        ib_hi[u] = make_uint4(0, 0, 0, 0); ib_lo[u] = ib_hi[u];
         if (c < B_TOT && n < p.N) {
           const size_t e = ((size_t)tap * p.N + n) * p.Kp + k0 + kc * 8;
-          bh[u] = __ldg(reinterpret_cast<const uint4*>(p.Bimg + e));
-          bl[u] = __ldg(reinterpret_cast<const uint4*>(p.Bimg + (size_t)p.taps * p.N * p.Kp + e));
+          ib_hi[u] = __ldg(reinterpret_cast<const uint4*>(p.Bimg + e));
+          ib_lo[u] = __ldg(reinterpret_cast<const uint4*>(p.Bimg + (size_t)p.taps * p.N * p.Kp + e));
         }
-      }
-#pragma unroll
-      for (int u = 0; u < B_CH; ++u) {
-        const int c = tid + u * THREADS;
-        if (c < B_TOT) {
-          const uint32_t off = (uint32_t)(c & 3) * S::LBO_B + (uint32_t)(c >> 2) * 16;
-          *reinterpret_cast<uint4*>(b_hi + off) = bh[u];
-          *reinterpret_cast<uint4*>(b_lo + off) = bl[u];
-        }
-      }
-    } else {
-#pragma unroll 1
-      for (int u0 = 0; u0 < B_CH; u0 += 2) {             // batches of 2 chunks keep register use bounded
-        float vb[2][8];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = tid + (u0 + u) * THREADS;
-          int r, kc;
-          if (BMODE == 0) { kc = c & 3; r = c >> 2; } else { r = c % BN; kc = c / BN; }
-          const int n = n0 + r;
-          const bool ok = (c < B_TOT) && (n < p.N);
-          const float* base = p.B + (long)n * p.b_sn + (long)tap * p.b_stap;
-          if (BMODE == 0) load8_kc(base, k0 + kc * 8, p.K, ok, vb[u]);
-          else load8_strided(base, p.b_sk, k0 + kc * 8, p.K, p.T ? p.T : 1, p.b_kshift, ok, vb[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = tid + (u0 + u) * THREADS;
-          if (c < B_TOT) {
-            int r, kc;
-            if (BMODE == 0) { kc = c & 3; r = c >> 2; } else { r = c % BN; kc = c / BN; }
-            uint4 hi, lo; split8(vb[u], hi, lo);
-            const uint32_t off = (uint32_t)kc * S::LBO_B + (uint32_t)r * 16;
-            *reinterpret_cast<uint4*>(b_hi + off) = hi;
-            *reinterpret_cast<uint4*>(b_lo + off) = lo;
-          }
-        }
+      } else {
+        int r, kc;
+        if (BMODE == 0) { kc = c & 3; r = c >> 2; } else { r = c % BN; kc = c / BN; }
+        const int n = n0 + r;
+        const bool ok = (c < B_TOT) && (n < p.N);
+        const float* base = p.B + (long)n * p.b_sn + (long)tap * p.b_stap;
+        if (BMODE == 0) load8_kc(base, k0 + kc * 8, p.K, ok, vb[u]);
+        else load8_strided(base, p.b_sk, k0 + kc * 8, p.K, p.T ? p.T : 1, p.b_kshift, ok, vb[u]);
       }
     }
+  };
+  prefetch(0);
+
+  for (int i = 0; i < nkb; ++i) {
+    const int s = i % STAGES;
+    if (i >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((i / STAGES) - 1) & 1));
+    const int k0 = ((kb_begin + i) % kb_per_tap) * BK;
+    uint8_t* st = smem + s * S::STAGE;
+    uint8_t* a_hi = st; uint8_t* a_lo = st + S::A_PART;
+    uint8_t* b_hi = st + 2 * S::A_PART; uint8_t* b_lo = b_hi + S::B_PART;
 #pragma unroll
     for (int u = 0; u < A_CH; ++u) {
       uint4 hi, lo; split8(va[u], hi, lo);
@@ -213,6 +191,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       *reinterpret_cast<uint4*>(a_hi + off) = hi;
       *reinterpret_cast<uint4*>(a_lo + off) = lo;
     }
+#pragma unroll
+    for (int u = 0; u < B_CH; ++u) {
+      const int c = tid + u * THREADS;
+      if (c < B_TOT) {
+        int r, kc;
+        if (BMODE == 1) { r = c % BN; kc = c / BN; } else { kc = c & 3; r = c >> 2; }
+        uint4 hi, lo;
+        if (BMODE == 2) { hi = ib_hi[u]; lo = ib_lo[u]; } else split8(vb[u], hi, lo);
+        const uint32_t off = (uint32_t)kc * S::LBO_B + (uint32_t)r * 16;
+        *reinterpret_cast<uint4*>(b_hi + off) = hi;
+        *reinterpret_cast<uint4*>(b_lo + off) = lo;
+      }
+    }
+    if (i + 1 < nkb) prefetch(i + 1);
     fence_async_smem();
     __syncthreads();
     // ---- one elected thread issues this k-block's MMAs (async: they overlap the staging of the next k-block)
@@ -265,10 +257,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       float* dst = p.C + (long)(m0 + q * 32) * p.ldc + n;
       const int rows = min(32, p.M - (m0 + q * 32));
       if (n_ok) {
-        for (int r = 0; r < rows; ++r) {
-          float x = tr[r * 33 + lane] + bias;
-          if (p.act == 1) x = x > 0.f ? x : x * p.slope;
-          if (p.split_k > 1) atomicAdd(dst + (long)r * p.ldc, x); else dst[(long)r * p.ldc] = x;
+        if (rows == 32) {
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            float x = tr[r * 33 + lane] + bias;
+            if (p.act == 1) x = x > 0.f ? x : x * p.slope;
+            if (p.split_k > 1) atomicAdd(dst + (long)r * p.ldc, x); else dst[(long)r * p.ldc] = x;
+          }
+        } else {
+          for (int r = 0; r < rows; ++r) {
+            float x = tr[r * 33 + lane] + bias;
+            if (p.act == 1) x = x > 0.f ? x : x * p.slope;
+            if (p.split_k > 1) atomicAdd(dst + (long)r * p.ldc, x); else dst[(long)r * p.ldc] = x;
+          }
         }
       }
       __syncwarp();

@@ -19,6 +19,7 @@ using namespace tc05;
 
 constexpr int TC_THREADS = 256;       // 8 warps: warp w owns TMEM lanes 32*(w%4).., batch columns (w/4)*NB/2 ..
 constexpr uint32_t ACC_COL = 384;     // accumulators start after the 384 weight columns
+constexpr int FWD_RING = 4, BWD_RING = 3;   // depth of the TMA input rings (steps in flight)
 
 // Load W rows (this thread's lane) into TMEM as split bf16 A-operands.  src: 3 blocks of [128][128] fp32 with
 // element (row j, k) at src[g*block_stride + j*row_stride + k*k_stride].
@@ -52,8 +53,10 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   constexpr int NC = NB / 2;                         // batch columns per thread
   constexpr uint32_t LBO = NB * 16 + 16;             // padded: conflict-free 2-byte operand stores
   __shared__ __align__(128) uint8_t h_tile[2 * 16 * LBO];   // [hi | lo] x 16 k-chunks x (NB rows x 16 B + pad)
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, in_bar[FWD_RING];
   __shared__ uint32_t tmem_base;
+  extern __shared__ __align__(128) float in_ring[];         // FWD_RING x { gx [NB][384], mask [NB][128] }  (TMA-filled)
+  constexpr int SLOT = NB * 512;                            // floats per ring slot
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int d = blockIdx.y, b0 = (tile0 + blockIdx.x) * NB;
   const int j = (warp & 3) * 32 + lane;              // hidden unit == TMEM lane
@@ -61,7 +64,11 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   uint8_t* h_hi = h_tile;
   uint8_t* h_lo = h_tile + 16 * LBO;
 
-  if (tid == 0) { mbar_init(&bar, 3); fence_mbar_init(); }   // 3 gate-issuer warps commit per step
+  if (tid == 0) {
+    mbar_init(&bar, 3);                                      // 3 gate-issuer warps commit per step
+    for (int r = 0; r < FWD_RING; ++r) mbar_init(&in_bar[r], 1);
+    fence_mbar_init();
+  }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_base, 512);
   fence_before_sync();
@@ -84,20 +91,28 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
     off[c] = (bc * T + t_first) * 256;
     offo[c] = bc * T2 * 256;
   }
-  const float* gx_j = gx + d * SLU_G3 + j;
-  const float* mask_j = mask ? mask + d * SLU_H + j : nullptr;
   float* yf_j = y_full + d * SLU_H + j;
   float* yo_j = y_out + d * SLU_H + j;
   float* st_j = STASH ? stash + d * 512 + j : nullptr;
 
-  float hprev[NC], pend[NC], gxr[NC], gxz[NC], gxn[NC], mk[NC];
+  // Step inputs arrive through a TMA ring: one elected thread bulk-copies the NB gx rows (1536 B each) and mask rows
+  // (512 B) of step `s` into slot s % FWD_RING, FWD_RING steps ahead of their use.
+  auto tma_issue = [&](int s) {
+    const int t = t_first + dt * s, slot = s % FWD_RING;
+    float* dst = in_ring + slot * SLOT;
+    mbar_arrive_expect_tx(&in_bar[slot], NB * (1536u + (mask ? 512u : 0u)));
+    for (int c = 0; c < NB; ++c) {
+      const long bt = (long)min(b0 + c, B - 1) * T + t;
+      tma_load_1d(dst + c * 384, gx + bt * 768 + d * SLU_G3, 1536, &in_bar[slot]);
+      if (mask) tma_load_1d(dst + NB * 384 + c * 128, mask + bt * 256 + d * SLU_H, 512, &in_bar[slot]);
+    }
+  };
+  if (warp == 3 && elect_one())
+    for (int s = 0; s < FWD_RING && s < T; ++s) tma_issue(s);
+
+  float hprev[NC], pend[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    hprev[c] = 0.f; pend[c] = 0.f; mk[c] = 1.f;
-    const float* p = gx_j + 3 * (long)off[c];
-    gxr[c] = __ldg(p); gxz[c] = __ldg(p + 128); gxn[c] = __ldg(p + 256);
-    if (mask_j) mk[c] = __ldg(mask_j + off[c]);
-  }
+  for (int c = 0; c < NC; ++c) { hprev[c] = 0.f; pend[c] = 0.f; }
   const uint32_t idesc = idesc_bf16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
   const uint64_t bdesc_hi = smem_desc(smem_u32(h_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(h_lo), LBO, 128);
@@ -123,23 +138,26 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
     const bool single = (ds == 1) || (((t & 1) == 0) && (t == T - 1));
     const bool first = !single && ((t & 1) == (d ? 1 : 0));
     const int to = (ds == 2 ? (t >> 1) : t) * 256;
+    mbar_wait(&in_bar[s % FWD_RING], (uint32_t)((s / FWD_RING) & 1));       // this step's gx / mask rows have landed
+    const float* gxs = in_ring + (s % FWD_RING) * SLOT + c0 * 384 + j;
+    const float* mks = in_ring + (s % FWD_RING) * SLOT + NB * 384 + c0 * 128 + j;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       // r, z share one reciprocal:  r = (1+v)/((1+u)(1+v)), z = (1+u)/((1+u)(1+v)),  u = e^-pr, v = e^-pz
-      const float pr = fmaxf(gxr[c] + (ar[c] + bhr), -40.f);           // lower clamp keeps (1+u)(1+v) finite
-      const float pz = fmaxf(gxz[c] + (az[c] + bhz), -40.f);
+      const float pr = fmaxf(gxs[c * 384] + (ar[c] + bhr), -40.f);     // lower clamp keeps (1+u)(1+v) finite
+      const float pz = fmaxf(gxs[c * 384 + 128] + (az[c] + bhz), -40.f);
       const float su = 1.f + ex2_approx(-kLog2e * pr), sv = 1.f + ex2_approx(-kLog2e * pz);
       const float w = rcp_approx(su * sv);
       const float r = w * sv, z = w * su;
       const float hn = an[c] + bhn;
-      const float n = 2.f * rcp_approx(1.f + ex2_approx(-2.f * kLog2e * (gxn[c] + r * hn))) - 1.f;   // tanh; inf-safe
+      const float n = 2.f * rcp_approx(1.f + ex2_approx(-2.f * kLog2e * (gxs[c * 384 + 256] + r * hn))) - 1.f;   // tanh; inf-safe
       const float hnew = n + z * (hprev[c] - n);
       hprev[c] = hnew;
       const __nv_bfloat16 hh = __float2bfloat16_rn(hnew);
       const __nv_bfloat16 hl = __float2bfloat16_rn(hnew - __bfloat162float(hh));
       *reinterpret_cast<__nv_bfloat16*>(h_hi_j + c * 16) = hh;
       *reinterpret_cast<__nv_bfloat16*>(h_lo_j + c * 16) = hl;
-      const float val = hnew * mk[c];
+      const float val = mask ? hnew * mks[c * 128] : hnew;
       const float outv = single ? val : 0.5f * (pend[c] + val);
       pend[c] = val;
       if (ok[c]) {
@@ -171,13 +189,8 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
         }
         __syncwarp();
       }
-      // next step's inputs: issued now, they land while the tensor core works (consumed after the mbarrier wait)
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const float* p = gx_j + 3 * (long)off[c];
-        gxr[c] = __ldg(p); gxz[c] = __ldg(p + 128); gxn[c] = __ldg(p + 256);
-        if (mask_j) mk[c] = __ldg(mask_j + off[c]);
-      }
+      // slot s % FWD_RING has been read by every thread (barrier above): refill it for step s + FWD_RING
+      if (warp == 3 && s + FWD_RING < T && elect_one()) tma_issue(s + FWD_RING);
     }
   }
   fence_before_sync();
@@ -195,15 +208,21 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   constexpr int NC = NB / 2;
   constexpr uint32_t LBO = NB * 16 + 16;
   __shared__ __align__(128) uint8_t g_tile[2 * 48 * LBO];   // [hi | lo] x 48 k-chunks (384 gate rows)
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, in_bar[BWD_RING];
   __shared__ uint32_t tmem_base;
+  extern __shared__ __align__(128) float in_ring[];         // BWD_RING x { stash [NB][512], h_prev, dy, mask [NB][128] each }
+  constexpr int SLOT = NB * 896;
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int d = blockIdx.y, b0 = (tile0 + blockIdx.x) * NB;
   const int j = (warp & 3) * 32 + lane;
   const int c0 = (warp >> 2) * NC;
   uint8_t* g_hi = g_tile;
   uint8_t* g_lo = g_tile + 48 * LBO;
-  if (tid == 0) { mbar_init(&bar, 3); fence_mbar_init(); }   // the K=384 reduction is issued as 3 chunks by 3 warps
+  if (tid == 0) {
+    mbar_init(&bar, 3);                                      // the K=384 reduction is issued as 3 chunks by 3 warps
+    for (int r = 0; r < BWD_RING; ++r) mbar_init(&in_bar[r], 1);
+    fence_mbar_init();
+  }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_base, 512);
   fence_before_sync();
@@ -226,29 +245,27 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
     off[c] = (bc * T + t_first) * 256;
     offo[c] = bc * T2 * 256;
   }
-  const float* st_j = stash + d * 512 + j;
-  const float* yf_j = y_full + d * SLU_H + j;
-  const float* dy_j = dy_out + d * SLU_H + j;
-  const float* mask_j = mask ? mask + d * SLU_H + j : nullptr;
   float* dgx_j = dgx + d * SLU_G3 + j;
   float* dhn_j = dhn_out + d * SLU_H + j;
 
-  // raw step inputs (no arithmetic at load time, so the loads stay in flight across the tensor-core phase)
-  float in_r[NC], in_z[NC], in_n[NC], in_hn[NC], in_hp[NC], in_dy[NC], in_mk[NC];
-  auto issue_loads = [&](int t) {
-    const int tp = t + dt;                                   // the step the forward pass took before t
-    const int hp_shift = (tp >= 0 && tp < T) ? dt * 256 : 0;
-    const int to = (ds == 2 ? (t >> 1) : t) * 256;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const float* sp = st_j + 4 * (long)off[c];
-      in_r[c] = __ldg(sp); in_z[c] = __ldg(sp + 128); in_n[c] = __ldg(sp + 256); in_hn[c] = __ldg(sp + 384);
-      in_hp[c] = __ldg(yf_j + off[c] + hp_shift);
-      in_dy[c] = __ldg(dy_j + offo[c] + to);
-      in_mk[c] = mask_j ? __ldg(mask_j + off[c]) : 1.f;
+  // TMA ring of step inputs (see the forward kernel): per batch row the stashed gates (2048 B), h of the previous
+  // forward step (512 B; the row itself when there is none -- it is multiplied by 0), dL/dy (512 B) and the mask row.
+  auto tma_issue = [&](int s) {
+    const int t = t_first + dt * s, slot = s % BWD_RING;
+    const int tp = t + dt, tpv = (tp >= 0 && tp < T) ? tp : t;
+    const int to = ds == 2 ? (t >> 1) : t;
+    float* dst = in_ring + slot * SLOT;
+    mbar_arrive_expect_tx(&in_bar[slot], NB * (2048u + 512u + 512u + (mask ? 512u : 0u)));
+    for (int c = 0; c < NB; ++c) {
+      const long bc = min(b0 + c, B - 1);
+      tma_load_1d(dst + c * 512, stash + (bc * T + t) * 1024 + d * 512, 2048, &in_bar[slot]);
+      tma_load_1d(dst + NB * 512 + c * 128, y_full + (bc * T + tpv) * 256 + d * SLU_H, 512, &in_bar[slot]);
+      tma_load_1d(dst + NB * 640 + c * 128, dy_out + (bc * T2 + to) * 256 + d * SLU_H, 512, &in_bar[slot]);
+      if (mask) tma_load_1d(dst + NB * 768 + c * 128, mask + (bc * T + t) * 256 + d * SLU_H, 512, &in_bar[slot]);
     }
   };
-  issue_loads(t_first);
+  if (warp == 3 && elect_one())
+    for (int s = 0; s < BWD_RING && s < T; ++s) tma_issue(s);
   const uint32_t idesc = idesc_bf16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
   const uint64_t bdesc_hi = smem_desc(smem_u32(g_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(g_lo), LBO, 128);
@@ -277,14 +294,21 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
     const int tp = t + dt;
     const float hp_on = (tp >= 0 && tp < T) ? 1.f : 0.f;
     const float dscale = (ds == 2 && !((t & 1) == 0 && t == T - 1)) ? 0.5f : 1.f;
+    mbar_wait(&in_bar[s % BWD_RING], (uint32_t)((s / BWD_RING) & 1));
+    const float* sl = in_ring + (s % BWD_RING) * SLOT;
+    const float* sts = sl + c0 * 512 + j;
+    const float* hps = sl + NB * 512 + c0 * 128 + j;
+    const float* dys = sl + NB * 640 + c0 * 128 + j;
+    const float* mks = sl + NB * 768 + c0 * 128 + j;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const float dh = rec[c] + dh_direct[c] + in_dy[c] * (dscale * in_mk[c]);
-      const float r = in_r[c], z = in_z[c], n = in_n[c];
+      const float mkv = mask ? mks[c * 128] : 1.f;
+      const float dh = rec[c] + dh_direct[c] + dys[c * 128] * (dscale * mkv);
+      const float r = sts[c * 512], z = sts[c * 512 + 128], n = sts[c * 512 + 256];
       const float dn_pre = dh * (1.f - z) * (1.f - n * n);
-      const float dz_pre = dh * (in_hp[c] * hp_on - n) * z * (1.f - z);
+      const float dz_pre = dh * (hps[c * 128] * hp_on - n) * z * (1.f - z);
       const float dhn = dn_pre * r;
-      const float dr_pre = dn_pre * in_hn[c] * r * (1.f - r);
+      const float dr_pre = dn_pre * sts[c * 512 + 384] * r * (1.f - r);
       dh_direct[c] = dh * z;
       const float gv[3] = {dr_pre, dz_pre, dhn};
 #pragma unroll
@@ -321,7 +345,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
         }
         __syncwarp();
       }
-      issue_loads(t + dt);            // land during the tensor-core phase
+      if (warp == 3 && s + BWD_RING < T && elect_one()) tma_issue(s + BWD_RING);   // slot fully read: refill
     }
   }
   fence_before_sync();
@@ -337,15 +361,19 @@ extern "C" int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b
   constexpr int NB = 16;
   cudaStream_t st = (cudaStream_t)stream;
   const int full = B / NB, rem = B % NB;
+  const size_t smem = (size_t)FWD_RING * NB * 512 * sizeof(float);
+  static int a0 = slu_set_smem((const void*)gru_fwd_tc_kernel<NB, true, true>, smem) | slu_set_smem((const void*)gru_fwd_tc_kernel<NB, false, true>, smem) |
+                  slu_set_smem((const void*)gru_fwd_tc_kernel<NB, true, false>, smem) | slu_set_smem((const void*)gru_fwd_tc_kernel<NB, false, false>, smem);
+  if (a0) return a0;
   if (full) {
     dim3 grid(full, 2);
-    if (stash) gru_fwd_tc_kernel<NB, true, true><<<grid, TC_THREADS, 0, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, stash);
-    else gru_fwd_tc_kernel<NB, false, true><<<grid, TC_THREADS, 0, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, nullptr);
+    if (stash) gru_fwd_tc_kernel<NB, true, true><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, stash);
+    else gru_fwd_tc_kernel<NB, false, true><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, nullptr);
   }
   if (rem) {                          // ragged last tile: predicated stores
     dim3 grid(1, 2);
-    if (stash) gru_fwd_tc_kernel<NB, true, false><<<grid, TC_THREADS, 0, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, stash);
-    else gru_fwd_tc_kernel<NB, false, false><<<grid, TC_THREADS, 0, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, nullptr);
+    if (stash) gru_fwd_tc_kernel<NB, true, false><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, stash);
+    else gru_fwd_tc_kernel<NB, false, false><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, nullptr);
   }
   SLU_CHECK_LAUNCH();
   return 0;
@@ -357,8 +385,11 @@ extern "C" int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const
   constexpr int NB = 16;
   cudaStream_t st = (cudaStream_t)stream;
   const int full = B / NB, rem = B % NB;
-  if (full) gru_bwd_tc_kernel<NB, true><<<dim3(full, 2), TC_THREADS, 0, st>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn);
-  if (rem) gru_bwd_tc_kernel<NB, false><<<dim3(1, 2), TC_THREADS, 0, st>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn);
+  const size_t smem = (size_t)BWD_RING * NB * 896 * sizeof(float);
+  static int a0 = slu_set_smem((const void*)gru_bwd_tc_kernel<NB, true>, smem) | slu_set_smem((const void*)gru_bwd_tc_kernel<NB, false>, smem);
+  if (a0) return a0;
+  if (full) gru_bwd_tc_kernel<NB, true><<<dim3(full, 2), TC_THREADS, smem, st>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn);
+  if (rem) gru_bwd_tc_kernel<NB, false><<<dim3(1, 2), TC_THREADS, smem, st>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn);
   SLU_CHECK_LAUNCH();
   return 0;
 }
