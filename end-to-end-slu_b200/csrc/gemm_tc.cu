@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         *reinterpret_cast<uint4*>(b_lo + off) = lo;
       }
     }
+    fence_async_smem();                   // before the prefetch: a proxy fence waits for this thread's outstanding loads
     if (i + 1 < nkb) prefetch(i + 1);
-    fence_async_smem();
     __syncthreads();
     // ---- one elected thread issues this k-block's MMAs (async: they overlap the staging of the next k-block)
     if (warp == 0) {

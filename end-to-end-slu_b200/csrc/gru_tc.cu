@@ -141,6 +141,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
     mbar_wait(&in_bar[s % FWD_RING], (uint32_t)((s / FWD_RING) & 1));       // this step's gx / mask rows have landed
     const float* gxs = in_ring + (s % FWD_RING) * SLOT + c0 * 384 + j;
     const float* mks = in_ring + (s % FWD_RING) * SLOT + NB * 384 + c0 * 128 + j;
+    float o_h[NC], o_out[NC], o_r[NC], o_z[NC], o_n[NC], o_hn[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       // r, z share one reciprocal:  r = (1+v)/((1+u)(1+v)), z = (1+u)/((1+u)(1+v)),  u = e^-pr, v = e^-pz
@@ -158,19 +159,14 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       *reinterpret_cast<__nv_bfloat16*>(h_hi_j + c * 16) = hh;
       *reinterpret_cast<__nv_bfloat16*>(h_lo_j + c * 16) = hl;
       const float val = mask ? hnew * mks[c * 128] : hnew;
-      const float outv = single ? val : 0.5f * (pend[c] + val);
+      o_out[c] = single ? val : 0.5f * (pend[c] + val);
       pend[c] = val;
-      if (ok[c]) {
-        yf_j[off[c]] = hnew;
-        if (STASH) {
-          float* sp = st_j + 4 * (long)off[c];
-          sp[0] = r; sp[128] = z; sp[256] = n; sp[384] = hn;
-        }
-        if (!first) yo_j[offo[c] + to] = outv;
-      }
-      off[c] += dt * 256;
+      o_h[c] = hnew;
+      if (STASH) { o_r[c] = r; o_z[c] = z; o_n[c] = n; o_hn[c] = hn; }
     }
     if (s + 1 < T) {
+      // Operand tile first: fence + barrier + MMA issue happen BEFORE this step's global stores are even issued, so the
+      // proxy fence has nothing outstanding to wait for and the stores drain while the tensor core works.
       fence_async_smem();          // h tile (generic-proxy stores) -> visible to the tensor core (async proxy)
       fence_before_sync();         // order this thread's tcgen05.ld before the barrier
       __syncthreads();
@@ -191,6 +187,18 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       }
       // slot s % FWD_RING has been read by every thread (barrier above): refill it for step s + FWD_RING
       if (warp == 3 && s + FWD_RING < T && elect_one()) tma_issue(s + FWD_RING);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (ok[c]) {
+        yf_j[off[c]] = o_h[c];
+        if (STASH) {
+          float* sp = st_j + 4 * (long)off[c];
+          sp[0] = o_r[c]; sp[128] = o_z[c]; sp[256] = o_n[c]; sp[384] = o_hn[c];
+        }
+        if (!first) yo_j[offo[c] + to] = o_out[c];
+      }
+      off[c] += dt * 256;
     }
   }
   fence_before_sync();
@@ -300,6 +308,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
     const float* hps = sl + NB * 512 + c0 * 128 + j;
     const float* dys = sl + NB * 640 + c0 * 128 + j;
     const float* mks = sl + NB * 768 + c0 * 128 + j;
+    float o_r[NC], o_z[NC], o_n[NC], o_hn[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const float mkv = mask ? mks[c * 128] : 1.f;
@@ -318,15 +327,10 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
         *reinterpret_cast<__nv_bfloat16*>(g_hi_j + (uint32_t)g * 16 * LBO + c * 16) = hh;
         *reinterpret_cast<__nv_bfloat16*>(g_lo_j + (uint32_t)g * 16 * LBO + c * 16) = hl;
       }
-      if (ok[c]) {
-        float* p = dgx_j + 3 * (long)off[c];
-        p[0] = dr_pre; p[128] = dz_pre; p[256] = dn_pre;
-        dhn_j[off[c]] = dhn;
-      }
-      off[c] += dt * 256;
+      o_r[c] = dr_pre; o_z[c] = dz_pre; o_n[c] = dn_pre; o_hn[c] = dhn;
     }
     if (s + 1 < T) {
-      fence_async_smem();
+      fence_async_smem();             // before any global store of this step is issued (see the forward kernel)
       fence_before_sync();
       __syncthreads();
       if (warp < 3) {                 // warp g reduces gate-row chunk g (K steps 8g..8g+7) into its own accumulator
@@ -346,6 +350,15 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
         __syncwarp();
       }
       if (warp == 3 && s + BWD_RING < T && elect_one()) tma_issue(s + BWD_RING);   // slot fully read: refill
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (ok[c]) {
+        float* p = dgx_j + 3 * (long)off[c];
+        p[0] = o_r[c]; p[128] = o_z[c]; p[256] = o_n[c];
+        dhn_j[off[c]] = o_hn[c];
+      }
+      off[c] += dt * 256;
     }
   }
   fence_before_sync();

@@ -12,10 +12,10 @@ from . import _lib
 H = 128
 # Which persistent-GRU kernel family runs the recurrence: "tc" = tcgen05 (weights stationary in TMEM),
 # "simt" = fp32 CUDA-core variant.  Both are sm_100a kernels of this library with identical contracts.
-GRU_IMPL = os.environ.get("SLU_GRU_IMPL", "simt")
+GRU_IMPL = os.environ.get("SLU_GRU_IMPL", "tc")
 # Dense contractions (x-projection, CNN tail, weight/input gradients): "tc" = this library's tcgen05 tap-GEMM,
 # "lib" = cuBLAS fp32 through torch (plain library GEMMs).
-GEMM_IMPL = os.environ.get("SLU_GEMM_IMPL", "lib")
+GEMM_IMPL = os.environ.get("SLU_GEMM_IMPL", "tc")
 
 
 def _f32(t):
