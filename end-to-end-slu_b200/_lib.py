@@ -23,6 +23,7 @@ SIGNATURES = {
     "slu_gru_bwd_simt": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
     "slu_gru_fwd_tc": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "slu_set_gru_precision": [_I],
     "slu_gemm_tc": [_P, _L, _L, _P, _L, _L, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "slu_presplit_bf16": [_P, _L, _L, _L, _I, _I, _I, _P, _P],
     "slu_tc_selftest": [_P, _P, _P, _I, _I, _P],
@@ -42,6 +43,7 @@ def load():
             fn.argtypes = argtypes
             fn.restype = _I
         _lib = lib
+        lib.slu_set_gru_precision(1 if os.environ.get("SLU_GRU_PRECISION", "bf16x3") == "fp16" else 0)
     return _lib
 
 

@@ -72,16 +72,18 @@ __device__ __forceinline__ void load8_kc(const float* base, int k0, int K, bool 
 // Strided form: 8 consecutive reduction indices k0..k0+7 at stride s_k; with shift != 0 the index is a frame number
 // inside utterances of T frames and is shifted (0 outside the utterance).
 __device__ __forceinline__ void load8_strided(const float* base, long s_k, int k0, int K, int T, int shift, bool ok, float* v) {
+  if (shift == 0) {
+    const float* p = base + (long)k0 * s_k;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    v[i] = 0.f;
-    const int k = k0 + i;
-    if (ok && k < K) {
-      if (shift == 0) v[i] = __ldg(base + (long)k * s_k);
-      else {
-        const int t = k % T + shift;
-        if (t >= 0 && t < T) v[i] = __ldg(base + (long)(k + shift) * s_k);
-      }
+    for (int i = 0; i < 8; ++i) v[i] = (ok && k0 + i < K) ? __ldg(p + (long)i * s_k) : 0.f;
+  } else {
+    int t = k0 % T + shift;                 // one modulo per chunk; frames are consecutive, wrap at the utterance end
+    const float* p = base + (long)(k0 + shift) * s_k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = (ok && k0 + i < K && t >= 0 && t < T) ? __ldg(p + (long)i * s_k) : 0.f;
+      ++t;
+      if (t - shift >= T) t -= T;
     }
   }
 }
@@ -121,11 +123,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   constexpr int A_CH = BM * (BK / 8) / THREADS;            // 2
   constexpr int B_TOT = BN * (BK / 8);
   constexpr int B_CH = (B_TOT + THREADS - 1) / THREADS;
-  int a_r[A_CH], a_kc[A_CH];
+  int a_r[A_CH], a_kc[A_CH], a_t[A_CH];
 #pragma unroll
   for (int u = 0; u < A_CH; ++u) {
     const int c = tid + u * THREADS;
     if (A_KC) { a_kc[u] = c & 3; a_r[u] = c >> 2; } else { a_r[u] = c % BM; a_kc[u] = c / BM; }
+    a_t[u] = (A_KC && p.T) ? (m0 + a_r[u]) % p.T : 0;      // frame of this row inside its utterance (tap boundaries)
   }
 
   // Register-prefetch pipeline: the global loads of k-block i+1 are issued right after k-block i has been
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         long row = m;
         if (p.taps > 1 || p.tap_pad) {
           const int sh = tap - p.tap_pad;
-          const int t = p.T ? (m % p.T) + sh : 0;
+          const int t = a_t[u] + sh;
           ok = ok && (p.T == 0 || (t >= 0 && t < p.T));
           row = (long)m + sh;
         }

@@ -23,6 +23,7 @@ constexpr int FWD_RING = 4, BWD_RING = 3;   // depth of the TMA input rings (ste
 
 // Load W rows (this thread's lane) into TMEM as split bf16 A-operands.  src: 3 blocks of [128][128] fp32 with
 // element (row j, k) at src[g*block_stride + j*row_stride + k*k_stride].
+template <int PASSES>
 __device__ __forceinline__ void load_weights_to_tmem(uint32_t tmem, uint32_t lane_base, const float* src, size_t block_stride,
                                                      size_t row_stride, size_t k_stride, int j, int half) {
   // `half` (0/1) splits the work between the two warps that share a lane quarter: half 0 -> k in [0,64), 1 -> [64,128)
@@ -32,7 +33,36 @@ __device__ __forceinline__ void load_weights_to_tmem(uint32_t tmem, uint32_t lan
 #pragma unroll 8
     for (int k = 0; k < 64; ++k) row[k] = __ldg(p + (size_t)k * k_stride);
     const uint32_t t_hi = tmem + lane_base + (uint32_t)(g * 64 + half * 32);
-    tmem_store_row_split(t_hi, t_hi + 192, row, 64);
+    if (PASSES == 3) tmem_store_row_split(t_hi, t_hi + 192, row, 64);
+    else tmem_store_row_f16(t_hi, row, 64);
+  }
+}
+
+// Operand copy of one activation value into the K-major B tile: bf16 hi + lo (3-pass) or a single fp16 (1-pass).
+template <int PASSES>
+__device__ __forceinline__ void store_operand(uint8_t* hi, uint8_t* lo, float v) {
+  if (PASSES == 3) {
+    const __nv_bfloat16 hh = __float2bfloat16_rn(v);
+    *reinterpret_cast<__nv_bfloat16*>(hi) = hh;
+    *reinterpret_cast<__nv_bfloat16*>(lo) = __float2bfloat16_rn(v - __bfloat162float(hh));
+  } else {
+    *reinterpret_cast<__half*>(hi) = __float2half_rn(v);
+  }
+}
+
+// The 8 K-steps of one [128 x NB] += A(tmem) . B(smem)^T product: 24 MMAs (bf16 hi*hi + hi*lo + lo*hi) or 8 (fp16).
+template <int PASSES>
+__device__ __forceinline__ void issue_product(uint32_t dacc, uint32_t a_hi, uint32_t a_lo, uint64_t bdesc_hi, uint64_t bdesc_lo,
+                                              uint32_t k_byte0, uint32_t lbo, uint32_t idesc) {
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const uint64_t bh = desc_advance(bdesc_hi, k_byte0 + kk * 2 * lbo);
+    mma_bf16_ts(dacc, a_hi + kk * 8, bh, idesc, kk > 0 ? 1u : 0u);
+    if (PASSES == 3) {
+      const uint64_t bl = desc_advance(bdesc_lo, k_byte0 + kk * 2 * lbo);
+      mma_bf16_ts(dacc, a_hi + kk * 8, bl, idesc, 1u);
+      mma_bf16_ts(dacc, a_lo + kk * 8, bh, idesc, 1u);
+    }
   }
 }
 
@@ -45,7 +75,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 // column, off[c] = (b*T + t) * 256, advanced by +-256 per step; gx = base + 3*off, stash = base + 4*off, ... so each
 // access costs a single IMAD.WIDE.  FULL = all NB rows of this CTA exist (stores unpredicated); the ragged last tile
 // is launched separately with FULL = false.
-template <int NB, bool STASH, bool FULL>
+template <int NB, bool STASH, bool FULL, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                   const float* __restrict__ mask, int B, int T, int ds, int tile0, float* __restrict__ y_full,
@@ -76,7 +106,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   fence_after_sync();
   const uint32_t tmem = tmem_base;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  load_weights_to_tmem(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, SLU_H, 1, j, warp >> 2);
+  load_weights_to_tmem<PASSES>(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, SLU_H, 1, j, warp >> 2);
 
   const float bhr = b_hh[d * SLU_G3 + j], bhz = b_hh[d * SLU_G3 + 128 + j], bhn = b_hh[d * SLU_G3 + 256 + j];
   const int T2 = (T + ds - 1) / ds;
@@ -113,7 +143,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   float hprev[NC], pend[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) { hprev[c] = 0.f; pend[c] = 0.f; }
-  const uint32_t idesc = idesc_bf16_f32(128, NB);
+  const uint32_t idesc = PASSES == 3 ? idesc_bf16_f32(128, NB) : idesc_f16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
   const uint64_t bdesc_hi = smem_desc(smem_u32(h_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(h_lo), LBO, 128);
   // byte offset of element (k = j) inside a k-chunk-major row b: (j/8)*LBO + b*16 + (j%8)*2
@@ -154,10 +184,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       const float n = 2.f * rcp_approx(1.f + ex2_approx(-2.f * kLog2e * (gxs[c * 384 + 256] + r * hn))) - 1.f;   // tanh; inf-safe
       const float hnew = n + z * (hprev[c] - n);
       hprev[c] = hnew;
-      const __nv_bfloat16 hh = __float2bfloat16_rn(hnew);
-      const __nv_bfloat16 hl = __float2bfloat16_rn(hnew - __bfloat162float(hh));
-      *reinterpret_cast<__nv_bfloat16*>(h_hi_j + c * 16) = hh;
-      *reinterpret_cast<__nv_bfloat16*>(h_lo_j + c * 16) = hl;
+      store_operand<PASSES>(h_hi_j + c * 16, h_lo_j + c * 16, hnew);
       const float val = mask ? hnew * mks[c * 128] : hnew;
       o_out[c] = single ? val : 0.5f * (pend[c] + val);
       pend[c] = val;
@@ -173,14 +200,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       if (warp < 3) {              // warps 0,1,2 (three different SM sub-partitions) issue gate r, z, n concurrently
         if (elect_one()) {
           fence_after_sync();
-          const uint32_t dacc = tmem + ACC_COL + warp * NB, a_hi = tmem + warp * 64, a_lo = a_hi + 192;
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t bh = desc_advance(bdesc_hi, kk * 2 * LBO), bl = desc_advance(bdesc_lo, kk * 2 * LBO);
-            mma_bf16_ts(dacc, a_hi + kk * 8, bh, idesc, kk > 0 ? 1u : 0u);
-            mma_bf16_ts(dacc, a_hi + kk * 8, bl, idesc, 1u);
-            mma_bf16_ts(dacc, a_lo + kk * 8, bh, idesc, 1u);
-          }
+          issue_product<PASSES>(tmem + ACC_COL + warp * NB, tmem + warp * 64, tmem + warp * 64 + 192, bdesc_hi, bdesc_lo, 0, LBO, idesc);
           mma_commit(&bar);
         }
         __syncwarp();
@@ -208,7 +228,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
 
 // Backward through time on tensor cores.  dh_{t-1}[k] += sum_row W_hh[row][k] * dG[row]:  M = 128 (k), K = 384 (gate rows),
 // N = NB.  W_hh^T (hi/lo) is stationary in TMEM (2 x 192 columns); dG = (dr, dz, dhn) is the shared-memory B tile.
-template <int NB, bool FULL>
+template <int NB, bool FULL, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, const float* __restrict__ y_full,
                   const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds, int tile0,
@@ -239,7 +259,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   const uint32_t tmem = tmem_base;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   // A[k=j][K index = row]: element (lane j, kk = g*128 + i) = W_hh[d][g*128 + i][j]  -> block stride 128*128, "row" stride 1, k stride 128
-  load_weights_to_tmem(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, 1, SLU_H, j, warp >> 2);
+  load_weights_to_tmem<PASSES>(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, 1, SLU_H, j, warp >> 2);
 
   const int T2 = (T + ds - 1) / ds;
   const int t_first = d ? 0 : T - 1, dt = d ? 1 : -1;       // walk time against the forward direction
@@ -274,7 +294,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   };
   if (warp == 3 && elect_one())
     for (int s = 0; s < BWD_RING && s < T; ++s) tma_issue(s);
-  const uint32_t idesc = idesc_bf16_f32(128, NB);
+  const uint32_t idesc = PASSES == 3 ? idesc_bf16_f32(128, NB) : idesc_f16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
   const uint64_t bdesc_hi = smem_desc(smem_u32(g_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(g_lo), LBO, 128);
   uint8_t* g_hi_j = g_hi + (uint32_t)(j >> 3) * LBO + (uint32_t)(j & 7) * 2 + c0 * 16;     // + gate*16*LBO + c*16
@@ -321,12 +341,8 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
       dh_direct[c] = dh * z;
       const float gv[3] = {dr_pre, dz_pre, dhn};
 #pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        const __nv_bfloat16 hh = __float2bfloat16_rn(gv[g]);
-        const __nv_bfloat16 hl = __float2bfloat16_rn(gv[g] - __bfloat162float(hh));
-        *reinterpret_cast<__nv_bfloat16*>(g_hi_j + (uint32_t)g * 16 * LBO + c * 16) = hh;
-        *reinterpret_cast<__nv_bfloat16*>(g_lo_j + (uint32_t)g * 16 * LBO + c * 16) = hl;
-      }
+      for (int g = 0; g < 3; ++g)
+        store_operand<PASSES>(g_hi_j + (uint32_t)g * 16 * LBO + c * 16, g_lo_j + (uint32_t)g * 16 * LBO + c * 16, gv[g]);
       o_r[c] = dr_pre; o_z[c] = dz_pre; o_n[c] = dn_pre; o_hn[c] = dhn;
     }
     if (s + 1 < T) {
@@ -336,15 +352,8 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
       if (warp < 3) {                 // warp g reduces gate-row chunk g (K steps 8g..8g+7) into its own accumulator
         if (elect_one()) {
           fence_after_sync();
-          const uint32_t dacc = tmem + ACC_COL + warp * NB, a_hi = tmem + warp * 64, a_lo = a_hi + 192;
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t koff = (uint32_t)(warp * 8 + kk) * 2 * LBO;
-            const uint64_t bh = desc_advance(bdesc_hi, koff), bl = desc_advance(bdesc_lo, koff);
-            mma_bf16_ts(dacc, a_hi + kk * 8, bh, idesc, kk > 0 ? 1u : 0u);
-            mma_bf16_ts(dacc, a_hi + kk * 8, bl, idesc, 1u);
-            mma_bf16_ts(dacc, a_lo + kk * 8, bh, idesc, 1u);
-          }
+          issue_product<PASSES>(tmem + ACC_COL + warp * NB, tmem + warp * 64, tmem + warp * 64 + 192, bdesc_hi, bdesc_lo,
+                                (uint32_t)(warp * 8) * 2 * LBO, LBO, idesc);
           mma_commit(&bar);
         }
         __syncwarp();
@@ -368,6 +377,25 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
 
 }  // namespace
 
+// 0 = bf16 hi/lo 3-pass (fp32-class accuracy, default), 1 = single fp16 pass (11-bit operands; logits stay inside the
+// 1e-3 tolerance, see oracle/precision_study.py) -- 3x fewer MMAs on the step-critical path.
+static int g_gru_mode = 0;
+extern "C" int slu_set_gru_precision(int mode) {
+  if (mode != 0 && mode != 1) return (int)cudaErrorInvalidValue;
+  g_gru_mode = mode;
+  return 0;
+}
+
+template <int NB, bool STASH, bool FULL>
+static void launch_fwd(dim3 grid, size_t smem, cudaStream_t st, const float* gx, const float* w_hh, const float* b_hh,
+                       const float* mask, int B, int T, int ds, int tile0, float* y_full, float* y_out, float* stash) {
+  static int a3 = slu_set_smem((const void*)gru_fwd_tc_kernel<NB, STASH, FULL, 3>, smem);
+  static int a1 = slu_set_smem((const void*)gru_fwd_tc_kernel<NB, STASH, FULL, 1>, smem);
+  (void)a3; (void)a1;
+  if (g_gru_mode == 0) gru_fwd_tc_kernel<NB, STASH, FULL, 3><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
+  else gru_fwd_tc_kernel<NB, STASH, FULL, 1><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
+}
+
 extern "C" int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T,
                               int ds, float* y_full, float* y_out, float* stash, void* stream) {
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (long)B * T * 1024 >= (1L << 31)) return (int)cudaErrorInvalidValue;
@@ -375,21 +403,26 @@ extern "C" int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b
   cudaStream_t st = (cudaStream_t)stream;
   const int full = B / NB, rem = B % NB;
   const size_t smem = (size_t)FWD_RING * NB * 512 * sizeof(float);
-  static int a0 = slu_set_smem((const void*)gru_fwd_tc_kernel<NB, true, true>, smem) | slu_set_smem((const void*)gru_fwd_tc_kernel<NB, false, true>, smem) |
-                  slu_set_smem((const void*)gru_fwd_tc_kernel<NB, true, false>, smem) | slu_set_smem((const void*)gru_fwd_tc_kernel<NB, false, false>, smem);
-  if (a0) return a0;
   if (full) {
-    dim3 grid(full, 2);
-    if (stash) gru_fwd_tc_kernel<NB, true, true><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, stash);
-    else gru_fwd_tc_kernel<NB, false, true><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, nullptr);
+    if (stash) launch_fwd<NB, true, true>(dim3(full, 2), smem, st, gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, stash);
+    else launch_fwd<NB, false, true>(dim3(full, 2), smem, st, gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, nullptr);
   }
   if (rem) {                          // ragged last tile: predicated stores
-    dim3 grid(1, 2);
-    if (stash) gru_fwd_tc_kernel<NB, true, false><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, stash);
-    else gru_fwd_tc_kernel<NB, false, false><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, nullptr);
+    if (stash) launch_fwd<NB, true, false>(dim3(1, 2), smem, st, gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, stash);
+    else launch_fwd<NB, false, false>(dim3(1, 2), smem, st, gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, nullptr);
   }
   SLU_CHECK_LAUNCH();
   return 0;
+}
+
+template <int NB, bool FULL>
+static void launch_bwd(dim3 grid, size_t smem, cudaStream_t st, const float* dy_out, const float* mask, const float* y_full,
+                       const float* stash, const float* w_hh, int B, int T, int ds, int tile0, float* dgx, float* dhn) {
+  static int a3 = slu_set_smem((const void*)gru_bwd_tc_kernel<NB, FULL, 3>, smem);
+  static int a1 = slu_set_smem((const void*)gru_bwd_tc_kernel<NB, FULL, 1>, smem);
+  (void)a3; (void)a1;
+  if (g_gru_mode == 0) gru_bwd_tc_kernel<NB, FULL, 3><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn);
+  else gru_bwd_tc_kernel<NB, FULL, 1><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn);
 }
 
 extern "C" int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
@@ -399,10 +432,8 @@ extern "C" int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const
   cudaStream_t st = (cudaStream_t)stream;
   const int full = B / NB, rem = B % NB;
   const size_t smem = (size_t)BWD_RING * NB * 896 * sizeof(float);
-  static int a0 = slu_set_smem((const void*)gru_bwd_tc_kernel<NB, true>, smem) | slu_set_smem((const void*)gru_bwd_tc_kernel<NB, false>, smem);
-  if (a0) return a0;
-  if (full) gru_bwd_tc_kernel<NB, true><<<dim3(full, 2), TC_THREADS, smem, st>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn);
-  if (rem) gru_bwd_tc_kernel<NB, false><<<dim3(1, 2), TC_THREADS, smem, st>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn);
+  if (full) launch_bwd<NB, true>(dim3(full, 2), smem, st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn);
+  if (rem) launch_bwd<NB, false>(dim3(1, 2), smem, st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn);
   SLU_CHECK_LAUNCH();
   return 0;
 }

@@ -11,6 +11,7 @@
 //   * D (accumulator) lives in TMEM: lane = M row (0..127), column = N index (fp32).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace tc05 {
@@ -82,6 +83,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 // Instruction descriptor: kind::f16, A=B=bf16 (K-major), D=f32, dense.
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 with fp16 operands (11-bit significand), D=f32: the single-pass mode of the GRU recurrence.
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---- MMA issue / commit (single thread) ------------------------------------------------------------
@@ -179,6 +185,20 @@ __device__ __forceinline__ void tmem_store_row_split(uint32_t t_hi, uint32_t t_l
     for (int i = 0; i < 8; ++i) split2(row[c0 + 2 * i], row[c0 + 2 * i + 1], hi[i], lo[i]);
     tmem_st8(t_hi + c0 / 2, hi);
     tmem_st8(t_lo + c0 / 2, lo);
+  }
+  tmem_st_wait();
+}
+
+// fp16 single-pass variant of tmem_store_row_split: one packed fp16 A-operand.
+__device__ __forceinline__ void tmem_store_row_f16(uint32_t t_a, const float* row, int n) {
+  for (int c0 = 0; c0 < n; c0 += 16) {
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __half2 h = __floats2half2_rn(row[c0 + 2 * i], row[c0 + 2 * i + 1]);
+      v[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    tmem_st8(t_a + c0 / 2, v);
   }
   tmem_st_wait();
 }

@@ -127,6 +127,11 @@ def conv_block(x, weight, bias, slope):
     return conv_block_nlc(x, weight, bias, slope)
 
 
+def set_gru_precision(mode):
+    """'bf16x3' (default, fp32-class) or 'fp16' (single pass) operand format of the tcgen05 recurrence."""
+    _lib.load().slu_set_gru_precision({"bf16x3": 0, "fp16": 1}[mode])
+
+
 class SincFrontend(torch.autograd.Function):
     """SincLayer conv (80 filters, 401 taps, stride 80, pad 200) + Abs + MaxPool1d(2, ceil).
     Reference: models.py:77-110, 163-168, 205.  Output is NLC [B, L1, 80]."""

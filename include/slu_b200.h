@@ -57,6 +57,10 @@ int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const 
 int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
                    const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, void* stream);
 
+/* Operand format of the tcgen05 recurrence: 0 = bf16 hi/lo 3-pass (fp32-class accuracy, default), 1 = one fp16 pass
+ * (11-bit operands: 3x fewer MMAs per step; intent logits stay within the 1e-3 parity tolerance). */
+int slu_set_gru_precision(int mode);
+
 /* Dense "tap-GEMM" on tcgen05 (fp32 in/out, 3-pass bf16 split, fp32 accumulate in TMEM) -- replaces the cuBLAS / cuDNN
  * calls behind nn.GRU's input projection (models.py:232/262/686), nn.Conv1d (models.py:200) and their autograd:
  *   C[m][n] (+)= sum_tap sum_k A(m,tap,k) * B(n,tap,k) (+ bias[n]) (LeakyReLU if act==1)

@@ -172,6 +172,31 @@ def test_conv_block_tc_fwd_bwd(pkg, monkeypatch, B, T, Cin, Cout):
     assert rel_err(wc.grad.cpu(), w.grad) < GRAD_TOL and rel_err(bc.grad.cpu(), b.grad) < GRAD_TOL
 
 
+@pytest.mark.parametrize("B,T,I,ds", [(16, 40, 256, 2), (5, 23, 60, 1)])
+def test_bigru_fp16_single_pass_mode(pkg, monkeypatch, B, T, I, ds):
+    """Optional operand format of the recurrence (one fp16 pass): looser per-layer tolerance, same semantics."""
+    monkeypatch.setattr(pkg.ops, "GRU_IMPL", "tc")
+    pkg.ops.set_gru_precision("fp16")
+    try:
+        rs = np.random.RandomState(B + T)
+        gru = torch.nn.GRU(I, 128, batch_first=True, bidirectional=True)
+        x = torch.from_numpy(rs.standard_normal((B, T, I)).astype(np.float32)).requires_grad_(True)
+        y = R.downsample(R.bigru(x, {"g." + k: v for k, v in gru.named_parameters()}, "g"), "avg" if ds == 2 else "none", ds)
+        gy = torch.from_numpy(rs.standard_normal(tuple(y.shape)).astype(np.float32))
+        y.backward(gy)
+        gru_c = torch.nn.GRU(I, 128, batch_first=True, bidirectional=True).cuda()
+        gru_c.load_state_dict(gru.state_dict())
+        xc = x.detach().cuda().requires_grad_(True)
+        yc = pkg.ops.bigru(xc, gru_c, None, ds)
+        assert rel_err(yc.detach().cpu(), y.detach()) < 2e-3
+        yc.backward(gy.cuda())
+        assert rel_err(xc.grad.cpu(), x.grad) < 1e-2
+        for k, v in gru_c.named_parameters():
+            assert rel_err(v.grad.cpu(), gru.get_parameter(k).grad) < 1e-2, k
+    finally:
+        pkg.ops.set_gru_precision("bf16x3")
+
+
 def test_conv_block_nlc(pkg):
     rs = np.random.RandomState(5)
     x = torch.from_numpy(rs.standard_normal((3, 80, 37)).astype(np.float32))

@@ -46,6 +46,21 @@ def test_known_answer_testwav_on_gpu():
     assert feats.shape == (1, 23, 256) and rel_err(feats.detach().cpu(), g["features"]) < LOGIT_TOL / 10
 
 
+def test_fp16_recurrence_mode_meets_the_logit_tolerance():
+    """Single-pass fp16 operands in the GRU recurrence: trained checkpoint + test.wav stay within the north-star 1e-3."""
+    pkg = importlib.import_module("end-to-end-slu_b200")
+    g = golden("golden_testwav.npz")
+    m = gpu_model(ckpt_params())
+    pkg.ops.set_gru_precision("fp16")
+    try:
+        logits, pred = m.predict_intents(load_test_wav())
+        err = rel_err(logits.detach().cpu(), g["logits"])
+        assert err < LOGIT_TOL, err
+        assert pred.tolist() == [[1, 2, 1]]
+    finally:
+        pkg.ops.set_gru_precision("bf16x3")
+
+
 @pytest.mark.parametrize("tag", ["small", "ragged", "odd"])
 def test_loss_logits_grads_match_reference_goldens(tag):
     g = golden("golden_synth_%s.npz" % tag)
