@@ -17,24 +17,29 @@
 namespace {
 using namespace tc05;
 
-constexpr int TC_THREADS = 256;       // 8 warps: warp w owns TMEM lanes 32*(w%4).., batch columns (w/4)*NB/2 ..
+constexpr int TC_THREADS = 512;       // 16 warps: warp w owns TMEM lanes 32*(w%4).., batch columns (w/4)*NC ..
 constexpr uint32_t ACC_COL = 384;     // accumulators start after the 384 weight columns
-constexpr int FWD_RING = 4, BWD_RING = 3;   // depth of the TMA input rings (steps in flight)
+constexpr int FWD_RING = 4, BWD_RING = 3;
+// Optional phase timing (developer tool, tools/gru_phase_timing.py): when set, CTA (0,0) accumulates clock64() deltas of the
+// step phases for threads 0 and 128 into this buffer [2][8].
+__device__ long long* g_phase_clk = nullptr;
+#define PHASE(i) do { if (dbg) { const long long now_ = clock64(); dbg[i] += now_ - tprev_; tprev_ = now_; } } while (0)   // depth of the TMA input rings (steps in flight)
 
 // Load W rows (this thread's lane) into TMEM as split bf16 A-operands.  src: 3 blocks of [128][128] fp32 with
 // element (row j, k) at src[g*block_stride + j*row_stride + k*k_stride].
 template <int PASSES>
 __device__ __forceinline__ void load_weights_to_tmem(uint32_t tmem, uint32_t lane_base, const float* src, size_t block_stride,
                                                      size_t row_stride, size_t k_stride, int j, int half) {
-  // `half` (0/1) splits the work between the two warps that share a lane quarter: half 0 -> k in [0,64), 1 -> [64,128)
+  // `half` (0..PARTS-1) splits the K range between the warps that share a lane quarter
+  constexpr int PARTS = TC_THREADS / 128, KW = 128 / PARTS;
   for (int g = 0; g < 3; ++g) {
-    float row[64];
-    const float* p = src + g * block_stride + (size_t)j * row_stride + (size_t)(half * 64) * k_stride;
+    float row[KW];
+    const float* p = src + g * block_stride + (size_t)j * row_stride + (size_t)(half * KW) * k_stride;
 #pragma unroll 8
-    for (int k = 0; k < 64; ++k) row[k] = __ldg(p + (size_t)k * k_stride);
-    const uint32_t t_hi = tmem + lane_base + (uint32_t)(g * 64 + half * 32);
-    if (PASSES == 3) tmem_store_row_split(t_hi, t_hi + 192, row, 64);
-    else tmem_store_row_f16(t_hi, row, 64);
+    for (int k = 0; k < KW; ++k) row[k] = __ldg(p + (size_t)k * k_stride);
+    const uint32_t t_hi = tmem + lane_base + (uint32_t)(g * 64 + half * (KW / 2));
+    if (PASSES == 3) tmem_store_row_split(t_hi, t_hi + 192, row, KW);
+    else tmem_store_row_f16(t_hi, row, KW);
   }
 }
 
@@ -80,7 +85,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                   const float* __restrict__ mask, int B, int T, int ds, int tile0, float* __restrict__ y_full,
                   float* __restrict__ y_out, float* __restrict__ stash) {
-  constexpr int NC = NB / 2;                         // batch columns per thread
+  constexpr int NC = NB * 128 / TC_THREADS;         // batch columns per thread
   constexpr uint32_t LBO = NB * 16 + 16;             // padded: conflict-free 2-byte operand stores
   __shared__ __align__(128) uint8_t h_tile[2 * 16 * LBO];   // [hi | lo] x 16 k-chunks x (NB rows x 16 B + pad)
   __shared__ uint64_t bar, in_bar[FWD_RING];
@@ -150,18 +155,22 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   uint8_t* h_hi_j = h_hi + (uint32_t)(j >> 3) * LBO + (uint32_t)(j & 7) * 2 + c0 * 16;
   uint8_t* h_lo_j = h_hi_j + 16 * LBO;
 
+  long long* dbg = (g_phase_clk && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 128)) ? g_phase_clk + (tid ? 8 : 0) : nullptr;
+  long long tprev_ = clock64();
   for (int s = 0; s < T; ++s) {
     const int t = t_first + dt * s;
     float ar[NC], az[NC], an[NC];
+    PHASE(7);
     if (s == 0) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) ar[c] = az[c] = an[c] = 0.f;       // h_{-1} = 0
     } else {
       mbar_wait(&bar, (uint32_t)((s - 1) & 1));
       fence_after_sync();
-      if (NC == 8) { tmem_ld8(acc_addr, ar); tmem_ld8(acc_addr + NB, az); tmem_ld8(acc_addr + 2 * NB, an); }
-      else { tmem_ld16(acc_addr, ar); tmem_ld16(acc_addr + NB, az); tmem_ld16(acc_addr + 2 * NB, an); }
+      PHASE(0);                      // mbarrier wait for the MMAs
+      tmem_ld<NC>(acc_addr, ar); tmem_ld<NC>(acc_addr + NB, az); tmem_ld<NC>(acc_addr + 2 * NB, an);
       tmem_ld_wait();
+      PHASE(1);                      // tcgen05.ld
     }
     // Downsample(avg,2) bookkeeping, uniform per step: `single` = odd tail frame (divisor 1, ceil_mode),
     // `first` = first visited frame of its pair (value parked in `pend`), otherwise the pair is completed.
@@ -169,6 +178,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
     const bool first = !single && ((t & 1) == (d ? 1 : 0));
     const int to = (ds == 2 ? (t >> 1) : t) * 256;
     mbar_wait(&in_bar[s % FWD_RING], (uint32_t)((s / FWD_RING) & 1));       // this step's gx / mask rows have landed
+    PHASE(2);                        // TMA ring wait
     const float* gxs = in_ring + (s % FWD_RING) * SLOT + c0 * 384 + j;
     const float* mks = in_ring + (s % FWD_RING) * SLOT + NB * 384 + c0 * 128 + j;
     float o_h[NC], o_out[NC], o_r[NC], o_z[NC], o_n[NC], o_hn[NC];
@@ -191,12 +201,15 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       o_h[c] = hnew;
       if (STASH) { o_r[c] = r; o_z[c] = z; o_n[c] = n; o_hn[c] = hn; }
     }
+    PHASE(3);                        // gate math + operand stores
     if (s + 1 < T) {
       // Operand tile first: fence + barrier + MMA issue happen BEFORE this step's global stores are even issued, so the
       // proxy fence has nothing outstanding to wait for and the stores drain while the tensor core works.
       fence_async_smem();          // h tile (generic-proxy stores) -> visible to the tensor core (async proxy)
       fence_before_sync();         // order this thread's tcgen05.ld before the barrier
+      PHASE(4);                    // fences
       __syncthreads();
+      PHASE(5);                    // barrier
       if (warp < 3) {              // warps 0,1,2 (three different SM sub-partitions) issue gate r, z, n concurrently
         if (elect_one()) {
           fence_after_sync();
@@ -205,6 +218,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
         }
         __syncwarp();
       }
+      PHASE(6);                    // MMA issue
       // slot s % FWD_RING has been read by every thread (barrier above): refill it for step s + FWD_RING
       if (warp == 3 && s + FWD_RING < T && elect_one()) tma_issue(s + FWD_RING);
     }
@@ -233,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, const float* __restrict__ y_full,
                   const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds, int tile0,
                   float* __restrict__ dgx, float* __restrict__ dhn_out) {
-  constexpr int NC = NB / 2;
+  constexpr int NC = NB * 128 / TC_THREADS;
   constexpr uint32_t LBO = NB * 16 + 16;
   __shared__ __align__(128) uint8_t g_tile[2 * 48 * LBO];   // [hi | lo] x 48 k-chunks (384 gate rows)
   __shared__ uint64_t bar, in_bar[BWD_RING];
@@ -313,8 +327,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
       mbar_wait(&bar, (uint32_t)((s - 1) & 1));
       fence_after_sync();
       float r1[NC], r2[NC];                 // three partial accumulators (one per gate-row chunk / issuing warp)
-      if (NC == 8) { tmem_ld8(acc_addr, rec); tmem_ld8(acc_addr + NB, r1); tmem_ld8(acc_addr + 2 * NB, r2); }
-      else { tmem_ld16(acc_addr, rec); tmem_ld16(acc_addr + NB, r1); tmem_ld16(acc_addr + 2 * NB, r2); }
+      tmem_ld<NC>(acc_addr, rec); tmem_ld<NC>(acc_addr + NB, r1); tmem_ld<NC>(acc_addr + 2 * NB, r2);
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < NC; ++c) rec[c] += r1[c] + r2[c];
@@ -376,6 +389,10 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
 }
 
 }  // namespace
+
+extern "C" int slu_debug_gru_phase_clocks(long long* buf) {   // developer tool; buf = 16 zeroed int64 on the device, or NULL
+  return (int)cudaMemcpyToSymbol(g_phase_clk, &buf, sizeof(buf));
+}
 
 // 0 = bf16 hi/lo 3-pass (fp32-class accuracy, default), 1 = single fp16 pass (11-bit operands; logits stay inside the
 // 1e-3 tolerance, see oracle/precision_study.py) -- 3x fewer MMAs on the step-critical path.

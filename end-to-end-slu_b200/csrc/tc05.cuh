@@ -132,6 +132,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v) {
+  static_assert(N == 4 || N == 8 || N == 16, "tmem_ld width");
+  if (N == 4) tmem_ld4(taddr, v); else if (N == 8) tmem_ld8(taddr, v); else tmem_ld16(taddr, v);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- fp32 -> (bf16 hi, bf16 lo) split helpers --------------------------------------------------------

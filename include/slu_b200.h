@@ -61,6 +61,9 @@ int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_f
  * (11-bit operands: 3x fewer MMAs per step; intent logits stay within the 1e-3 parity tolerance). */
 int slu_set_gru_precision(int mode);
 
+/* Developer tool: accumulate clock64() per step phase of slu_gru_fwd_tc (CTA 0, threads 0 and 128) into buf[2][8]. */
+int slu_debug_gru_phase_clocks(long long* buf);
+
 /* Dense "tap-GEMM" on tcgen05 (fp32 in/out, 3-pass bf16 split, fp32 accumulate in TMEM) -- replaces the cuBLAS / cuDNN
  * calls behind nn.GRU's input projection (models.py:232/262/686), nn.Conv1d (models.py:200) and their autograd:
  *   C[m][n] (+)= sum_tap sum_k A(m,tap,k) * B(n,tap,k) (+ bias[n]) (LeakyReLU if act==1)
