@@ -210,9 +210,19 @@ def main():
         flops = sum(2 * 2 * t * 384 * 128 * B for t in GRU_T)
         sec = kern[name]["ms_per_step"] * 1e-3
         ach = flops / sec / 1e12
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture (layer 0, B=256)
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                traffic = json.load(f).get(name, {}).get("bytes_per_launch")
+        except Exception:
+            pass
         roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s",
-                    "frac": ach / tf_sust, "traffic": None, "peak_source": how + " bf16 sustained (kernel timed inside a step)",
-                    "note": "5 launches/step; flops = 2 dirs * T_l * 2*384*128 * B summed over layers"}
+                    "frac": ach / tf_sust, "traffic": traffic, "peak_source": how + " bf16 sustained (kernel timed inside a step)",
+                    "traffic_note": "bytes of the layer-0 launch (T=400, the largest of the 5); its algorithmic bytes are 996 MB",
+                    "executed_tflops": 3 * ach if pkg.ops.GRU_IMPL == "tc" else ach,
+                    "note": "persistent-GRU forward, 5 launches/step summed; algorithmic flops = 2 dirs * T_l * 2*384*128 * B over the "
+                            "5 layers (h.W_hh only; the bf16 hi/lo 3-pass split executes 3x that on the tensor core). The recurrence is "
+                            "latency-bound at 32 CTAs: see DESIGN.md section 4"}
     sinc_names = [k for k in prof if k.startswith("slu_sincconv_fwd")]
     if sinc_names:
         name = sinc_names[0]
@@ -238,7 +248,7 @@ def main():
                                                  "what": "reference-structured port (cuDNN GRU, cuDNN conv, 80x conv loop), wall clock"}
         line = {"metric": "utterances_per_sec_train_step", "value": value, "unit": "utt/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split on tensor cores where used)",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tensor-core contractions as bf16 hi/lo 3-pass split, fp32 accumulate)",
                 "data": "synthetic", "impl": "ours",
                 "config": {"workload": "experiments/unfreeze_all_layers.cfg SLU train step (all layers unfrozen, dropout 0.5), "
                                        "4 s @16 kHz synthetic utterances", "batch_per_gpu": B, "global_batch": B * world,
