@@ -19,10 +19,12 @@ SIGNATURES = {
     "slu_sinc_filters_bwd": [_P, _P, _P, _P, _P, _P],
     "slu_sincconv_fwd_simt": [_P, _P, _I, _I, _P, _P, _P],
     "slu_sincconv_bwd_simt": [_P, _P, _P, _I, _I, _P, _P],
+    "slu_sincconv_fwd_tc": [_P, _P, _I, _I, _P, _P, _P, _P],
+    "slu_sincconv_bwd_tc": [_P, _P, _P, _I, _I, _P, _P],
     "slu_gru_fwd_simt": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
-    "slu_gru_bwd_simt": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "slu_gru_bwd_simt": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_gru_fwd_tc": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
-    "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_set_gru_precision": [_I],
     "slu_debug_gru_phase_clocks": [_P],
     "slu_gemm_tc": [_P, _L, _L, _P, _L, _L, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],

@@ -38,6 +38,10 @@ struct GemmParams {
   int split_k;                // gridDim.z; >1 => atomic accumulation into a zeroed C
   int act;                    // 0 none, 1 LeakyReLU(slope)
   float slope;
+  // SincNet front end (AMODE 2/3, BMODE 3, EPI 1): rows / reduction indices are frames m = b*L0p + t of the waveform x[B][Ts]
+  int Ts, L0, L0p, L1;        // samples per utterance, conv frames, L0 rounded up to even, pooled frames
+  const float* gy;            // [B][L1][80] gradient of the pooled output (AMODE 3)
+  uint8_t* route;             // [B][L1][80] pooling route bits (written by EPI 1, read by AMODE 3)
 };
 
 constexpr int BM = 128, BK = 32, STAGES = 2, THREADS = 256;
@@ -88,9 +92,29 @@ __device__ __forceinline__ void load8_strided(const float* base, long s_k, int k
   }
 }
 
-// BMODE: 0 = fp32 K-contiguous, 1 = fp32 strided, 2 = pre-split bf16 image
-template <int BN, bool A_KC, int BMODE>
+// SincConv forward A operand: A(m=(b,t), tap, k) = x[b][80*(t+tap) + k - 200]  (zero outside [0,Ts), for pad frames t>=L0
+// and for k >= 80).  The waveform itself is the [frames][80] matrix: no im2col.
+__device__ __forceinline__ void load8_sinc_rows(const float* xb, int idx0, int k0, int Ts, bool row_ok, float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  if (!row_ok || k0 >= SLU_STRIDE) return;
+  const float* p = xb + idx0;
+  if (idx0 >= 0 && idx0 + 8 <= Ts && k0 + 8 <= SLU_STRIDE && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (k0 + i < SLU_STRIDE && idx0 + i >= 0 && idx0 + i < Ts) v[i] = __ldg(p + i);
+  }
+}
+
+// AMODE: 0 = fp32 K-contiguous rows (+ row-shift taps), 1 = fp32 strided (frames), 2 = sinc frames of the waveform,
+//        3 = routed pooled-gradient (sinc backward);  BMODE: 0 = fp32 K-contiguous, 1 = fp32 strided, 2 = pre-split bf16
+//        image, 3 = waveform samples per frame (sinc backward);  EPI: 0 = bias/act/store or split-K atomics, 1 = abs+maxpool2+route
+template <int BN, int AMODE, int BMODE, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  constexpr bool A_KC = (AMODE == 0);
   using S = Smem<BN>;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t empty_bar[STAGES], acc_bar;
@@ -127,8 +151,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 #pragma unroll
   for (int u = 0; u < A_CH; ++u) {
     const int c = tid + u * THREADS;
-    if (A_KC) { a_kc[u] = c & 3; a_r[u] = c >> 2; } else { a_r[u] = c % BM; a_kc[u] = c / BM; }
+    if (AMODE == 0 || AMODE == 2) { a_kc[u] = c & 3; a_r[u] = c >> 2; } else { a_r[u] = c % BM; a_kc[u] = c / BM; }
     a_t[u] = (A_KC && p.T) ? (m0 + a_r[u]) % p.T : 0;      // frame of this row inside its utterance (tap boundaries)
+    if (AMODE == 2) a_t[u] = (m0 + a_r[u]) % p.L0p;        // sinc: frame t; the utterance is (m0 + r) / L0p
   }
 
   // Register-prefetch pipeline: the global loads of k-block i+1 are issued right after k-block i has been
@@ -142,7 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 #pragma unroll
     for (int u = 0; u < A_CH; ++u) {
       const int m = m0 + a_r[u];
-      if (A_KC) {
+      if (AMODE == 0) {
         bool ok = m < p.M;
         long row = m;
         if (p.taps > 1 || p.tap_pad) {
@@ -152,8 +177,26 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           row = (long)m + sh;
         }
         load8_kc(p.A + row * p.a_sm, k0 + a_kc[u] * 8, p.K, ok, va[u]);
-      } else {
+      } else if (AMODE == 1) {
         load8_strided(p.A + (long)m * p.a_sm, p.a_sk, k0 + a_kc[u] * 8, p.K, p.T ? p.T : 1, p.a_kshift, m < p.M, va[u]);
+      } else if (AMODE == 2) {
+        const int t = a_t[u], b = (m - t) / p.L0p;
+        load8_sinc_rows(p.A + (long)b * p.Ts, SLU_STRIDE * (t + tap) + k0 + a_kc[u] * 8 - SLU_PAD, k0 + a_kc[u] * 8, p.Ts,
+                        m < p.M && t < p.L0, va[u]);
+      } else {   // AMODE 3: A(m = filter c, k = frame (b,t)) = pooled-output gradient routed back through max-pool and abs
+        const int kf = k0 + a_kc[u] * 8;
+        int b = kf / p.L0p, t = kf - b * p.L0p;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float g = 0.f;
+          if (m < p.M && kf + i < p.K && t < p.L0) {
+            const long o = ((long)b * p.L1 + (t >> 1)) * SLU_NFILT + m;
+            const uint8_t rb = p.route[o];
+            if ((rb & 1) == (t & 1) && !(rb & 4)) { g = __ldg(p.gy + o); if (rb & 2) g = -g; }
+          }
+          va[u][i] = g;
+          if (++t == p.L0p) { t = 0; ++b; }
+        }
       }
     }
 #pragma unroll
@@ -174,7 +217,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         const bool ok = (c < B_TOT) && (n < p.N);
         const float* base = p.B + (long)n * p.b_sn + (long)tap * p.b_stap;
         if (BMODE == 0) load8_kc(base, k0 + kc * 8, p.K, ok, vb[u]);
-        else load8_strided(base, p.b_sk, k0 + kc * 8, p.K, p.T ? p.T : 1, p.b_kshift, ok, vb[u]);
+        else if (BMODE == 1) load8_strided(base, p.b_sk, k0 + kc * 8, p.K, p.T ? p.T : 1, p.b_kshift, ok, vb[u]);
+        else {   // BMODE 3: B(n = tap sample 0..400, k = frame (b,t)) = x[b][80 t + n - 200]
+          const int kf = k0 + kc * 8;
+          int b = kf / p.L0p, t = kf - b * p.L0p;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = SLU_STRIDE * t + n - SLU_PAD;
+            vb[u][i] = (ok && kf + i < p.K && t < p.L0 && idx >= 0 && idx < p.Ts) ? __ldg(p.B + (long)b * p.Ts + idx) : 0.f;
+            if (++t == p.L0p) { t = 0; ++b; }
+          }
+        }
       }
     }
   };
@@ -199,7 +252,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       const int c = tid + u * THREADS;
       if (c < B_TOT) {
         int r, kc;
-        if (BMODE == 1) { r = c % BN; kc = c / BN; } else { kc = c & 3; r = c >> 2; }
+        if (BMODE == 1 || BMODE == 3) { r = c % BN; kc = c / BN; } else { kc = c & 3; r = c >> 2; }
         uint4 hi, lo;
         if (BMODE == 2) { hi = ib_hi[u]; lo = ib_lo[u]; } else split8(vb[u], hi, lo);
         const uint32_t off = (uint32_t)kc * S::LBO_B + (uint32_t)r * 16;
@@ -256,6 +309,25 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       __syncwarp();
       const int n = n0 + c0 + lane;
       const bool n_ok = n < p.N;
+      if (EPI == 1) {          // |.| + max over frame pairs (2j, 2j+1) + route bits; rows are frames m = b*L0p + t, t even first
+        int m = m0 + q * 32;
+        int b = m / p.L0p, t = m - b * p.L0p;
+        for (int r = 0; r < 32; r += 2) {
+          if (m + r < p.M && t < p.L0 && n_ok) {
+            const float v0 = tr[r * 33 + lane], v1 = tr[(r + 1) * 33 + lane];
+            const float a0 = fabsf(v0), a1 = (t + 1 < p.L0) ? fabsf(v1) : -1.f;
+            const int sel = a1 > a0 ? 1 : 0;
+            const float v = sel ? v1 : v0;
+            const long o = ((long)b * p.L1 + (t >> 1)) * SLU_NFILT + n;
+            p.C[o] = sel ? a1 : a0;
+            if (p.route) p.route[o] = (uint8_t)(sel | ((v < 0.f) ? 2 : 0) | ((v == 0.f) ? 4 : 0));
+          }
+          t += 2;
+          if (t >= p.L0p) { t -= p.L0p; ++b; }
+        }
+        __syncwarp();
+        continue;
+      }
       const float bias = (p.bias && n_ok && blockIdx.z == 0) ? __ldg(p.bias + n) : 0.f;
       float* dst = p.C + (long)(m0 + q * 32) * p.ldc + n;
       const int rows = min(32, p.M - (m0 + q * 32));
@@ -283,33 +355,33 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   if (warp == 0) tmem_dealloc(tmem, tmem_cols(BN));
 }
 
-template <int BN, bool A_KC, int BMODE>
+template <int BN, int AMODE, int BMODE, int EPI>
 int launch(const GemmParams& p, cudaStream_t stream) {
   const size_t smem = Smem<BN>::TOTAL;
-  static int attr = slu_set_smem((const void*)gemm_tc_kernel<BN, A_KC, BMODE>, smem);
+  static int attr = slu_set_smem((const void*)gemm_tc_kernel<BN, AMODE, BMODE, EPI>, smem);
   if (attr) return attr;
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, p.split_k);
-  gemm_tc_kernel<BN, A_KC, BMODE><<<grid, THREADS, smem, stream>>>(p);
+  gemm_tc_kernel<BN, AMODE, BMODE, EPI><<<grid, THREADS, smem, stream>>>(p);
   return (int)cudaGetLastError();
 }
 
-template <bool A_KC, int BMODE>
+template <int AMODE, int BMODE>
 int dispatch_bn(const GemmParams& p, cudaStream_t stream) {
-  if (p.N <= 64) return launch<64, A_KC, BMODE>(p, stream);
-  if (p.N <= 128) return launch<128, A_KC, BMODE>(p, stream);
-  return launch<256, A_KC, BMODE>(p, stream);
+  if (p.N <= 64) return launch<64, AMODE, BMODE, 0>(p, stream);
+  if (p.N <= 128) return launch<128, AMODE, BMODE, 0>(p, stream);
+  return launch<256, AMODE, BMODE, 0>(p, stream);
 }
 
 // fp32 strided weights -> bf16 hi / lo images [2][taps][N][Kp] (zero padded to Kp, a multiple of 32)
 __global__ void presplit_kernel(const float* __restrict__ W, long sn, long sk, long stap, int taps, int N, int K, int Kp,
-                                __nv_bfloat16* __restrict__ img) {
+                                int row_len, __nv_bfloat16* __restrict__ img) {
   const size_t total = (size_t)taps * N * Kp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % Kp);
     const size_t tn = i / Kp;
     const int n = (int)(tn % N), tap = (int)(tn / N);
     float v = 0.f;
-    if (k < K) v = W[(long)n * sn + (long)k * sk + (long)tap * stap];
+    if (k < K && (row_len == 0 || (long)k * sk + (long)tap * stap < row_len)) v = W[(long)n * sn + (long)k * sk + (long)tap * stap];
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     img[i] = h;
     img[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -320,13 +392,17 @@ __global__ void presplit_kernel(const float* __restrict__ W, long sn, long sk, l
 
 // Pre-split a (strided) fp32 weight operand into the bf16 hi/lo image the GEMM's B side can copy verbatim.
 // img must hold 2 * taps * N * Kp bf16 values, Kp = K rounded up to a multiple of 32.
+static int presplit(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream);
 extern "C" int slu_presplit_bf16(const float* W, long sn, long sk, long stap, int taps, int N, int K, void* img, void* stream) {
+  return presplit(W, sn, sk, stap, taps, N, K, 0, img, stream);
+}
+static int presplit(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream) {
   if (taps <= 0 || N <= 0 || K <= 0) return (int)cudaErrorInvalidValue;
   const int Kp = (K + 31) / 32 * 32;
   const size_t total = (size_t)taps * N * Kp;
   int grid = (int)((total + 255) / 256);
   if (grid > 1184) grid = 1184;
-  presplit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, sn, sk, stap, taps, N, K, Kp, (__nv_bfloat16*)img);
+  presplit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, sn, sk, stap, taps, N, K, Kp, row_len, (__nv_bfloat16*)img);
   return (int)cudaGetLastError();
 }
 
@@ -340,9 +416,41 @@ extern "C" int slu_gemm_tc(const float* A, long a_sm, long a_sk, const float* B,
   p.Bimg = (const __nv_bfloat16*)b_img; p.Kp = (K + 31) / 32 * 32; p.bias = bias;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.taps = taps; p.tap_pad = tap_pad; p.T = T;
   p.a_kshift = a_kshift; p.b_kshift = b_kshift; p.split_k = split_k; p.act = act; p.slope = slope;
+  p.Ts = p.L0 = p.L0p = p.L1 = 0; p.gy = nullptr; p.route = nullptr;
   const bool a_kc = (a_sk == 1);
   cudaStream_t st = (cudaStream_t)stream;
-  if (b_img) return a_kc ? dispatch_bn<true, 2>(p, st) : dispatch_bn<false, 2>(p, st);
-  if (b_sk == 1) return a_kc ? dispatch_bn<true, 0>(p, st) : dispatch_bn<false, 0>(p, st);
-  return a_kc ? dispatch_bn<true, 1>(p, st) : dispatch_bn<false, 1>(p, st);
+  if (b_img) return a_kc ? dispatch_bn<0, 2>(p, st) : dispatch_bn<1, 2>(p, st);
+  if (b_sk == 1) return a_kc ? dispatch_bn<0, 0>(p, st) : dispatch_bn<1, 0>(p, st);
+  return a_kc ? dispatch_bn<0, 1>(p, st) : dispatch_bn<1, 1>(p, st);
+}
+
+// ---- SincNet front end on the tensor core -----------------------------------------------------------------------
+// Forward: out[B][L1][80] = maxpool2(|conv1d(x, W, stride 80, pad 200)|) as a 6-tap GEMM over the waveform viewed as
+// [frames][80] (M = B*L0p frames, N = 80 filters, K = 80 per tap), abs + pool + route in the epilogue.
+// `img` = scratch for the pre-split bank: 2*6*80*96 bf16 values.
+extern "C" int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T, float* out, uint8_t* route, void* img, void* stream) {
+  if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
+  const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2, L0p = 2 * L1;
+  if ((long)B * L0p >= (1L << 31)) return (int)cudaErrorInvalidValue;
+  int e = presplit(W, SLU_NTAPS, 1, SLU_STRIDE, 6, SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // bank[c][80a + k], 0 beyond tap 400
+  if (e) return e;
+  GemmParams p{};
+  p.A = x; p.Bimg = (const __nv_bfloat16*)img; p.Kp = 96; p.C = out; p.ldc = SLU_NFILT;
+  p.M = B * L0p; p.N = SLU_NFILT; p.K = SLU_STRIDE; p.taps = 6; p.split_k = 1;
+  p.Ts = T; p.L0 = L0; p.L0p = L0p; p.L1 = L1; p.route = route;
+  return launch<128, 2, 2, 1>(p, (cudaStream_t)stream);
+}
+
+// Backward: dW[80][401] = sum over frames (b,t) of g0[b][t][c] * xpad[b][80 t + n], g0 = dL/dout routed through max-pool / abs:
+// one split-K GEMM, M = 80 filters, N = 401 taps, K = B*L0p frames; dW must be zero-filled by the caller.
+extern "C" int slu_sincconv_bwd_tc(const float* x, const float* gy, const uint8_t* route, int B, int T, float* dW, void* stream) {
+  if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
+  const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2, L0p = 2 * L1;
+  if ((long)B * L0p >= (1L << 31)) return (int)cudaErrorInvalidValue;
+  GemmParams p{};
+  p.B = x; p.C = dW; p.ldc = SLU_NTAPS; p.M = SLU_NFILT; p.N = SLU_NTAPS; p.K = B * L0p; p.taps = 1;
+  p.Ts = T; p.L0 = L0; p.L0p = L0p; p.L1 = L1; p.gy = gy; p.route = const_cast<uint8_t*>(route);
+  const int kb = (p.K + BK - 1) / BK;
+  p.split_k = kb < 148 ? kb : 148;
+  return launch<256, 3, 3, 0>(p, (cudaStream_t)stream);
 }

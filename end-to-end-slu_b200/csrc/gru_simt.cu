@@ -125,7 +125,7 @@ gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, con
 __global__ void __launch_bounds__(512, 1)
 gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, const float* __restrict__ y_full,
                const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds,
-               float* __restrict__ dgx, float* __restrict__ dhn_out) {
+               float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ dbias) {
   extern __shared__ float4 smem4[];
   float4* Wt = smem4;                                          // [c*128 + k] = W[4c..4c+3][k], c < 96
   float* gs = reinterpret_cast<float*>(smem4 + 96 * 128);      // [2][BT][384]
@@ -162,6 +162,7 @@ gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask,
   if (T > 0) load_step(d ? 0 : T - 1, cur_in);
   __syncthreads();
   float dh_rec = 0.f;
+  float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_hn = 0.f;
   int cur = 0;
   for (int s = 0; s < T; ++s) {
     const int t = d ? s : T - 1 - s;
@@ -179,6 +180,7 @@ gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask,
       float* p = dgx + bt * 768 + d * SLU_G3 + j;
       p[0] = dr_pre; p[128] = dz_pre; p[256] = dn_pre;
       dhn_out[bt * 256 + d * SLU_H + j] = dhn;
+      sb_r += dr_pre; sb_z += dz_pre; sb_n += dn_pre; sb_hn += dhn;
     }
     __syncthreads();
     const float4* g4 = reinterpret_cast<const float4*>(gs + cur * BT * SLU_G3);
@@ -197,6 +199,10 @@ gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask,
     dh_rec = reduce_scatter4(acc, q) + dh * z;
     cur_in = nxt_in;
     cur ^= 1;
+  }
+  if (dbias) {
+    float* pb = dbias + d * 512 + j;
+    atomicAdd(pb, sb_r); atomicAdd(pb + 128, sb_z); atomicAdd(pb + 256, sb_n); atomicAdd(pb + 384, sb_hn);
   }
 }
 
@@ -217,13 +223,13 @@ extern "C" int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float*
 }
 
 extern "C" int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                                const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, void* stream) {
+                                const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* dbias, void* stream) {
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2)) return (int)cudaErrorInvalidValue;
   const size_t smem = W_SMEM + 2 * BT * SLU_G3 * sizeof(float);
   static int a1 = slu_set_smem((const void*)gru_bwd_kernel, smem);
   if (a1) return a1;
   dim3 grid((B + BT - 1) / BT, 2);
-  gru_bwd_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn);
+  gru_bwd_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, dbias);
   SLU_CHECK_LAUNCH();
   return 0;
 }

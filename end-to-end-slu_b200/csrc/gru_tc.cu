@@ -246,7 +246,7 @@ template <int NB, bool FULL, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, const float* __restrict__ y_full,
                   const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds, int tile0,
-                  float* __restrict__ dgx, float* __restrict__ dhn_out) {
+                  float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ dbias) {
   constexpr int NC = NB * 128 / TC_THREADS;
   constexpr uint32_t LBO = NB * 16 + 16;
   __shared__ __align__(128) uint8_t g_tile[2 * 48 * LBO];   // [hi | lo] x 48 k-chunks (384 gate rows)
@@ -316,6 +316,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   float dh_direct[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) dh_direct[c] = 0.f;
+  float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_hn = 0.f;    // bias gradients: sums over this thread's columns and all steps
 
   for (int s = 0; s < T; ++s) {
     const int t = t_first + dt * s;
@@ -357,6 +358,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
       for (int g = 0; g < 3; ++g)
         store_operand<PASSES>(g_hi_j + (uint32_t)g * 16 * LBO + c * 16, g_lo_j + (uint32_t)g * 16 * LBO + c * 16, gv[g]);
       o_r[c] = dr_pre; o_z[c] = dz_pre; o_n[c] = dn_pre; o_hn[c] = dhn;
+      if (ok[c]) { sb_r += dr_pre; sb_z += dz_pre; sb_n += dn_pre; sb_hn += dhn; }
     }
     if (s + 1 < T) {
       fence_async_smem();             // before any global store of this step is issued (see the forward kernel)
@@ -382,6 +384,10 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
       }
       off[c] += dt * 256;
     }
+  }
+  if (dbias) {     // dbias[d][4][128]: sums of dr, dz, dn (-> b_ih and b_hh r/z rows), dhn (-> b_hh n rows)
+    float* pb = dbias + d * 512 + j;
+    atomicAdd(pb, sb_r); atomicAdd(pb + 128, sb_z); atomicAdd(pb + 256, sb_n); atomicAdd(pb + 384, sb_hn);
   }
   fence_before_sync();
   __syncthreads();
@@ -434,23 +440,23 @@ extern "C" int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b
 
 template <int NB, bool FULL>
 static void launch_bwd(dim3 grid, size_t smem, cudaStream_t st, const float* dy_out, const float* mask, const float* y_full,
-                       const float* stash, const float* w_hh, int B, int T, int ds, int tile0, float* dgx, float* dhn) {
+                       const float* stash, const float* w_hh, int B, int T, int ds, int tile0, float* dgx, float* dhn, float* dbias) {
   static int a3 = slu_set_smem((const void*)gru_bwd_tc_kernel<NB, FULL, 3>, smem);
   static int a1 = slu_set_smem((const void*)gru_bwd_tc_kernel<NB, FULL, 1>, smem);
   (void)a3; (void)a1;
-  if (g_gru_mode == 0) gru_bwd_tc_kernel<NB, FULL, 3><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn);
-  else gru_bwd_tc_kernel<NB, FULL, 1><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn);
+  if (g_gru_mode == 0) gru_bwd_tc_kernel<NB, FULL, 3><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
+  else gru_bwd_tc_kernel<NB, FULL, 1><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
 }
 
 extern "C" int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                              const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, void* stream) {
+                              const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* dbias, void* stream) {
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (long)B * T * 1024 >= (1L << 31)) return (int)cudaErrorInvalidValue;
   constexpr int NB = 16;
   cudaStream_t st = (cudaStream_t)stream;
   const int full = B / NB, rem = B % NB;
   const size_t smem = (size_t)BWD_RING * NB * 896 * sizeof(float);
-  if (full) launch_bwd<NB, true>(dim3(full, 2), smem, st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn);
-  if (rem) launch_bwd<NB, false>(dim3(1, 2), smem, st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn);
+  if (full) launch_bwd<NB, true>(dim3(full, 2), smem, st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn, dbias);
+  if (rem) launch_bwd<NB, false>(dim3(1, 2), smem, st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn, dbias);
   SLU_CHECK_LAUNCH();
   return 0;
 }

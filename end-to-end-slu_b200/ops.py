@@ -16,6 +16,8 @@ GRU_IMPL = os.environ.get("SLU_GRU_IMPL", "tc")
 # Dense contractions (x-projection, CNN tail, weight/input gradients): "tc" = this library's tcgen05 tap-GEMM,
 # "lib" = cuBLAS fp32 through torch (plain library GEMMs).
 GEMM_IMPL = os.environ.get("SLU_GEMM_IMPL", "tc")
+# SincConv: "tc" = tcgen05 6-tap framing GEMM, "simt" = fp32 CUDA-core kernel.
+SINC_IMPL = os.environ.get("SLU_SINC_IMPL", "tc")
 
 
 def _f32(t):
@@ -149,7 +151,12 @@ class SincFrontend(torch.autograd.Function):
         out = torch.empty(B, L1, 80, device=x.device, dtype=torch.float32)
         need = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         route = torch.empty(B, L1, 80, device=x.device, dtype=torch.uint8) if need else None
-        _lib.call("slu_sincconv_fwd_simt", _lib.ptr(x), _lib.ptr(W), B, T, _lib.ptr(out), _lib.ptr(route), _lib.stream())
+        if SINC_IMPL == "tc":
+            img = torch.empty(2 * 6 * 80 * 96, device=x.device, dtype=torch.bfloat16)
+            _lib.call("slu_sincconv_fwd_tc", _lib.ptr(x), _lib.ptr(W), B, T, _lib.ptr(out), _lib.ptr(route), img.data_ptr(),
+                      _lib.stream())
+        else:
+            _lib.call("slu_sincconv_fwd_simt", _lib.ptr(x), _lib.ptr(W), B, T, _lib.ptr(out), _lib.ptr(route), _lib.stream())
         if need:
             ctx.save_for_backward(x, b1, band, route)
         return out
@@ -159,8 +166,12 @@ class SincFrontend(torch.autograd.Function):
         x, b1, band, route = ctx.saved_tensors
         B, T = x.shape
         gy = _f32(gy)
-        dW = torch.empty(80, 401, device=x.device, dtype=torch.float32)
-        _lib.call("slu_sincconv_bwd_simt", _lib.ptr(x), _lib.ptr(gy), _lib.ptr(route), B, T, _lib.ptr(dW), _lib.stream())
+        if SINC_IMPL == "tc":
+            dW = torch.zeros(80, 401, device=x.device, dtype=torch.float32)
+            _lib.call("slu_sincconv_bwd_tc", _lib.ptr(x), _lib.ptr(gy), _lib.ptr(route), B, T, _lib.ptr(dW), _lib.stream())
+        else:
+            dW = torch.empty(80, 401, device=x.device, dtype=torch.float32)
+            _lib.call("slu_sincconv_bwd_simt", _lib.ptr(x), _lib.ptr(gy), _lib.ptr(route), B, T, _lib.ptr(dW), _lib.stream())
         d_b1 = torch.empty(80, device=x.device, dtype=torch.float64)
         d_band = torch.empty(80, device=x.device, dtype=torch.float64)
         _lib.call("slu_sinc_filters_bwd", _lib.ptr(b1), _lib.ptr(band), _lib.ptr(dW), _lib.ptr(d_b1), _lib.ptr(d_band),
@@ -225,8 +236,9 @@ class BiGRU(torch.autograd.Function):
         gy = _f32(gy)
         dgx = torch.empty(B, T, 768, device=dev, dtype=torch.float32)
         dhn = torch.empty(B, T, 256, device=dev, dtype=torch.float32)
+        dbias = torch.zeros(2, 4, H, device=dev, dtype=torch.float32)          # sums of dr, dz, dn, dhn per direction
         _lib.call("slu_gru_bwd_" + GRU_IMPL, _lib.ptr(gy), _lib.ptr(mask), _lib.ptr(y_full), _lib.ptr(stash), _lib.ptr(w_hh_cat),
-                  B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), _lib.stream())
+                  B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), _lib.ptr(dbias), _lib.stream())
         ni = ctx.needs_input_grad
         dgx2 = dgx.view(B * T, 768)
         dx = matmul_nn(dgx2, w_ih_cat.contiguous()).view(B, T, I) if ni[0] else None
@@ -234,8 +246,6 @@ class BiGRU(torch.autograd.Function):
         if any(ni[1:9]):
             x2 = x.view(B * T, I)
             dw_ih = matmul_tn(dgx2, x2)                                         # [768, I]
-            db_ih = dgx2.sum(0)
-            db_hn = dhn.view(B * T, 256).sum(0)
             if GEMM_IMPL == "tc":
                 R = B * T
                 dw_hh_cat = torch.zeros(2, 384, H, device=dev, dtype=torch.float32)
@@ -255,11 +265,10 @@ class BiGRU(torch.autograd.Function):
                     hprev = torch.cat([zero, hd[:, :-1]], 1) if d == 0 else torch.cat([hd[:, 1:], zero], 1)
                     gd = torch.cat([dgx[:, :, d * 384:d * 384 + 256], dhn[:, :, d * H:(d + 1) * H]], 2).reshape(B * T, 384)
                     dw_hh = gd.t() @ hprev.reshape(B * T, H)
-                db_hh = torch.cat([db_ih[d * 384:d * 384 + 256], db_hn[d * H:(d + 1) * H]])
                 grads[4 * d + 0] = dw_ih[d * 384:(d + 1) * 384]
                 grads[4 * d + 1] = dw_hh
-                grads[4 * d + 2] = db_ih[d * 384:(d + 1) * 384]
-                grads[4 * d + 3] = db_hh
+                grads[4 * d + 2] = dbias[d, :3].reshape(384)                                   # b_ih: dr, dz, dn
+                grads[4 * d + 3] = torch.cat([dbias[d, :2].reshape(256), dbias[d, 3]])         # b_hh: dr, dz, dhn
         return (dx, *grads, None, None)
 
 

@@ -33,6 +33,12 @@ int slu_sincconv_fwd_simt(const float* x, const float* W, int B, int T, float* o
  * needs no gradient. */
 int slu_sincconv_bwd_simt(const float* x, const float* gy, const uint8_t* route, int B, int T, float* dW, void* stream);
 
+/* Same contracts on tcgen05 tensor cores: the waveform is viewed as a [frames][80] matrix and the 401-tap filter as 6
+ * accumulating K=80 taps (no im2col), bf16 hi/lo 3-pass split, abs + max-pool + route bits in the GEMM epilogue.
+ * `img` = scratch for the pre-split bank (2*6*80*96 bf16 values).  slu_sincconv_bwd_tc needs dW zero-filled (split-K atomics). */
+int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T, float* out, uint8_t* route, void* img, void* stream);
+int slu_sincconv_bwd_tc(const float* x, const float* gy, const uint8_t* route, int B, int T, float* dW, void* stream);
+
 /* Persistent bidirectional GRU recurrence (h0 = 0) with fused gate non-linearities, Dropout mask multiply and
  * Downsample -- replaces nn.GRU (_VF.gru / cuDNN RNN) at models.py:232/262/686 plus RNNSelect :138-149,
  * Dropout :246/276/700 and Downsample :26-46.
@@ -46,16 +52,17 @@ int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float* b_hh, cons
                      float* y_full, float* y_out, float* stash, void* stream);
 /* Backward through time -- replaces _cudnn_rnn_backward.  Emits dgx[B][T][768] (gradient wrt gx) and
  * dhn[B][T][256] (gradient wrt the n-gate's recurrent pre-activation); the weight/input gradients are dense
- * GEMMs over these. */
+ * GEMMs over these.  dbias[2][4][128] (caller-zeroed, may be NULL) accumulates the bias gradients: sums over (b,t) of
+ * dr, dz, dn (b_ih; and b_hh for r, z) and dhn (b_hh, n rows). */
 int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                     const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, void* stream);
+                     const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* dbias, void* stream);
 
 /* Same contracts as slu_gru_fwd_simt / slu_gru_bwd_simt, executed on tcgen05 tensor cores: W_hh (bf16 hi+lo) stationary
  * in tensor memory, h / dG as the shared-memory B operand, 3-pass bf16 split with fp32 accumulation in TMEM. */
 int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T, int ds,
                    float* y_full, float* y_out, float* stash, void* stream);
 int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                   const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, void* stream);
+                   const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* dbias, void* stream);
 
 /* Operand format of the tcgen05 recurrence: 0 = bf16 hi/lo 3-pass (fp32-class accuracy, default), 1 = one fp16 pass
  * (11-bit operands: 3x fewer MMAs per step; intent logits stay within the 1e-3 parity tolerance). */

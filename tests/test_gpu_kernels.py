@@ -76,8 +76,10 @@ def test_sinc_filters_fwd_bwd(pkg):
         assert e1 < 1e-3 and e2 < 1e-3, (src, e1, e2)
 
 
-@pytest.mark.parametrize("B,T", [(1, 57585), (3, 8000), (2, 1234), (2, 81), (1, 1), (5, 64000)])
-def test_sinc_frontend_fwd_bwd(pkg, B, T):
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("B,T", [(1, 57585), (3, 8000), (2, 1234), (2, 81), (1, 1), (5, 64000), (3, 12345)])
+def test_sinc_frontend_fwd_bwd(pkg, monkeypatch, impl, B, T):
+    monkeypatch.setattr(pkg.ops, "SINC_IMPL", impl)
     p = ckpt_params() if T == 57585 else R.synthetic_params()
     x = load_test_wav() if T == 57585 else R.synthetic_batch(B, T, seed=T)[0]
     b1 = p[R.P + "phoneme_layers.0.filt_b1"].clone().requires_grad_(True)
