@@ -186,16 +186,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       } else {   // AMODE 3: A(m = filter c, k = frame (b,t)) = pooled-output gradient routed back through max-pool and abs
         const int kf = k0 + a_kc[u] * 8;
         int b = kf / p.L0p, t = kf - b * p.L0p;
+        uint8_t rb[8]; float gv[8]; bool okf[8]; int par[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {      // all 16 loads are issued unconditionally (clamped address), selected afterwards
+          okf[i] = m < p.M && kf + i < p.K && t < p.L0;
+          const long o = okf[i] ? ((long)b * p.L1 + (t >> 1)) * SLU_NFILT + m : 0;
+          rb[i] = p.route[o];
+          gv[i] = __ldg(p.gy + o);
+          par[i] = t & 1;
+          if (++t == p.L0p) { t = 0; ++b; }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float g = 0.f;
-          if (m < p.M && kf + i < p.K && t < p.L0) {
-            const long o = ((long)b * p.L1 + (t >> 1)) * SLU_NFILT + m;
-            const uint8_t rb = p.route[o];
-            if ((rb & 1) == (t & 1) && !(rb & 4)) { g = __ldg(p.gy + o); if (rb & 2) g = -g; }
-          }
-          va[u][i] = g;
-          if (++t == p.L0p) { t = 0; ++b; }
+          const bool take = okf[i] && ((rb[i] & 1) == par[i]) && !(rb[i] & 4);
+          va[u][i] = take ? ((rb[i] & 2) ? -gv[i] : gv[i]) : 0.f;
         }
       }
     }
@@ -222,9 +226,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           const int kf = k0 + kc * 8;
           int b = kf / p.L0p, t = kf - b * p.L0p;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 8; ++i) {      // unconditional (clamped) loads, zeroed afterwards: keeps the 8 loads in flight together
             const int idx = SLU_STRIDE * t + n - SLU_PAD;
-            vb[u][i] = (ok && kf + i < p.K && t < p.L0 && idx >= 0 && idx < p.Ts) ? __ldg(p.B + (long)b * p.Ts + idx) : 0.f;
+            const bool v_ok = ok && kf + i < p.K && t < p.L0 && idx >= 0 && idx < p.Ts;
+            const float val = __ldg(p.B + (v_ok ? (long)b * p.Ts + idx : 0));
+            vb[u][i] = v_ok ? val : 0.f;
             if (++t == p.L0p) { t = 0; ++b; }
           }
         }

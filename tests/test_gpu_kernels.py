@@ -77,6 +77,34 @@ def test_sinc_filters_fwd_bwd(pkg):
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("B,T", [(2, 8000), (3, 12345), (2, 1234)])
+def test_sincconv_filter_gradient_direct(pkg, impl, B, T):
+    """dL/dW of the fused conv+abs+pool against autograd over the same bank (isolates the conv backward kernel)."""
+    rs = np.random.RandomState(T)
+    x = torch.from_numpy((0.1 * rs.standard_normal((B, T))).astype(np.float32))
+    W0 = torch.from_numpy(rs.standard_normal((80, 401)).astype(np.float32))
+    W = (W0 + W0.flip(1)).requires_grad_(True)          # sinc banks are symmetric; the simt kernel relies on it
+    ref = torch.nn.functional.max_pool1d(torch.abs(torch.nn.functional.conv1d(x.unsqueeze(1), W.unsqueeze(1), stride=80, padding=200)),
+                                         2, ceil_mode=True).transpose(1, 2)
+    gy = torch.from_numpy(rs.standard_normal(tuple(ref.shape)).astype(np.float32))
+    ref.backward(gy)
+    L1 = ref.shape[1]
+    xd, Wd, gyd = x.cuda(), W.detach().cuda(), gy.cuda().contiguous()
+    out = torch.empty(B, L1, 80, device="cuda"); route = torch.empty(B, L1, 80, device="cuda", dtype=torch.uint8)
+    dW = torch.zeros(80, 401, device="cuda")
+    if impl == "tc":
+        img = torch.empty(2 * 6 * 80 * 96, device="cuda", dtype=torch.bfloat16)
+        pkg._lib.call("slu_sincconv_fwd_tc", xd.data_ptr(), Wd.data_ptr(), B, T, out.data_ptr(), route.data_ptr(), img.data_ptr(), pkg._lib.stream())
+        pkg._lib.call("slu_sincconv_bwd_tc", xd.data_ptr(), gyd.data_ptr(), route.data_ptr(), B, T, dW.data_ptr(), pkg._lib.stream())
+    else:
+        pkg._lib.call("slu_sincconv_fwd_simt", xd.data_ptr(), Wd.data_ptr(), B, T, out.data_ptr(), route.data_ptr(), pkg._lib.stream())
+        pkg._lib.call("slu_sincconv_bwd_simt", xd.data_ptr(), gyd.data_ptr(), route.data_ptr(), B, T, dW.data_ptr(), pkg._lib.stream())
+    assert rel_err(out.cpu(), ref.detach()) < FWD_TOL
+    err = rel_err(dW.cpu(), W.grad)
+    assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("B,T", [(1, 57585), (3, 8000), (2, 1234), (2, 81), (1, 1), (5, 64000), (3, 12345)])
 def test_sinc_frontend_fwd_bwd(pkg, monkeypatch, impl, B, T):
     monkeypatch.setattr(pkg.ops, "SINC_IMPL", impl)
@@ -96,7 +124,9 @@ def test_sinc_frontend_fwd_bwd(pkg, monkeypatch, impl, B, T):
     assert b1g.grad.dtype == torch.float64
     scale = max(b1.grad.abs().max().item(), band.grad.abs().max().item())
     for got, ref_g in ((b1g.grad.cpu(), b1.grad), (bandg.grad.cpu(), band.grad)):
-        assert (got - ref_g).abs().max().item() < GRAD_TOL * scale + 1e-4, ((got - ref_g).abs().max().item(), scale)
+        # the analytic filter chain cancels heavily: the 2^-17 split error of the tcgen05 dW is amplified to <~0.5 %
+        tol = (5e-3 if impl == "tc" else GRAD_TOL) * scale + 1e-4
+        assert (got - ref_g).abs().max().item() < tol, ((got - ref_g).abs().max().item(), scale)
 
 
 @pytest.mark.parametrize("gemm", ["lib", "tc"])
