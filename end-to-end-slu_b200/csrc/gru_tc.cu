@@ -80,25 +80,26 @@ constexpr float kLog2e = 1.4426950408889634f;
 // column, off[c] = (b*T + t) * 256, advanced by +-256 per step; gx = base + 3*off, stash = base + 4*off, ... so each
 // access costs a single IMAD.WIDE.  FULL = all NB rows of this CTA exist (stores unpredicated); the ragged last tile
 // is launched separately with FULL = false.
-template <int NB, bool STASH, bool FULL, int PASSES>
+template <int NB, int NR, bool STASH, bool FULL, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                   const float* __restrict__ mask, int B, int T, int ds, int tile0, float* __restrict__ y_full,
                   float* __restrict__ y_out, float* __restrict__ stash) {
-  constexpr int NC = NB * 128 / TC_THREADS;         // batch columns per thread
+  constexpr int NC = NR * 128 / TC_THREADS;         // batch columns per thread (NR real rows; the MMA is N = NB wide)
   constexpr uint32_t LBO = NB * 16 + 16;             // padded: conflict-free 2-byte operand stores
   __shared__ __align__(128) uint8_t h_tile[2 * 16 * LBO];   // [hi | lo] x 16 k-chunks x (NB rows x 16 B + pad)
   __shared__ uint64_t bar, in_bar[FWD_RING];
   __shared__ uint32_t tmem_base;
   extern __shared__ __align__(128) float in_ring[];         // FWD_RING x { gx [NB][384], mask [NB][128] }  (TMA-filled)
-  constexpr int SLOT = NB * 512;                            // floats per ring slot
+  constexpr int SLOT = NR * 512;                            // floats per ring slot
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
-  const int d = blockIdx.y, b0 = (tile0 + blockIdx.x) * NB;
+  const int d = blockIdx.y, b0 = (tile0 + blockIdx.x) * NR;
   const int j = (warp & 3) * 32 + lane;              // hidden unit == TMEM lane
   const int c0 = (warp >> 2) * NC;                   // first batch column of this thread
   uint8_t* h_hi = h_tile;
   uint8_t* h_lo = h_tile + 16 * LBO;
 
+  for (int i = tid; i < (int)(2 * 16 * LBO / 4); i += TC_THREADS) reinterpret_cast<uint32_t*>(h_tile)[i] = 0u;   // pad rows stay 0
   if (tid == 0) {
     mbar_init(&bar, 3);                                      // 3 gate-issuer warps commit per step
     for (int r = 0; r < FWD_RING; ++r) mbar_init(&in_bar[r], 1);
@@ -135,11 +136,11 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   auto tma_issue = [&](int s) {
     const int t = t_first + dt * s, slot = s % FWD_RING;
     float* dst = in_ring + slot * SLOT;
-    mbar_arrive_expect_tx(&in_bar[slot], NB * (1536u + (mask ? 512u : 0u)));
-    for (int c = 0; c < NB; ++c) {
+    mbar_arrive_expect_tx(&in_bar[slot], NR * (1536u + (mask ? 512u : 0u)));
+    for (int c = 0; c < NR; ++c) {
       const long bt = (long)min(b0 + c, B - 1) * T + t;
       tma_load_1d(dst + c * 384, gx + bt * 768 + d * SLU_G3, 1536, &in_bar[slot]);
-      if (mask) tma_load_1d(dst + NB * 384 + c * 128, mask + bt * 256 + d * SLU_H, 512, &in_bar[slot]);
+      if (mask) tma_load_1d(dst + NR * 384 + c * 128, mask + bt * 256 + d * SLU_H, 512, &in_bar[slot]);
     }
   };
   if (warp == 3 && elect_one())
@@ -180,7 +181,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
     mbar_wait(&in_bar[s % FWD_RING], (uint32_t)((s / FWD_RING) & 1));       // this step's gx / mask rows have landed
     PHASE(2);                        // TMA ring wait
     const float* gxs = in_ring + (s % FWD_RING) * SLOT + c0 * 384 + j;
-    const float* mks = in_ring + (s % FWD_RING) * SLOT + NB * 384 + c0 * 128 + j;
+    const float* mks = in_ring + (s % FWD_RING) * SLOT + NR * 384 + c0 * 128 + j;
     float o_h[NC], o_out[NC], o_r[NC], o_z[NC], o_n[NC], o_hn[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -242,24 +243,25 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
 
 // Backward through time on tensor cores.  dh_{t-1}[k] += sum_row W_hh[row][k] * dG[row]:  M = 128 (k), K = 384 (gate rows),
 // N = NB.  W_hh^T (hi/lo) is stationary in TMEM (2 x 192 columns); dG = (dr, dz, dhn) is the shared-memory B tile.
-template <int NB, bool FULL, int PASSES>
+template <int NB, int NR, bool FULL, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, const float* __restrict__ y_full,
                   const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds, int tile0,
                   float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ dbias) {
-  constexpr int NC = NB * 128 / TC_THREADS;
+  constexpr int NC = NR * 128 / TC_THREADS;
   constexpr uint32_t LBO = NB * 16 + 16;
   __shared__ __align__(128) uint8_t g_tile[2 * 48 * LBO];   // [hi | lo] x 48 k-chunks (384 gate rows)
   __shared__ uint64_t bar, in_bar[BWD_RING];
   __shared__ uint32_t tmem_base;
   extern __shared__ __align__(128) float in_ring[];         // BWD_RING x { stash [NB][512], h_prev, dy, mask [NB][128] each }
-  constexpr int SLOT = NB * 896;
+  constexpr int SLOT = NR * 896;
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
-  const int d = blockIdx.y, b0 = (tile0 + blockIdx.x) * NB;
+  const int d = blockIdx.y, b0 = (tile0 + blockIdx.x) * NR;
   const int j = (warp & 3) * 32 + lane;
   const int c0 = (warp >> 2) * NC;
   uint8_t* g_hi = g_tile;
   uint8_t* g_lo = g_tile + 48 * LBO;
+  for (int i = tid; i < (int)(2 * 48 * LBO / 4); i += TC_THREADS) reinterpret_cast<uint32_t*>(g_tile)[i] = 0u;   // pad rows stay 0
   if (tid == 0) {
     mbar_init(&bar, 3);                                      // the K=384 reduction is issued as 3 chunks by 3 warps
     for (int r = 0; r < BWD_RING; ++r) mbar_init(&in_bar[r], 1);
@@ -297,13 +299,13 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
     const int tp = t + dt, tpv = (tp >= 0 && tp < T) ? tp : t;
     const int to = ds == 2 ? (t >> 1) : t;
     float* dst = in_ring + slot * SLOT;
-    mbar_arrive_expect_tx(&in_bar[slot], NB * (2048u + 512u + 512u + (mask ? 512u : 0u)));
-    for (int c = 0; c < NB; ++c) {
+    mbar_arrive_expect_tx(&in_bar[slot], NR * (2048u + 512u + 512u + (mask ? 512u : 0u)));
+    for (int c = 0; c < NR; ++c) {
       const long bc = min(b0 + c, B - 1);
       tma_load_1d(dst + c * 512, stash + (bc * T + t) * 1024 + d * 512, 2048, &in_bar[slot]);
-      tma_load_1d(dst + NB * 512 + c * 128, y_full + (bc * T + tpv) * 256 + d * SLU_H, 512, &in_bar[slot]);
-      tma_load_1d(dst + NB * 640 + c * 128, dy_out + (bc * T2 + to) * 256 + d * SLU_H, 512, &in_bar[slot]);
-      if (mask) tma_load_1d(dst + NB * 768 + c * 128, mask + (bc * T + t) * 256 + d * SLU_H, 512, &in_bar[slot]);
+      tma_load_1d(dst + NR * 512 + c * 128, y_full + (bc * T + tpv) * 256 + d * SLU_H, 512, &in_bar[slot]);
+      tma_load_1d(dst + NR * 640 + c * 128, dy_out + (bc * T2 + to) * 256 + d * SLU_H, 512, &in_bar[slot]);
+      if (mask) tma_load_1d(dst + NR * 768 + c * 128, mask + (bc * T + t) * 256 + d * SLU_H, 512, &in_bar[slot]);
     }
   };
   if (warp == 3 && elect_one())
@@ -339,9 +341,9 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
     mbar_wait(&in_bar[s % BWD_RING], (uint32_t)((s / BWD_RING) & 1));
     const float* sl = in_ring + (s % BWD_RING) * SLOT;
     const float* sts = sl + c0 * 512 + j;
-    const float* hps = sl + NB * 512 + c0 * 128 + j;
-    const float* dys = sl + NB * 640 + c0 * 128 + j;
-    const float* mks = sl + NB * 768 + c0 * 128 + j;
+    const float* hps = sl + NR * 512 + c0 * 128 + j;
+    const float* dys = sl + NR * 640 + c0 * 128 + j;
+    const float* mks = sl + NR * 768 + c0 * 128 + j;
     float o_r[NC], o_z[NC], o_n[NC], o_hn[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -409,54 +411,76 @@ extern "C" int slu_set_gru_precision(int mode) {
   return 0;
 }
 
-template <int NB, bool STASH, bool FULL>
-static void launch_fwd(dim3 grid, size_t smem, cudaStream_t st, const float* gx, const float* w_hh, const float* b_hh,
-                       const float* mask, int B, int T, int ds, int tile0, float* y_full, float* y_out, float* stash) {
-  static int a3 = slu_set_smem((const void*)gru_fwd_tc_kernel<NB, STASH, FULL, 3>, smem);
-  static int a1 = slu_set_smem((const void*)gru_fwd_tc_kernel<NB, STASH, FULL, 1>, smem);
+// Tile shape: the MMA is always N = 16 wide; NR of those columns carry real batch rows.  Small batches use fewer rows
+// per CTA so that more SMs share the latency-bound recurrence (B=256: NR=4 -> 128 CTAs), large batches fill all 16.
+static int pick_rows(int B) { return B >= 1184 ? 16 : (B >= 592 ? 8 : 4); }
+
+template <int NR, bool STASH, bool FULL>
+static void launch_fwd(dim3 grid, cudaStream_t st, const float* gx, const float* w_hh, const float* b_hh, const float* mask,
+                       int B, int T, int ds, int tile0, float* y_full, float* y_out, float* stash) {
+  constexpr size_t smem = (size_t)FWD_RING * NR * 512 * sizeof(float);
+  static int a3 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, 3>, smem);
+  static int a1 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, 1>, smem);
   (void)a3; (void)a1;
-  if (g_gru_mode == 0) gru_fwd_tc_kernel<NB, STASH, FULL, 3><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
-  else gru_fwd_tc_kernel<NB, STASH, FULL, 1><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
+  if (g_gru_mode == 0) gru_fwd_tc_kernel<16, NR, STASH, FULL, 3><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
+  else gru_fwd_tc_kernel<16, NR, STASH, FULL, 1><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
+}
+
+template <int NR>
+static void run_fwd(cudaStream_t st, const float* gx, const float* w_hh, const float* b_hh, const float* mask, int B, int T, int ds,
+                    float* y_full, float* y_out, float* stash) {
+  const int full = B / NR, rem = B % NR;
+  if (full) {
+    if (stash) launch_fwd<NR, true, true>(dim3(full, 2), st, gx, w_hh, b_hh, mask, B, T, ds, 0, y_full, y_out, stash);
+    else launch_fwd<NR, false, true>(dim3(full, 2), st, gx, w_hh, b_hh, mask, B, T, ds, 0, y_full, y_out, nullptr);
+  }
+  if (rem) {                          // ragged last tile: predicated stores
+    if (stash) launch_fwd<NR, true, false>(dim3(1, 2), st, gx, w_hh, b_hh, mask, B, T, ds, full, y_full, y_out, stash);
+    else launch_fwd<NR, false, false>(dim3(1, 2), st, gx, w_hh, b_hh, mask, B, T, ds, full, y_full, y_out, nullptr);
+  }
 }
 
 extern "C" int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T,
                               int ds, float* y_full, float* y_out, float* stash, void* stream) {
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (long)B * T * 1024 >= (1L << 31)) return (int)cudaErrorInvalidValue;
-  constexpr int NB = 16;
   cudaStream_t st = (cudaStream_t)stream;
-  const int full = B / NB, rem = B % NB;
-  const size_t smem = (size_t)FWD_RING * NB * 512 * sizeof(float);
-  if (full) {
-    if (stash) launch_fwd<NB, true, true>(dim3(full, 2), smem, st, gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, stash);
-    else launch_fwd<NB, false, true>(dim3(full, 2), smem, st, gx, w_hh, b_hh, drop_mask, B, T, ds, 0, y_full, y_out, nullptr);
-  }
-  if (rem) {                          // ragged last tile: predicated stores
-    if (stash) launch_fwd<NB, true, false>(dim3(1, 2), smem, st, gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, stash);
-    else launch_fwd<NB, false, false>(dim3(1, 2), smem, st, gx, w_hh, b_hh, drop_mask, B, T, ds, full, y_full, y_out, nullptr);
+  switch (pick_rows(B)) {
+    case 16: run_fwd<16>(st, gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, stash); break;
+    case 8: run_fwd<8>(st, gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, stash); break;
+    default: run_fwd<4>(st, gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, stash); break;
   }
   SLU_CHECK_LAUNCH();
   return 0;
 }
 
-template <int NB, bool FULL>
-static void launch_bwd(dim3 grid, size_t smem, cudaStream_t st, const float* dy_out, const float* mask, const float* y_full,
-                       const float* stash, const float* w_hh, int B, int T, int ds, int tile0, float* dgx, float* dhn, float* dbias) {
-  static int a3 = slu_set_smem((const void*)gru_bwd_tc_kernel<NB, FULL, 3>, smem);
-  static int a1 = slu_set_smem((const void*)gru_bwd_tc_kernel<NB, FULL, 1>, smem);
+template <int NR, bool FULL>
+static void launch_bwd(dim3 grid, cudaStream_t st, const float* dy_out, const float* mask, const float* y_full, const float* stash,
+                       const float* w_hh, int B, int T, int ds, int tile0, float* dgx, float* dhn, float* dbias) {
+  constexpr size_t smem = (size_t)BWD_RING * NR * 896 * sizeof(float);
+  static int a3 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, 3>, smem);
+  static int a1 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, 1>, smem);
   (void)a3; (void)a1;
-  if (g_gru_mode == 0) gru_bwd_tc_kernel<NB, FULL, 3><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
-  else gru_bwd_tc_kernel<NB, FULL, 1><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
+  if (g_gru_mode == 0) gru_bwd_tc_kernel<16, NR, FULL, 3><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
+  else gru_bwd_tc_kernel<16, NR, FULL, 1><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
+}
+
+template <int NR>
+static void run_bwd(cudaStream_t st, const float* dy_out, const float* mask, const float* y_full, const float* stash, const float* w_hh,
+                    int B, int T, int ds, float* dgx, float* dhn, float* dbias) {
+  const int full = B / NR, rem = B % NR;
+  if (full) launch_bwd<NR, true>(dim3(full, 2), st, dy_out, mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn, dbias);
+  if (rem) launch_bwd<NR, false>(dim3(1, 2), st, dy_out, mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn, dbias);
 }
 
 extern "C" int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
                               const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* dbias, void* stream) {
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (long)B * T * 1024 >= (1L << 31)) return (int)cudaErrorInvalidValue;
-  constexpr int NB = 16;
   cudaStream_t st = (cudaStream_t)stream;
-  const int full = B / NB, rem = B % NB;
-  const size_t smem = (size_t)BWD_RING * NB * 896 * sizeof(float);
-  if (full) launch_bwd<NB, true>(dim3(full, 2), smem, st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn, dbias);
-  if (rem) launch_bwd<NB, false>(dim3(1, 2), smem, st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn, dbias);
+  switch (pick_rows(B)) {
+    case 16: run_bwd<16>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, dbias); break;
+    case 8: run_bwd<8>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, dbias); break;
+    default: run_bwd<4>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, dbias); break;
+  }
   SLU_CHECK_LAUNCH();
   return 0;
 }
