@@ -136,10 +136,19 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr));
+}
 template <int N>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v) {
-  static_assert(N == 4 || N == 8 || N == 16, "tmem_ld width");
-  if (N == 4) tmem_ld4(taddr, v); else if (N == 8) tmem_ld8(taddr, v); else tmem_ld16(taddr, v);
+  static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 16, "tmem_ld width");
+  if (N == 1) tmem_ld1(taddr, v); else if (N == 2) tmem_ld2(taddr, v); else if (N == 4) tmem_ld4(taddr, v);
+  else if (N == 8) tmem_ld8(taddr, v); else tmem_ld16(taddr, v);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
