@@ -92,6 +92,31 @@ __device__ __forceinline__ void load8_strided(const float* base, long s_k, int k
   }
 }
 
+// Strided ("frames") form, vectorised: a 4 (consecutive m) x 8 (consecutive reduction frames) block with one 16-byte load per
+// frame -- 4x fewer load instructions than 8 scalar loads per row.  Needs m-contiguous rows (stride 1) and 16-byte alignment.
+__device__ __forceinline__ void load_frames_4x8(const float* base, long s_frame, int m, int M, int k0, int K, int T, int shift,
+                                                bool on, float (*v)[8]) {
+  const bool vec = on && (m + 4 <= M) && (((reinterpret_cast<uintptr_t>(base + m) | (uintptr_t)(s_frame * 4)) & 15) == 0);
+  int t = (shift != 0) ? k0 % T + shift : 0;
+  const float* p = base + (long)(k0 + shift) * s_frame + m;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool f_ok = on && (k0 + i < K) && (shift == 0 || (t >= 0 && t < T));
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec) {
+      if (f_ok) q = __ldg(reinterpret_cast<const float4*>(p + (long)i * s_frame));
+    } else if (f_ok) {
+      const float* pi = p + (long)i * s_frame;
+      if (m < M) q.x = __ldg(pi);
+      if (m + 1 < M) q.y = __ldg(pi + 1);
+      if (m + 2 < M) q.z = __ldg(pi + 2);
+      if (m + 3 < M) q.w = __ldg(pi + 3);
+    }
+    v[0][i] = q.x; v[1][i] = q.y; v[2][i] = q.z; v[3][i] = q.w;
+    if (shift != 0) { ++t; if (t - shift >= T) t -= T; }
+  }
+}
+
 // SincConv forward A operand: A(m=(b,t), tap, k) = x[b][80*(t+tap) + k - 200]  (zero outside [0,Ts), for pad frames t>=L0
 // and for k >= 80).  The waveform itself is the [frames][80] matrix: no im2col.
 __device__ __forceinline__ void load8_sinc_rows(const float* xb, int idx0, int k0, int Ts, bool row_ok, float* v) {
@@ -158,14 +183,26 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 
   // Register-prefetch pipeline: the global loads of k-block i+1 are issued right after k-block i has been
   // converted into its shared-memory stage, so their latency hides behind the fence / barrier / MMA issue.
-  float va[A_CH][8];
-  float vb[(BMODE == 2) ? 1 : B_CH][8];
+  // frames-form operands (AMODE 1 / BMODE 1) are staged as 4x8 blocks: A blocks by threads 128..255, B blocks by threads < BN
+  constexpr bool A_FR = (AMODE == 1), B_FR = (BMODE == 1);
+  const bool fa_on = A_FR && tid >= 128, fb_on = B_FR && tid < BN;
+  const int fa_m4 = (tid - 128) & 31, fa_kc = (tid - 128) >> 5, fb_m4 = tid % (BN / 4), fb_kc = tid / (BN / 4);
+  // when both operands are frames-form (weight gradients, BN <= 128) a thread owns exactly one block: one register array
+  constexpr bool FR_BOTH = A_FR && B_FR;
+  static_assert(!FR_BOTH || BN <= 128, "frames-form weight-gradient tiles use BN <= 128");
+  float fa[A_FR ? 4 : 1][8];
+  float fb_own[(B_FR && !FR_BOTH) ? 4 : 1][8];
+  float (*fb)[8] = FR_BOTH ? fa : fb_own;
+  float va[A_FR ? 1 : A_CH][8];
+  float vb[(BMODE == 2 || B_FR) ? 1 : B_CH][8];
   uint4 ib_hi[(BMODE == 2) ? B_CH : 1], ib_lo[(BMODE == 2) ? B_CH : 1];
   auto prefetch = [&](int i) {
     const int kb = kb_begin + i;
     const int tap = kb / kb_per_tap, k0 = (kb % kb_per_tap) * BK;
+    if (A_FR) load_frames_4x8(p.A, p.a_sk, m0 + fa_m4 * 4, p.M, k0 + fa_kc * 8, p.K, p.T ? p.T : 1, p.a_kshift, fa_on, fa);
+    if (B_FR) load_frames_4x8(p.B + (long)tap * p.b_stap, p.b_sk, n0 + fb_m4 * 4, p.N, k0 + fb_kc * 8, p.K, p.T ? p.T : 1, p.b_kshift, fb_on, fb);
 #pragma unroll
-    for (int u = 0; u < A_CH; ++u) {
+    for (int u = 0; u < (A_FR ? 0 : A_CH); ++u) {
       const int m = m0 + a_r[u];
       if (AMODE == 0) {
         bool ok = m < p.M;
@@ -204,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       }
     }
 #pragma unroll
-    for (int u = 0; u < B_CH; ++u) {
+    for (int u = 0; u < (B_FR ? 0 : B_CH); ++u) {
       const int c = tid + u * THREADS;
       if (BMODE == 2) {
         const int kc = c & 3, r = c >> 2, n = n0 + r;
@@ -246,15 +283,33 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     uint8_t* st = smem + s * S::STAGE;
     uint8_t* a_hi = st; uint8_t* a_lo = st + S::A_PART;
     uint8_t* b_hi = st + 2 * S::A_PART; uint8_t* b_lo = b_hi + S::B_PART;
+    if (A_FR && fa_on) {
 #pragma unroll
-    for (int u = 0; u < A_CH; ++u) {
+      for (int r = 0; r < 4; ++r) {
+        uint4 hi, lo; split8(fa[r], hi, lo);
+        const uint32_t off = (uint32_t)fa_kc * S::LBO_A + (uint32_t)(fa_m4 * 4 + r) * 16;
+        *reinterpret_cast<uint4*>(a_hi + off) = hi;
+        *reinterpret_cast<uint4*>(a_lo + off) = lo;
+      }
+    }
+    if (B_FR && fb_on) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        uint4 hi, lo; split8(fb[r], hi, lo);
+        const uint32_t off = (uint32_t)fb_kc * S::LBO_B + (uint32_t)(fb_m4 * 4 + r) * 16;
+        *reinterpret_cast<uint4*>(b_hi + off) = hi;
+        *reinterpret_cast<uint4*>(b_lo + off) = lo;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < (A_FR ? 0 : A_CH); ++u) {
       uint4 hi, lo; split8(va[u], hi, lo);
       const uint32_t off = (uint32_t)a_kc[u] * S::LBO_A + (uint32_t)a_r[u] * 16;
       *reinterpret_cast<uint4*>(a_hi + off) = hi;
       *reinterpret_cast<uint4*>(a_lo + off) = lo;
     }
 #pragma unroll
-    for (int u = 0; u < B_CH; ++u) {
+    for (int u = 0; u < (B_FR ? 0 : B_CH); ++u) {
       const int c = tid + u * THREADS;
       if (c < B_TOT) {
         int r, kc;
@@ -374,8 +429,9 @@ int launch(const GemmParams& p, cudaStream_t stream) {
 template <int AMODE, int BMODE>
 int dispatch_bn(const GemmParams& p, cudaStream_t stream) {
   if (p.N <= 64) return launch<64, AMODE, BMODE, 0>(p, stream);
-  if (p.N <= 128) return launch<128, AMODE, BMODE, 0>(p, stream);
-  return launch<256, AMODE, BMODE, 0>(p, stream);
+  if (p.N <= 128 || (AMODE == 1 && BMODE == 1)) return launch<128, AMODE, BMODE, 0>(p, stream);   // weight gradients: BN <= 128
+  if constexpr (!(AMODE == 1 && BMODE == 1)) return launch<256, AMODE, BMODE, 0>(p, stream);
+  return (int)cudaErrorInvalidValue;
 }
 
 // fp32 strided weights -> bf16 hi / lo images [2][taps][N][Kp] (zero padded to Kp, a multiple of 32)

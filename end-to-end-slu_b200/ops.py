@@ -48,7 +48,7 @@ def presplit(W, w_off, sn, sk, stap, taps, N, K):
 
 
 def _split_k(M, N, K, taps=1):
-    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1)
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)          # weight-gradient tiles are 128 x <=128
     kb = taps * ((K + 31) // 32)
     return max(1, min(kb, 296 // max(1, tiles)))
 
