@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   auto prefetch = [&](int i) {
     const int kb = kb_begin + i;
     const int tap = kb / kb_per_tap, k0 = (kb % kb_per_tap) * BK;
-    if (A_FR) load_frames_4x8(p.A, p.a_sk, m0 + fa_m4 * 4, p.M, k0 + fa_kc * 8, p.K, p.T ? p.T : 1, p.a_kshift, fa_on, fa);
-    if (B_FR) load_frames_4x8(p.B + (long)tap * p.b_stap, p.b_sk, n0 + fb_m4 * 4, p.N, k0 + fb_kc * 8, p.K, p.T ? p.T : 1, p.b_kshift, fb_on, fb);
+    if (A_FR && fa_on) load_frames_4x8(p.A, p.a_sk, m0 + fa_m4 * 4, p.M, k0 + fa_kc * 8, p.K, p.T ? p.T : 1, p.a_kshift, fa_on, fa);
+    if (B_FR && fb_on) load_frames_4x8(p.B + (long)tap * p.b_stap, p.b_sk, n0 + fb_m4 * 4, p.N, k0 + fb_kc * 8, p.K, p.T ? p.T : 1, p.b_kshift, fb_on, fb);
 #pragma unroll
     for (int u = 0; u < (A_FR ? 0 : A_CH); ++u) {
       const int m = m0 + a_r[u];
