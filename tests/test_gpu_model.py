@@ -178,3 +178,28 @@ def test_asr_pretraining_forward_on_gpu():
             assert abs(v.grad.double().norm().item() - ref) < GRAD_TOL * ref + 1e-9, k
     ph, _ = pm.compute_posteriors(x)
     assert rel_err(ph.detach().cpu(), g["phoneme_logits"]) < 1e-3
+
+
+def test_seq2seq_model_on_gpu_matches_its_cpu_execution():
+    """BASELINE config 5: the seq2seq intent module on top of the encoder kernels (decoder = torch ops)."""
+    cfg = make_config("seq2seq")
+    cfg.Sy_intent = ["<sos>"] + list("abcdefghij {}:'\",") + ["<eos>"]
+    torch.manual_seed(3)
+    m = models.Model(cfg).eval()
+    assert m.seq2seq and next(m.parameters()).is_cuda
+    S, U = len(cfg.Sy_intent), 6
+    x = 0.1 * torch.randn(3, 8000)
+    idx = torch.randint(1, S - 1, (3, U)); idx[:, 0] = 0; idx[:, -1] = S - 1
+    y = torch.nn.functional.one_hot(idx, S).float()
+    l_gpu, _ = m(x, y)
+    l_gpu.backward()
+    g_gpu = m.encoder.layers[0].weight_hh_l0.grad.detach().cpu().clone()
+    m.zero_grad()
+    m.cpu(); m.is_cuda = False
+    l_cpu, _ = m(x, y)
+    l_cpu.backward()
+    assert abs(l_gpu.item() - l_cpu.item()) < 1e-4 * abs(l_cpu.item())
+    assert rel_err(g_gpu, m.encoder.layers[0].weight_hh_l0.grad) < GRAD_TOL
+    m.cuda(); m.is_cuda = True
+    out = m.decode_intents(x[:1])           # beam search on the device (short alphabet, 200 steps)
+    assert isinstance(out, list) and isinstance(out[0], str)

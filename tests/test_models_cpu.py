@@ -185,3 +185,30 @@ def test_asr_forward_matches_reference(reference):
         assert abs(a.item() - b.item()) < 1e-5
     pr, wr = ref.compute_posteriors(x); pn, wn = new.compute_posteriors(x)
     assert rel_err(pn, pr) < 2e-5 and rel_err(wn, wr) < 2e-5
+
+
+def test_seq2seq_surface_matches_reference(reference):
+    """config 5 (repaired seq2seq cfg): same construction, teacher-forced loss and beam search as the reference, on CPU."""
+    cfg = make_config("seq2seq")
+    cfg.Sy_intent = ["<sos>"] + list("abcdefghij {}:'\",") + ["<eos>"]
+    torch.manual_seed(11)
+    ref = reference.Model(cfg); ref.cpu(); ref.is_cuda = False
+    torch.manual_seed(11)
+    new = cpu_model(cfg)
+    sd_r, sd_n = ref.state_dict(), new.state_dict()
+    assert list(sd_r) == list(sd_n)
+    for k in sd_r:
+        assert torch.equal(sd_r[k], sd_n[k]), k
+    S, U = len(cfg.Sy_intent), 7
+    x = 0.1 * torch.randn(3, 6000)
+    idx = torch.randint(1, S - 1, (3, U)); idx[:, 0] = 0; idx[:, -1] = S - 1
+    y = torch.nn.functional.one_hot(idx, S).float()
+    ref.eval(); new.eval()
+    l_r, _ = ref(x, y); l_n, _ = new(x, y)
+    assert abs(l_r.item() - l_n.item()) < 1e-4 * abs(l_r.item())
+    # beam search (shortened: the reference runs a fixed 200 steps unless y_lengths is given)
+    enc_r = ref.encoder(ref.pretrained_model.compute_features(x)); enc_n = new.encoder(new.pretrained_model.compute_features(x))
+    s_r, b_r = ref.decoder.infer(enc_r, cfg.Sy_intent, B=4, y_lengths=[6])
+    s_n, b_n = new.decoder.infer(enc_n, cfg.Sy_intent, B=4, y_lengths=[6])
+    assert rel_err(s_n, s_r) < 1e-4 and torch.equal(b_r.argmax(-1), b_n.argmax(-1))
+    assert ref.one_hot_to_string(b_r[0, 0], cfg.Sy_intent) == new.one_hot_to_string(b_n[0, 0], cfg.Sy_intent)
