@@ -389,22 +389,42 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         __syncwarp();
         continue;
       }
-      const float bias = (p.bias && n_ok && blockIdx.z == 0) ? __ldg(p.bias + n) : 0.f;
-      float* dst = p.C + (long)(m0 + q * 32) * p.ldc + n;
       const int rows = min(32, p.M - (m0 + q * 32));
-      if (n_ok) {
-        if (rows == 32) {
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            float x = tr[r * 33 + lane] + bias;
-            if (p.act == 1) x = x > 0.f ? x : x * p.slope;
-            if (p.split_k > 1) atomicAdd(dst + (long)r * p.ldc, x); else dst[(long)r * p.ldc] = x;
+      if (p.split_k == 1 && rows == 32 && n0 + c0 + 32 <= p.N && (p.ldc & 3) == 0 && ((n0 + c0) & 3) == 0 &&
+          (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+        // fast path: 16-byte stores, a warp instruction writes 4 rows x 128 B
+        const int cq = (lane & 7) * 4, r0 = lane >> 3;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + cq));
+        float* dst4 = p.C + (long)(m0 + q * 32) * p.ldc + n0 + c0 + cq;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 4 * i;
+          float4 x;
+          x.x = tr[r * 33 + cq] + b4.x; x.y = tr[r * 33 + cq + 1] + b4.y; x.z = tr[r * 33 + cq + 2] + b4.z; x.w = tr[r * 33 + cq + 3] + b4.w;
+          if (p.act == 1) {
+            x.x = x.x > 0.f ? x.x : x.x * p.slope; x.y = x.y > 0.f ? x.y : x.y * p.slope;
+            x.z = x.z > 0.f ? x.z : x.z * p.slope; x.w = x.w > 0.f ? x.w : x.w * p.slope;
           }
-        } else {
-          for (int r = 0; r < rows; ++r) {
-            float x = tr[r * 33 + lane] + bias;
-            if (p.act == 1) x = x > 0.f ? x : x * p.slope;
-            if (p.split_k > 1) atomicAdd(dst + (long)r * p.ldc, x); else dst[(long)r * p.ldc] = x;
+          *reinterpret_cast<float4*>(dst4 + (long)r * p.ldc) = x;
+        }
+      } else {
+        const float bias = (p.bias && n_ok && blockIdx.z == 0) ? __ldg(p.bias + n) : 0.f;
+        float* dst = p.C + (long)(m0 + q * 32) * p.ldc + n;
+        if (n_ok) {
+          if (rows == 32) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              float x = tr[r * 33 + lane] + bias;
+              if (p.act == 1) x = x > 0.f ? x : x * p.slope;
+              if (p.split_k > 1) atomicAdd(dst + (long)r * p.ldc, x); else dst[(long)r * p.ldc] = x;
+            }
+          } else {
+            for (int r = 0; r < rows; ++r) {
+              float x = tr[r * 33 + lane] + bias;
+              if (p.act == 1) x = x > 0.f ? x : x * p.slope;
+              if (p.split_k > 1) atomicAdd(dst + (long)r * p.ldc, x); else dst[(long)r * p.ldc] = x;
+            }
           }
         }
       }
