@@ -474,11 +474,12 @@ __global__ void presplit_kernel(const float* __restrict__ W, long sn, long sk, l
 
 // Pre-split a (strided) fp32 weight operand into the bf16 hi/lo image the GEMM's B side can copy verbatim.
 // img must hold 2 * taps * N * Kp bf16 values, Kp = K rounded up to a multiple of 32.
-static int presplit(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream);
+int slu_presplit_rows(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream);
 extern "C" int slu_presplit_bf16(const float* W, long sn, long sk, long stap, int taps, int N, int K, void* img, void* stream) {
-  return presplit(W, sn, sk, stap, taps, N, K, 0, img, stream);
+  return slu_presplit_rows(W, sn, sk, stap, taps, N, K, 0, img, stream);
 }
-static int presplit(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream) {
+// like slu_presplit_bf16, with elements whose in-row offset k*sk + tap*stap reaches row_len read as 0 (used by sinc_tc.cu)
+int slu_presplit_rows(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream) {
   if (taps <= 0 || N <= 0 || K <= 0) return (int)cudaErrorInvalidValue;
   const int Kp = (K + 31) / 32 * 32;
   const size_t total = (size_t)taps * N * Kp;
@@ -504,35 +505,4 @@ extern "C" int slu_gemm_tc(const float* A, long a_sm, long a_sk, const float* B,
   if (b_img) return a_kc ? dispatch_bn<0, 2>(p, st) : dispatch_bn<1, 2>(p, st);
   if (b_sk == 1) return a_kc ? dispatch_bn<0, 0>(p, st) : dispatch_bn<1, 0>(p, st);
   return a_kc ? dispatch_bn<0, 1>(p, st) : dispatch_bn<1, 1>(p, st);
-}
-
-// ---- SincNet front end on the tensor core -----------------------------------------------------------------------
-// Forward: out[B][L1][80] = maxpool2(|conv1d(x, W, stride 80, pad 200)|) as a 6-tap GEMM over the waveform viewed as
-// [frames][80] (M = B*L0p frames, N = 80 filters, K = 80 per tap), abs + pool + route in the epilogue.
-// `img` = scratch for the pre-split bank: 2*6*80*96 bf16 values.
-extern "C" int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T, float* out, uint8_t* route, void* img, void* stream) {
-  if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
-  const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2, L0p = 2 * L1;
-  if ((long)B * L0p >= (1L << 31)) return (int)cudaErrorInvalidValue;
-  int e = presplit(W, SLU_NTAPS, 1, SLU_STRIDE, 6, SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // bank[c][80a + k], 0 beyond tap 400
-  if (e) return e;
-  GemmParams p{};
-  p.A = x; p.Bimg = (const __nv_bfloat16*)img; p.Kp = 96; p.C = out; p.ldc = SLU_NFILT;
-  p.M = B * L0p; p.N = SLU_NFILT; p.K = SLU_STRIDE; p.taps = 6; p.split_k = 1;
-  p.Ts = T; p.L0 = L0; p.L0p = L0p; p.L1 = L1; p.route = route;
-  return launch<128, 2, 2, 1>(p, (cudaStream_t)stream);
-}
-
-// Backward: dW[80][401] = sum over frames (b,t) of g0[b][t][c] * xpad[b][80 t + n], g0 = dL/dout routed through max-pool / abs:
-// one split-K GEMM, M = 80 filters, N = 401 taps, K = B*L0p frames; dW must be zero-filled by the caller.
-extern "C" int slu_sincconv_bwd_tc(const float* x, const float* gy, const uint8_t* route, int B, int T, float* dW, void* stream) {
-  if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
-  const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2, L0p = 2 * L1;
-  if ((long)B * L0p >= (1L << 31)) return (int)cudaErrorInvalidValue;
-  GemmParams p{};
-  p.B = x; p.C = dW; p.ldc = SLU_NTAPS; p.M = SLU_NFILT; p.N = SLU_NTAPS; p.K = B * L0p; p.taps = 1;
-  p.Ts = T; p.L0 = L0; p.L0p = L0p; p.L1 = L1; p.gy = gy; p.route = const_cast<uint8_t*>(route);
-  const int kb = (p.K + BK - 1) / BK;
-  p.split_k = kb < 148 ? kb : 148;
-  return launch<256, 3, 3, 0>(p, (cudaStream_t)stream);
 }

@@ -1,0 +1,316 @@
+// SincNet front end on tcgen05 tensor cores, "the waveform IS the matrix" formulation.
+//
+// With stride 80 and 401 = 5*80 + 1 taps, the padded waveform of one utterance viewed as a row-major [frames][80]
+// matrix F (F[j][r] = xpad[80 j + r], xpad = x shifted by 200 zeros) gives
+//     conv[t][c] = sum_{a=0..5} sum_{r<80} F[t+a][r] * W[c][80a + r]            (taps beyond 400 are zero)
+// i.e. six accumulating K=80 MMAs over ONE staged tile whose row offset is the tap index.  The tile is staged once
+// per 128 output frames as bf16 hi/lo in the K-major "chunk-column" image  byte(row, k) = (k/8)*LBO + row*16 + (k%8)*2,
+// in which a row shift of `a` frames is just +16*a bytes on the descriptor start address: no im2col, no re-staging.
+//   forward : D[128 frames x 80 filters] = sum_a  F(rows a..a+127) . W_a^T ; epilogue = abs + max-pool(2) + route bits
+//   backward: dW[c][80a + r] = sum_t g0[t][c] * F[t+a][r]  -- the same image read as an MN-major B operand (K = frames),
+//             the routed gradient g0 as an MN-major A operand; six [128 x 80] accumulators live in TMEM (480 columns)
+//             across all tiles of a persistent CTA and are flushed once with fp32 atomics.
+// Every product is bf16 hi*hi + hi*lo + lo*hi with fp32 accumulation (see tc05.cuh).
+// Reference behaviour: models.py:108 (F.conv1d stride 80 pad 200), :163-168 (Abs), :205 (MaxPool1d(2, ceil)).
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace {
+using namespace tc05;
+
+constexpr int THREADS = 256;
+constexpr int TF = 128;                         // output frames per tile
+constexpr int XROWS = TF + 8;                   // staged frame rows (5 halo rows, padded to a multiple of 8)
+constexpr int KC = SLU_STRIDE / 8;              // 10 sample chunks per frame
+constexpr uint32_t LBO_X = XROWS * 16 + 16;     // 2192: chunk-column stride of the waveform image
+constexpr uint32_t X_PART = KC * LBO_X;         // 21920 B (one of hi / lo)
+constexpr uint32_t LBO_W = SLU_NFILT * 16 + 16; // 1296: chunk-column stride of one tap's filter tile [80 n][80 k]
+constexpr uint32_t W_PART = KC * LBO_W;         // 12960 B
+constexpr int WKP = 96;                         // row pitch (elements) of the pre-split bank image
+
+// Instruction descriptor with selectable operand majors (bit 15: A is MN-major, bit 16: B is MN-major).
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
+  return idesc_bf16_f32(M, N) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
+}
+
+// Stage the waveform slice of one tile: rows r = 0..XROWS-1 are frames t0 + r, 80 samples each, starting at sample
+// 80*t0 - 200 of utterance xb (zero outside [0, T)).
+__device__ __forceinline__ void stage_wave_image(uint8_t* hi, uint8_t* lo, const float* xb, int t0, int T, int tid) {
+  for (int task = tid; task < XROWS * KC; task += THREADS) {
+    const int r = task / KC, kc = task - r * KC;
+    const int idx0 = SLU_STRIDE * (t0 + r) + kc * 8 - SLU_PAD;
+    float v[8];
+    const float* p = xb + idx0;
+    if (idx0 >= 0 && idx0 + 8 <= T && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = idx0 + i;
+        const bool ok = idx >= 0 && idx < T;
+        const float val = __ldg(xb + (ok ? idx : 0));
+        v[i] = ok ? val : 0.f;
+      }
+    }
+    uint4 h, l; split8(v, h, l);
+    const uint32_t off = (uint32_t)kc * LBO_X + (uint32_t)r * 16;
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t FWD_SMEM = 2 * X_PART + 2 * 2 * W_PART;      // waveform image (hi, lo) + 2-slot ring of filter taps
+
+__global__ void __launch_bounds__(THREADS, 2)
+sincconv_fwd_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wimg, int T, int L0, int L1,
+                       float* __restrict__ out, uint8_t* __restrict__ route) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t empty_bar[2], acc_bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
+  const int b = blockIdx.y, t0 = blockIdx.x * TF;
+  uint8_t* x_hi = smem; uint8_t* x_lo = smem + X_PART;
+  uint8_t* w_ring = smem + 2 * X_PART;
+
+  if (tid == 0) { mbar_init(&empty_bar[0], 1); mbar_init(&empty_bar[1], 1); mbar_init(&acc_bar, 1); fence_mbar_init(); }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_base, 128);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t idesc = idesc_bf16(128, SLU_NFILT, false, false);
+
+  stage_wave_image(x_hi, x_lo, x + (size_t)b * T, t0, T, tid);
+
+  const size_t lo_off = (size_t)6 * SLU_NFILT * WKP;              // image = [hi | lo][tap][n][WKP]
+  for (int tap = 0; tap < 6; ++tap) {
+    const int slot = tap & 1;
+    if (tap >= 2) mbar_wait(&empty_bar[slot], (uint32_t)(((tap >> 1) - 1) & 1));
+    uint8_t* w_hi = w_ring + slot * 2 * W_PART; uint8_t* w_lo = w_hi + W_PART;
+    for (int task = tid; task < SLU_NFILT * KC; task += THREADS) {     // plain 16-byte copies of the pre-split bank
+      const int n = task / KC, kc = task - n * KC;
+      const size_t e = ((size_t)tap * SLU_NFILT + n) * WKP + kc * 8;
+      const uint32_t off = (uint32_t)kc * LBO_W + (uint32_t)n * 16;
+      *reinterpret_cast<uint4*>(w_hi + off) = __ldg(reinterpret_cast<const uint4*>(wimg + e));
+      *reinterpret_cast<uint4*>(w_lo + off) = __ldg(reinterpret_cast<const uint4*>(wimg + lo_off + e));
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        // rows tap .. tap+127 of the staged image: start address + 16 B per row
+        const uint64_t ah0 = smem_desc(smem_u32(x_hi) + tap * 16, LBO_X, 128), al0 = smem_desc(smem_u32(x_lo) + tap * 16, LBO_X, 128);
+        const uint64_t bh0 = smem_desc(smem_u32(w_hi), LBO_W, 128), bl0 = smem_desc(smem_u32(w_lo), LBO_W, 128);
+#pragma unroll
+        for (int kk = 0; kk < SLU_STRIDE / 16; ++kk) {
+          const uint64_t ah = desc_advance(ah0, kk * 2 * LBO_X), al = desc_advance(al0, kk * 2 * LBO_X);
+          const uint64_t bh = desc_advance(bh0, kk * 2 * LBO_W), bl = desc_advance(bl0, kk * 2 * LBO_W);
+          mma_bf16(tmem, ah, bh, idesc, (tap | kk) ? 1u : 0u);
+          mma_bf16(tmem, ah, bl, idesc, 1u);
+          mma_bf16(tmem, al, bh, idesc, 1u);
+        }
+        mma_commit(&empty_bar[slot]);
+        if (tap == 5) mma_commit(&acc_bar);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- epilogue: |.| + max over frame pairs + route bits, coalesced along the 80 filters
+  mbar_wait(&acc_bar, 0);
+  fence_after_sync();
+  {
+    const int q = warp & 3, half = warp >> 2;                         // TMEM lane quarter; columns [0,48) / [48,80) in 16-col steps
+    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 17);    // image buffers are free once acc_bar fired
+    for (int c0 = half * 48; c0 < (half ? SLU_NFILT : 48); c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tr[lane * 17 + i] = v[i];
+      __syncwarp();
+      // lane -> (pair jp = lane / 2 of this warp's 16 pairs, 8 of the 16 columns)
+      const int jp = lane >> 1, cb = (lane & 1) * 8;
+      const int t = t0 + q * 32 + 2 * jp;
+      if (t < L0) {
+        const bool has1 = t + 1 < L0;
+        const size_t o = ((size_t)b * L1 + (t >> 1)) * SLU_NFILT + c0 + cb;
+        float r_out[8]; uint8_t r_rt[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v0 = tr[(2 * jp) * 17 + cb + i], v1 = tr[(2 * jp + 1) * 17 + cb + i];
+          const float a0 = fabsf(v0), a1 = has1 ? fabsf(v1) : -1.f;
+          const int sel = a1 > a0 ? 1 : 0;
+          const float vs = sel ? v1 : v0;
+          r_out[i] = sel ? a1 : a0;
+          r_rt[i] = (uint8_t)(sel | ((vs < 0.f) ? 2 : 0) | ((vs == 0.f) ? 4 : 0));
+        }
+        *reinterpret_cast<float4*>(out + o) = make_float4(r_out[0], r_out[1], r_out[2], r_out[3]);
+        *reinterpret_cast<float4*>(out + o + 4) = make_float4(r_out[4], r_out[5], r_out[6], r_out[7]);
+        if (route) {
+          uint2 pk;
+          pk.x = r_rt[0] | (r_rt[1] << 8) | (r_rt[2] << 16) | ((uint32_t)r_rt[3] << 24);
+          pk.y = r_rt[4] | (r_rt[5] << 8) | (r_rt[6] << 16) | ((uint32_t)r_rt[7] << 24);
+          *reinterpret_cast<uint2*>(route + o) = pk;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward (filter gradient)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t SBO_G = TF * 16 + 16;                   // 2064: stride between 8-filter chunks of the routed-gradient image
+constexpr uint32_t G_PART = 16 * SBO_G;                    // 16 chunks = 128 filter rows (80 real), 33024 B
+constexpr uint32_t BWD_STAGE = 2 * X_PART + 2 * G_PART;    // 109888 B
+constexpr uint32_t BWD_SMEM = 2 * BWD_STAGE;               // two stages
+
+__global__ void __launch_bounds__(THREADS, 1)
+sincconv_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ gy, const uint8_t* __restrict__ route, int B, int T,
+                       int L0, int L1, int tiles_per_utt, float* __restrict__ dW) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t empty_bar[2], acc_bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
+  const int n_tiles = B * tiles_per_utt;
+
+  if (tid == 0) { mbar_init(&empty_bar[0], 1); mbar_init(&empty_bar[1], 1); mbar_init(&acc_bar, 1); fence_mbar_init(); }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  // filter chunks 10..15 (rows 80..127 of the M=128 tile) are never written: zero them once in both stages
+  for (int s = 0; s < 2; ++s)
+    for (int part = 0; part < 2; ++part) {
+      uint8_t* g = smem + s * BWD_STAGE + 2 * X_PART + part * G_PART + KC * SBO_G;
+      for (int i = tid * 16; i < (int)(6 * SBO_G); i += THREADS * 16) *reinterpret_cast<uint4*>(g + i) = make_uint4(0, 0, 0, 0);
+    }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t idesc = idesc_bf16(128, SLU_NFILT, true, true);     // both operands MN-major: the reduction runs over frames
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    if (it >= 2) mbar_wait(&empty_bar[s], (uint32_t)(((it >> 1) - 1) & 1));
+    const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TF;
+    uint8_t* st = smem + s * BWD_STAGE;
+    uint8_t* x_hi = st; uint8_t* x_lo = st + X_PART; uint8_t* g_hi = st + 2 * X_PART; uint8_t* g_lo = g_hi + G_PART;
+    stage_wave_image(x_hi, x_lo, x + (size_t)b * T, t0, T, tid);
+    // routed gradient g0[t][c] (through max-pool and abs) for frames t0..t0+127, 8 filters per 16-byte chunk
+    for (int task = tid; task < TF * KC; task += THREADS) {
+      const int r = task / KC, cc = task - r * KC;            // frame row, filter chunk
+      const int t = t0 + r;
+      float v[8];
+      const bool ok = t < L0;
+      const size_t o = ok ? ((size_t)b * L1 + (t >> 1)) * SLU_NFILT + cc * 8 : 0;
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(gy + o)), gb = __ldg(reinterpret_cast<const float4*>(gy + o) + 1);
+      const uint2 rt = __ldg(reinterpret_cast<const uint2*>(route + o));
+      const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t rb = ((i < 4 ? rt.x : rt.y) >> (8 * (i & 3))) & 0xffu;
+        const bool take = ok && ((rb & 1u) == (uint32_t)(t & 1)) && !(rb & 4u);
+        v[i] = take ? ((rb & 2u) ? -gv[i] : gv[i]) : 0.f;
+      }
+      uint4 h, l; split8(v, h, l);
+      const uint32_t off = (uint32_t)cc * SBO_G + (uint32_t)r * 16;
+      *reinterpret_cast<uint4*>(g_hi + off) = h;
+      *reinterpret_cast<uint4*>(g_lo + off) = l;
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        // MN-major no-swizzle descriptors: LBO = stride between 8-frame K groups (128 B), SBO = stride between 8-wide MN chunks
+        const uint64_t ah0 = smem_desc(smem_u32(g_hi), 128, SBO_G), al0 = smem_desc(smem_u32(g_lo), 128, SBO_G);
+        const uint64_t bh0 = smem_desc(smem_u32(x_hi), 128, LBO_X), bl0 = smem_desc(smem_u32(x_lo), 128, LBO_X);
+        for (int kk = 0; kk < TF / 16; ++kk) {               // 16 frames per MMA
+          const uint64_t ah = desc_advance(ah0, kk * 256), al = desc_advance(al0, kk * 256);
+          const uint32_t acc = (it | kk) ? 1u : 0u;
+#pragma unroll
+          for (int tap = 0; tap < 6; ++tap) {                // frame shift = tap rows of 16 B
+            const uint64_t bh = desc_advance(bh0, kk * 256 + tap * 16), bl = desc_advance(bl0, kk * 256 + tap * 16);
+            const uint32_t d = tmem + tap * SLU_NFILT;
+            mma_bf16(d, ah, bh, idesc, acc);
+            mma_bf16(d, ah, bl, idesc, 1u);
+            mma_bf16(d, al, bh, idesc, 1u);
+          }
+        }
+        mma_commit(&empty_bar[s]);
+      }
+      __syncwarp();
+    }
+  }
+  if (it > 0) {
+    if (warp == 0 && elect_one()) mma_commit(&acc_bar);
+    __syncwarp();
+    mbar_wait(&acc_bar, 0);
+    fence_after_sync();
+    // flush: D_tap[c][r] -> dW[c][80 tap + r]
+    const int q = warp & 3, half = warp >> 2;
+    const int c = q * 32 + lane;
+    for (int tap = half * 3; tap < half * 3 + 3; ++tap) {
+      for (int r0 = 0; r0 < SLU_NFILT; r0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + tap * SLU_NFILT + r0, v);
+        tmem_ld_wait();
+        if (c < SLU_NFILT) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k = SLU_STRIDE * tap + r0 + i;
+            if (k < SLU_NTAPS) atomicAdd(dW + c * SLU_NTAPS + k, v[i]);
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+int slu_presplit_rows(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream);
+
+// Forward: out[B][L1][80] = maxpool2(|conv1d(x, W, stride 80, pad 200)|), route bits for the backward pass.
+// `img` = scratch for the pre-split bank: 2*6*80*96 bf16 values.
+extern "C" int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T, float* out, uint8_t* route, void* img, void* stream) {
+  if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
+  const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
+  int e = slu_presplit_rows(W, SLU_NTAPS, 1, SLU_STRIDE, 6, SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // bank[c][80a + k], 0 beyond tap 400
+  if (e) return e;
+  static int attr = slu_set_smem((const void*)sincconv_fwd_tc_kernel, FWD_SMEM);
+  if (attr) return attr;
+  dim3 grid((L0 + TF - 1) / TF, B);
+  sincconv_fwd_tc_kernel<<<grid, THREADS, FWD_SMEM, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)img, T, L0, L1, out, route);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}
+
+// Backward: dW[80][401] (zero-filled by the caller) += sum over frames of the routed gradient times the waveform.
+extern "C" int slu_sincconv_bwd_tc(const float* x, const float* gy, const uint8_t* route, int B, int T, float* dW, void* stream) {
+  if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
+  const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
+  const int tiles_per_utt = (L0 + TF - 1) / TF;
+  static int attr = slu_set_smem((const void*)sincconv_bwd_tc_kernel, BWD_SMEM);
+  if (attr) return attr;
+  const long n_tiles = (long)B * tiles_per_utt;
+  const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
+  sincconv_bwd_tc_kernel<<<grid, THREADS, BWD_SMEM, (cudaStream_t)stream>>>(x, gy, route, B, T, L0, L1, tiles_per_utt, dW);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}
