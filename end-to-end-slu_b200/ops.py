@@ -47,6 +47,13 @@ def presplit(W, w_off, sn, sk, stap, taps, N, K):
     return img
 
 
+def wgrad_tc(G, g_off, ldg, M, X, x_off, ldx, N, B, T, out, o_off, s_m, s_n=1, s_tap=0, taps=1, shift0=0):
+    """out[...] += G^T . X over frames (slu_wgrad_tc); `out` must be pre-zeroed for a plain gradient."""
+    _lib.call("slu_wgrad_tc", _eptr(G, g_off), ldg, M, _eptr(X, x_off), ldx, N, B, T, taps, shift0, _eptr(out, o_off), s_m, s_n,
+              s_tap, _lib.stream())
+    return out
+
+
 def _split_k(M, N, K, taps=1):
     tiles = ((M + 127) // 128) * ((N + 127) // 128)          # weight-gradient tiles are 128 x <=128
     kb = taps * ((K + 31) // 32)
@@ -80,7 +87,7 @@ def matmul_tn(g2, x2):
     if GEMM_IMPL != "tc":
         return g2.t() @ x2
     out = torch.zeros(M, N, device=g2.device, dtype=torch.float32)
-    return gemm_tc(g2, 0, 1, M, x2, 0, 1, N, M, N, R, out, split_k=_split_k(M, N, R))
+    return wgrad_tc(g2, 0, M, M, x2, 0, N, N, 1, R, out, 0, N)
 
 
 class ConvBlock(torch.autograd.Function):
@@ -111,13 +118,9 @@ class ConvBlock(torch.autograd.Function):
             # dX[b,t,ci] = sum_d sum_co dpre[b,t-(d-k//2),co] W[co,ci,d]; tap' = k-1-d walks the kernel backwards
             gemm_tc(dpre, 0, Cout, 1, None, 0, 0, 0, B * T, Cin, Cout, dx, taps=k, tap_pad=k // 2, T=T,
                     b_img=presplit(w, k - 1, k, Cin * k, -1, k, Cin, Cout))
-        if ctx.needs_input_grad[1]:
-            dwt = torch.zeros(k, Cout, Cin, device=x.device, dtype=torch.float32)
-            sk = _split_k(Cout, Cin, B * T)
-            for d in range(k):
-                gemm_tc(dpre, 0, 1, Cout, x, 0, 1, Cin, Cout, Cin, B * T, dwt, c_off=d * Cout * Cin, T=T, b_kshift=d - k // 2,
-                        split_k=sk)
-            dw = dwt.permute(1, 2, 0).contiguous()
+        if ctx.needs_input_grad[1]:      # all k taps in one launch, written straight into the [Cout][Cin][k] weight layout
+            dw = torch.zeros(Cout, Cin, k, device=x.device, dtype=torch.float32)
+            wgrad_tc(dpre, 0, Cout, Cout, x, 0, Cin, Cin, B, T, dw, 0, Cin * k, k, 1, taps=k, shift0=-(k // 2))
         if ctx.needs_input_grad[2]:
             db = dpre.sum((0, 1))
         return dx, dw, db, None
@@ -245,17 +248,17 @@ class BiGRU(torch.autograd.Function):
         grads = [None] * 8
         if any(ni[1:9]):
             x2 = x.view(B * T, I)
-            dw_ih = matmul_tn(dgx2, x2)                                         # [768, I]
+            if GEMM_IMPL == "tc":
+                dw_ih = wgrad_tc(dgx, 0, 768, 768, x, 0, I, I, B, T, torch.zeros(768, I, device=dev, dtype=torch.float32), 0, I)
+            else:
+                dw_ih = matmul_tn(dgx2, x2)                                     # [768, I]
             if GEMM_IMPL == "tc":
                 R = B * T
                 dw_hh_cat = torch.zeros(2, 384, H, device=dev, dtype=torch.float32)
-                sk = _split_k(256, H, R)
                 for d in range(2):      # dW_hh[d] = [dr,dz | dhn]^T . h_{t-1}  (h_{t+1} for the reverse direction)
                     sh = 1 if d else -1
-                    gemm_tc(dgx, d * 384, 1, 768, y_full, d * H, 1, 256, 256, H, R, dw_hh_cat, c_off=d * 384 * H, T=T,
-                            b_kshift=sh, split_k=sk)
-                    gemm_tc(dhn, d * H, 1, 256, y_full, d * H, 1, 256, H, H, R, dw_hh_cat, c_off=(d * 384 + 256) * H, T=T,
-                            b_kshift=sh, split_k=sk)
+                    wgrad_tc(dgx, d * 384, 768, 256, y_full, d * H, 256, H, B, T, dw_hh_cat, d * 384 * H, H, shift0=sh)
+                    wgrad_tc(dhn, d * H, 256, H, y_full, d * H, 256, H, B, T, dw_hh_cat, (d * 384 + 256) * H, H, shift0=sh)
             zero = torch.zeros(B, 1, H, device=dev, dtype=torch.float32)
             for d in range(2):
                 if GEMM_IMPL == "tc":

@@ -85,6 +85,13 @@ int slu_gemm_tc(const float* A, long a_sm, long a_sk, const float* B, long b_sn,
 /* Weights (any strides) -> bf16 hi/lo image [2][taps][N][Kp], Kp = K rounded up to 32 (img: 2*taps*N*Kp bf16 values). */
 int slu_presplit_bf16(const float* W, long sn, long sk, long stap, int taps, int N, int K, void* img, void* stream);
 
+/* Weight-gradient GEMM (reduction over frames) with MN-major tcgen05 operands and TMEM-resident accumulators:
+ *   out[m*s_m + n*s_n + tap*s_tap] += sum_{b<B, t<T} G[(b*T+t)*ldg + m] * X[(b*T + t + shift0 + tap)*ldx + n]
+ * (frames outside [0,T) read 0; taps in {1, 5}).  Replaces the backward-weights kernels behind autograd of nn.GRU
+ * (dW_ih, dW_hh with shift0 = -1/+1) and nn.Conv1d (5 taps, shift0 = -2, out in the [Cout][Cin][5] weight layout). */
+int slu_wgrad_tc(const float* G, long ldg, int M, const float* X, long ldx, int N, int B, int T, int taps, int shift0, float* out,
+                 long s_m, long s_n, long s_tap, void* stream);
+
 /* tcgen05 self-test: C[128][N] = A[128][K] . B[N][K]^T (3-pass bf16 split, fp32 accumulate in TMEM). */
 int slu_tc_selftest(const float* A, const float* B, float* C, int N, int K, void* stream);
 /* Same, A operand resident in tensor memory (K <= 128), B tile with a padded leading-byte-offset. */
