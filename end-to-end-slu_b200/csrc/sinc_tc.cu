@@ -36,27 +36,34 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool 
 // Stage the waveform slice of one tile: rows r = 0..XROWS-1 are frames t0 + r, 80 samples each, starting at sample
 // 80*t0 - 200 of utterance xb (zero outside [0, T)).
 __device__ __forceinline__ void stage_wave_image(uint8_t* hi, uint8_t* lo, const float* xb, int t0, int T, int tid) {
-  for (int task = tid; task < XROWS * KC; task += THREADS) {
-    const int r = task / KC, kc = task - r * KC;
-    const int idx0 = SLU_STRIDE * (t0 + r) + kc * 8 - SLU_PAD;
-    float v[8];
-    const float* p = xb + idx0;
-    if (idx0 >= 0 && idx0 + 8 <= T && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
+  for (int base = 0; base < XROWS * KC; base += 4 * THREADS) {       // batches of 4 tasks: 8 loads in flight per thread
+    float v[4][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = idx0 + i;
-        const bool ok = idx >= 0 && idx < T;
-        const float val = __ldg(xb + (ok ? idx : 0));
-        v[i] = ok ? val : 0.f;
+    for (int u = 0; u < 4; ++u) {
+      const int task = base + u * THREADS + tid;
+      const int r = task / KC, kc = task - r * KC;
+      const int idx0 = SLU_STRIDE * (t0 + r) + kc * 8 - SLU_PAD;
+      const float* p = xb + idx0;
+      const bool on = task < XROWS * KC;
+      if (on && idx0 >= 0 && idx0 + 8 <= T && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[u][i] = (on && idx0 + i >= 0 && idx0 + i < T) ? __ldg(p + i) : 0.f;
       }
     }
-    uint4 h, l; split8(v, h, l);
-    const uint32_t off = (uint32_t)kc * LBO_X + (uint32_t)r * 16;
-    *reinterpret_cast<uint4*>(hi + off) = h;
-    *reinterpret_cast<uint4*>(lo + off) = l;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int task = base + u * THREADS + tid;
+      if (task < XROWS * KC) {
+        const int r = task / KC, kc = task - r * KC;
+        uint4 h, l; split8(v[u], h, l);
+        const uint32_t off = (uint32_t)kc * LBO_X + (uint32_t)r * 16;
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        *reinterpret_cast<uint4*>(lo + off) = l;
+      }
+    }
   }
 }
 
@@ -209,25 +216,38 @@ sincconv_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ gy
     uint8_t* x_hi = st; uint8_t* x_lo = st + X_PART; uint8_t* g_hi = st + 2 * X_PART; uint8_t* g_lo = g_hi + G_PART;
     stage_wave_image(x_hi, x_lo, x + (size_t)b * T, t0, T, tid);
     // routed gradient g0[t][c] (through max-pool and abs) for frames t0..t0+127, 8 filters per 16-byte chunk
-    for (int task = tid; task < TF * KC; task += THREADS) {
-      const int r = task / KC, cc = task - r * KC;            // frame row, filter chunk
-      const int t = t0 + r;
-      float v[8];
-      const bool ok = t < L0;
-      const size_t o = ok ? ((size_t)b * L1 + (t >> 1)) * SLU_NFILT + cc * 8 : 0;
-      const float4 ga = __ldg(reinterpret_cast<const float4*>(gy + o)), gb = __ldg(reinterpret_cast<const float4*>(gy + o) + 1);
-      const uint2 rt = __ldg(reinterpret_cast<const uint2*>(route + o));
-      const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    for (int base = 0; base < TF * KC; base += 5 * THREADS) {      // 1280 tasks = 5 per thread, loads batched
+      float4 ga[5], gb[5]; uint2 rt[5]; bool okv[5];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t rb = ((i < 4 ? rt.x : rt.y) >> (8 * (i & 3))) & 0xffu;
-        const bool take = ok && ((rb & 1u) == (uint32_t)(t & 1)) && !(rb & 4u);
-        v[i] = take ? ((rb & 2u) ? -gv[i] : gv[i]) : 0.f;
+      for (int u = 0; u < 5; ++u) {
+        const int task = base + u * THREADS + tid;
+        const int r = task / KC, cc = task - r * KC;            // frame row, filter chunk
+        const int t = t0 + r;
+        okv[u] = task < TF * KC && t < L0;
+        const size_t o = okv[u] ? ((size_t)b * L1 + (t >> 1)) * SLU_NFILT + cc * 8 : 0;
+        ga[u] = __ldg(reinterpret_cast<const float4*>(gy + o)); gb[u] = __ldg(reinterpret_cast<const float4*>(gy + o) + 1);
+        rt[u] = __ldg(reinterpret_cast<const uint2*>(route + o));
       }
-      uint4 h, l; split8(v, h, l);
-      const uint32_t off = (uint32_t)cc * SBO_G + (uint32_t)r * 16;
-      *reinterpret_cast<uint4*>(g_hi + off) = h;
-      *reinterpret_cast<uint4*>(g_lo + off) = l;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int task = base + u * THREADS + tid;
+        if (task < TF * KC) {
+          const int r = task / KC, cc = task - r * KC;
+          const int t = t0 + r;
+          const float gv[8] = {ga[u].x, ga[u].y, ga[u].z, ga[u].w, gb[u].x, gb[u].y, gb[u].z, gb[u].w};
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t rb = ((i < 4 ? rt[u].x : rt[u].y) >> (8 * (i & 3))) & 0xffu;
+            const bool take = okv[u] && ((rb & 1u) == (uint32_t)(t & 1)) && !(rb & 4u);
+            v[i] = take ? ((rb & 2u) ? -gv[i] : gv[i]) : 0.f;
+          }
+          uint4 h, l; split8(v, h, l);
+          const uint32_t off = (uint32_t)cc * SBO_G + (uint32_t)r * 16;
+          *reinterpret_cast<uint4*>(g_hi + off) = h;
+          *reinterpret_cast<uint4*>(g_lo + off) = l;
+        }
+      }
     }
     fence_async_smem();
     __syncthreads();

@@ -85,29 +85,52 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TFW;
     uint8_t* st = smem + s * STAGE;
     uint8_t* a_hi = st; uint8_t* a_lo = st + A_PART; uint8_t* b_hi = st + 2 * A_PART; uint8_t* b_lo = b_hi + B_PART;
+    // Staging in batches of 4 tasks per thread: the 8 16-byte loads of a batch are all in flight before any is converted.
     // G image: frames t0 .. t0+63, chunk cc covers rows m0 + 8cc .. +7
-    for (int task = tid; task < TFW * a_chunks; task += THREADS) {
-      const int r = task / a_chunks, cc = task - r * a_chunks;
-      const int t = t0 + r;
-      float v[8];
-      load_row8(p.G + ((long)b * p.T + min(t, p.T - 1)) * p.ldg + m0 + cc * 8, mv - cc * 8, t < p.T, v);
-      uint4 h, l; split8(v, h, l);
-      const uint32_t off = (uint32_t)cc * SBO_A + (uint32_t)r * 16;
-      *reinterpret_cast<uint4*>(a_hi + off) = h;
-      *reinterpret_cast<uint4*>(a_lo + off) = l;
+    for (int base = 0; base < TFW * a_chunks; base += 4 * THREADS) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int task = base + u * THREADS + tid;
+        const int r = task / a_chunks, cc = task - r * a_chunks;
+        const int t = t0 + r;
+        load_row8(p.G + ((long)b * p.T + min(t, p.T - 1)) * p.ldg + m0 + cc * 8, mv - cc * 8, task < TFW * a_chunks && t < p.T, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int task = base + u * THREADS + tid;
+        if (task < TFW * a_chunks) {
+          const int r = task / a_chunks, cc = task - r * a_chunks;
+          uint4 h, l; split8(v[u], h, l);
+          const uint32_t off = (uint32_t)cc * SBO_A + (uint32_t)r * 16;
+          *reinterpret_cast<uint4*>(a_hi + off) = h;
+          *reinterpret_cast<uint4*>(a_lo + off) = l;
+        }
+      }
     }
     // X image: staged row r is frame t0 + shift0 + r  (r = 0 .. 63 + NTAPS - 1), zero outside the utterance
     constexpr int XROWS = TFW + NTAPS - 1;
-    for (int task = tid; task < XROWS * NCH; task += THREADS) {
-      const int r = task / NCH, cc = task - r * NCH;
-      const int t = t0 + p.shift0 + r;
-      const bool ok = t >= 0 && t < p.T;
-      float v[8];
-      load_row8(p.X + ((long)b * p.T + (ok ? t : 0)) * p.ldx + n0 + cc * 8, nv - cc * 8, ok, v);
-      uint4 h, l; split8(v, h, l);
-      const uint32_t off = (uint32_t)cc * SBO_B + (uint32_t)r * 16;
-      *reinterpret_cast<uint4*>(b_hi + off) = h;
-      *reinterpret_cast<uint4*>(b_lo + off) = l;
+    for (int base = 0; base < XROWS * NCH; base += 4 * THREADS) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int task = base + u * THREADS + tid;
+        const int r = task / NCH, cc = task - r * NCH;
+        const int t = t0 + p.shift0 + r;
+        const bool ok = task < XROWS * NCH && t >= 0 && t < p.T;
+        load_row8(p.X + ((long)b * p.T + (ok ? t : 0)) * p.ldx + n0 + cc * 8, nv - cc * 8, ok, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int task = base + u * THREADS + tid;
+        if (task < XROWS * NCH) {
+          const int r = task / NCH, cc = task - r * NCH;
+          uint4 h, l; split8(v[u], h, l);
+          const uint32_t off = (uint32_t)cc * SBO_B + (uint32_t)r * 16;
+          *reinterpret_cast<uint4*>(b_hi + off) = h;
+          *reinterpret_cast<uint4*>(b_lo + off) = l;
+        }
+      }
     }
     fence_async_smem();
     __syncthreads();
