@@ -85,51 +85,49 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TFW;
     uint8_t* st = smem + s * STAGE;
     uint8_t* a_hi = st; uint8_t* a_lo = st + A_PART; uint8_t* b_hi = st + 2 * A_PART; uint8_t* b_lo = b_hi + B_PART;
-    // Staging in batches of 4 tasks per thread: the 8 16-byte loads of a batch are all in flight before any is converted.
-    // G image: frames t0 .. t0+63, chunk cc covers rows m0 + 8cc .. +7
-    for (int base = 0; base < TFW * a_chunks; base += 4 * THREADS) {
-      float v[4][8];
+    // Staging: every thread first issues ALL its 16-byte loads of this tile (<= 4 G tasks + <= 4 X tasks, 16 loads in
+    // flight), only then converts and stores -- one exposed memory latency per 64-frame tile.
+    // G image: frames t0 .. t0+63, chunk cc covers rows m0 + 8cc .. +7.  X image: staged row r is frame t0 + shift0 + r.
+    constexpr int XROWS = TFW + NTAPS - 1;
+    constexpr int A_PER = 4, B_PER = (XROWS * NCH + THREADS - 1) / THREADS;
+    static_assert(TFW * 16 <= A_PER * THREADS && B_PER <= 4, "staging task counts");
+    const int a_tasks = TFW * a_chunks;
+    float va[A_PER][8], vb[B_PER][8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int task = base + u * THREADS + tid;
+    for (int u = 0; u < A_PER; ++u) {
+      const int task = u * THREADS + tid;
+      const int r = task / a_chunks, cc = task - r * a_chunks;
+      const int t = t0 + r;
+      load_row8(p.G + ((long)b * p.T + min(t, p.T - 1)) * p.ldg + m0 + cc * 8, mv - cc * 8, task < a_tasks && t < p.T, va[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < B_PER; ++u) {
+      const int task = u * THREADS + tid;
+      const int r = task / NCH, cc = task - r * NCH;
+      const int t = t0 + p.shift0 + r;
+      const bool ok = task < XROWS * NCH && t >= 0 && t < p.T;
+      load_row8(p.X + ((long)b * p.T + (ok ? t : 0)) * p.ldx + n0 + cc * 8, nv - cc * 8, ok, vb[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < A_PER; ++u) {
+      const int task = u * THREADS + tid;
+      if (task < a_tasks) {
         const int r = task / a_chunks, cc = task - r * a_chunks;
-        const int t = t0 + r;
-        load_row8(p.G + ((long)b * p.T + min(t, p.T - 1)) * p.ldg + m0 + cc * 8, mv - cc * 8, task < TFW * a_chunks && t < p.T, v[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int task = base + u * THREADS + tid;
-        if (task < TFW * a_chunks) {
-          const int r = task / a_chunks, cc = task - r * a_chunks;
-          uint4 h, l; split8(v[u], h, l);
-          const uint32_t off = (uint32_t)cc * SBO_A + (uint32_t)r * 16;
-          *reinterpret_cast<uint4*>(a_hi + off) = h;
-          *reinterpret_cast<uint4*>(a_lo + off) = l;
-        }
+        uint4 h, l; split8(va[u], h, l);
+        const uint32_t off = (uint32_t)cc * SBO_A + (uint32_t)r * 16;
+        *reinterpret_cast<uint4*>(a_hi + off) = h;
+        *reinterpret_cast<uint4*>(a_lo + off) = l;
       }
     }
-    // X image: staged row r is frame t0 + shift0 + r  (r = 0 .. 63 + NTAPS - 1), zero outside the utterance
-    constexpr int XROWS = TFW + NTAPS - 1;
-    for (int base = 0; base < XROWS * NCH; base += 4 * THREADS) {
-      float v[4][8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int task = base + u * THREADS + tid;
+    for (int u = 0; u < B_PER; ++u) {
+      const int task = u * THREADS + tid;
+      if (task < XROWS * NCH) {
         const int r = task / NCH, cc = task - r * NCH;
-        const int t = t0 + p.shift0 + r;
-        const bool ok = task < XROWS * NCH && t >= 0 && t < p.T;
-        load_row8(p.X + ((long)b * p.T + (ok ? t : 0)) * p.ldx + n0 + cc * 8, nv - cc * 8, ok, v[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int task = base + u * THREADS + tid;
-        if (task < XROWS * NCH) {
-          const int r = task / NCH, cc = task - r * NCH;
-          uint4 h, l; split8(v[u], h, l);
-          const uint32_t off = (uint32_t)cc * SBO_B + (uint32_t)r * 16;
-          *reinterpret_cast<uint4*>(b_hi + off) = h;
-          *reinterpret_cast<uint4*>(b_lo + off) = l;
-        }
+        uint4 h, l; split8(vb[u], h, l);
+        const uint32_t off = (uint32_t)cc * SBO_B + (uint32_t)r * 16;
+        *reinterpret_cast<uint4*>(b_hi + off) = h;
+        *reinterpret_cast<uint4*>(b_lo + off) = l;
       }
     }
     fence_async_smem();
