@@ -78,59 +78,61 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     }
   __syncthreads();
 
+  // Register-prefetch pipeline over this CTA's tiles: the loads of tile i+1 are issued before tile i is converted, so
+  // the memory latency hides behind the conversion, the barrier and the (asynchronous) MMAs.
+  constexpr int XROWS = TFW + NTAPS - 1;
+  constexpr int A_PER = 4, B_PER = (XROWS * NCH + THREADS - 1) / THREADS;
+  static_assert(TFW * 16 <= A_PER * THREADS && B_PER <= 4, "staging task counts");
+  const int a_tasks = TFW * a_chunks;
+  int a_r[A_PER], a_cc[A_PER], b_r[B_PER], b_cc[B_PER];
+#pragma unroll
+  for (int u = 0; u < A_PER; ++u) { const int task = u * THREADS + tid; a_r[u] = task / a_chunks; a_cc[u] = task - a_r[u] * a_chunks; }
+#pragma unroll
+  for (int u = 0; u < B_PER; ++u) { const int task = u * THREADS + tid; b_r[u] = task / NCH; b_cc[u] = task - b_r[u] * NCH; }
+  float va[A_PER][8], vb[B_PER][8];
+  auto issue_loads = [&](int tile) {
+    const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TFW;
+#pragma unroll
+    for (int u = 0; u < A_PER; ++u) {
+      const int t = t0 + a_r[u];
+      load_row8(p.G + ((long)b * p.T + min(t, p.T - 1)) * p.ldg + m0 + a_cc[u] * 8, mv - a_cc[u] * 8,
+                u * THREADS + tid < a_tasks && t < p.T, va[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < B_PER; ++u) {
+      const int t = t0 + p.shift0 + b_r[u];
+      const bool ok = u * THREADS + tid < XROWS * NCH && t >= 0 && t < p.T;
+      load_row8(p.X + ((long)b * p.T + (ok ? t : 0)) * p.ldx + n0 + b_cc[u] * 8, nv - b_cc[u] * 8, ok, vb[u]);
+    }
+  };
+  if ((int)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
+
   int it = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int s = it & 1;
     if (it >= 2) mbar_wait(&empty_bar[s], (uint32_t)(((it >> 1) - 1) & 1));
-    const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TFW;
     uint8_t* st = smem + s * STAGE;
     uint8_t* a_hi = st; uint8_t* a_lo = st + A_PART; uint8_t* b_hi = st + 2 * A_PART; uint8_t* b_lo = b_hi + B_PART;
-    // Staging: every thread first issues ALL its 16-byte loads of this tile (<= 4 G tasks + <= 4 X tasks, 16 loads in
-    // flight), only then converts and stores -- one exposed memory latency per 64-frame tile.
-    // G image: frames t0 .. t0+63, chunk cc covers rows m0 + 8cc .. +7.  X image: staged row r is frame t0 + shift0 + r.
-    constexpr int XROWS = TFW + NTAPS - 1;
-    constexpr int A_PER = 4, B_PER = (XROWS * NCH + THREADS - 1) / THREADS;
-    static_assert(TFW * 16 <= A_PER * THREADS && B_PER <= 4, "staging task counts");
-    const int a_tasks = TFW * a_chunks;
-    float va[A_PER][8], vb[B_PER][8];
 #pragma unroll
     for (int u = 0; u < A_PER; ++u) {
-      const int task = u * THREADS + tid;
-      const int r = task / a_chunks, cc = task - r * a_chunks;
-      const int t = t0 + r;
-      load_row8(p.G + ((long)b * p.T + min(t, p.T - 1)) * p.ldg + m0 + cc * 8, mv - cc * 8, task < a_tasks && t < p.T, va[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < B_PER; ++u) {
-      const int task = u * THREADS + tid;
-      const int r = task / NCH, cc = task - r * NCH;
-      const int t = t0 + p.shift0 + r;
-      const bool ok = task < XROWS * NCH && t >= 0 && t < p.T;
-      load_row8(p.X + ((long)b * p.T + (ok ? t : 0)) * p.ldx + n0 + cc * 8, nv - cc * 8, ok, vb[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < A_PER; ++u) {
-      const int task = u * THREADS + tid;
-      if (task < a_tasks) {
-        const int r = task / a_chunks, cc = task - r * a_chunks;
+      if (u * THREADS + tid < a_tasks) {
         uint4 h, l; split8(va[u], h, l);
-        const uint32_t off = (uint32_t)cc * SBO_A + (uint32_t)r * 16;
+        const uint32_t off = (uint32_t)a_cc[u] * SBO_A + (uint32_t)a_r[u] * 16;
         *reinterpret_cast<uint4*>(a_hi + off) = h;
         *reinterpret_cast<uint4*>(a_lo + off) = l;
       }
     }
 #pragma unroll
     for (int u = 0; u < B_PER; ++u) {
-      const int task = u * THREADS + tid;
-      if (task < XROWS * NCH) {
-        const int r = task / NCH, cc = task - r * NCH;
+      if (u * THREADS + tid < XROWS * NCH) {
         uint4 h, l; split8(vb[u], h, l);
-        const uint32_t off = (uint32_t)cc * SBO_B + (uint32_t)r * 16;
+        const uint32_t off = (uint32_t)b_cc[u] * SBO_B + (uint32_t)b_r[u] * 16;
         *reinterpret_cast<uint4*>(b_hi + off) = h;
         *reinterpret_cast<uint4*>(b_lo + off) = l;
       }
     }
-    fence_async_smem();
+    fence_async_smem();                                   // before the prefetch: the proxy fence would wait for those loads
+    if (tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x);
     __syncthreads();
     if (warp == 0) {
       if (elect_one()) {
