@@ -163,18 +163,27 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     __syncwarp();
     mbar_wait(&acc_bar, 0);
     fence_after_sync();
+    // flush: per warp 32 rows x 16 columns through a shared-memory transpose so that every red.add instruction covers
+    // two rows x 16 consecutive columns (coalesced when s_n == 1)
     const int q = warp & 3, half = warp >> 2;
-    const int m = q * 32 + lane;
-    for (int c0 = half * 16; c0 < NTAPS * N; c0 += 32) {        // two warps per lane quarter alternate 16-column groups
+    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 17);        // stage buffers are idle after acc_bar
+    for (int c0 = half * 16; c0 < NTAPS * N; c0 += 32) {                  // two warps per lane quarter alternate 16-column groups
       float v[16];
       tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
       tmem_ld_wait();
-      if (m < mv) {
-        const int tap = c0 / N, nb = c0 - tap * N;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (nb + i < nv) atomicAdd(p.out + (long)(m0 + m) * p.s_m + (long)(n0 + nb + i) * p.s_n + (long)tap * p.s_tap, v[i]);
+      for (int i = 0; i < 16; ++i) tr[lane * 17 + i] = v[i];
+      __syncwarp();
+      const int tap = c0 / N, nb = c0 - tap * N + (lane & 15);
+      if (nb < nv) {
+        float* dst = p.out + (long)(n0 + nb) * p.s_n + (long)tap * p.s_tap;
+#pragma unroll 4
+        for (int rr = 0; rr < 16; ++rr) {
+          const int m = q * 32 + 2 * rr + (lane >> 4);
+          if (m < mv) atomicAdd(dst + (long)(m0 + m) * p.s_m, tr[(2 * rr + (lane >> 4)) * 17 + (lane & 15)]);
+        }
       }
+      __syncwarp();
     }
   }
   fence_before_sync();
@@ -188,9 +197,9 @@ int launch(const WgradParams& p, int m_tiles, int n_tiles_n, cudaStream_t st) {
   static int attr = slu_set_smem((const void*)wgrad_tc_kernel<NTAPS, NCH>, smem);
   if (attr) return attr;
   const long n_tiles = (long)p.B * p.tiles_per_utt;
-  int gx = 148 / (m_tiles * n_tiles_n);
+  int gx = 148 / (m_tiles * n_tiles_n);                  // CTAs per output tile: fill the SMs ...
+  if (gx > n_tiles / 6) gx = (int)(n_tiles / 6);        // ... but give every CTA >= 6 frame tiles per atomic flush
   if (gx < 1) gx = 1;
-  if (gx > n_tiles) gx = (int)n_tiles;
   wgrad_tc_kernel<NTAPS, NCH><<<dim3(gx, m_tiles, n_tiles_n), THREADS, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
