@@ -222,14 +222,21 @@ def main():
                     "executed_tflops": 3 * ach if pkg.ops.GRU_IMPL == "tc" else ach,
                     "note": "persistent-GRU forward, 5 launches/step summed; algorithmic flops = 2 dirs * T_l * 2*384*128 * B over the "
                             "5 layers (h.W_hh only; the bf16 hi/lo 3-pass split executes 3x that on the tensor core). The recurrence is "
-                            "latency-bound at 32 CTAs: see DESIGN.md section 4"}
+                            "latency-bound (128 CTAs of 4 batch rows at B=256): see DESIGN.md section 4"}
     sinc_names = [k for k in prof if k.startswith("slu_sincconv_fwd")]
     if sinc_names:
         name = sinc_names[0]
         bytes_ = B * (4 * T_SAMPLES + 4 * 80 * 400)
         sec = kern[name]["ms_per_step"] * 1e-3
+        tr_s = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                tr_s = json.load(f).get(name, {}).get("bytes_per_launch")
+        except Exception:
+            pass
         extra["roofline_sincconv"] = {"kernel": name, "bound": "hbm", "achieved": bytes_ / sec / 1e9, "peak": hbm_peak,
-                                      "unit": "GB/s", "frac": bytes_ / sec / 1e9 / hbm_peak, "traffic": None}
+                                      "unit": "GB/s", "frac": bytes_ / sec / 1e9 / hbm_peak, "traffic": tr_s,
+                                      "note": "algorithmic bytes = B*(4*T + 4*80*L1) = read the waveform once, write the pooled frames once"}
 
     line = None
     if rank == 0:
