@@ -29,13 +29,10 @@ def _eptr(t, off=0):
     return t.data_ptr() + 4 * off
 
 
-def gemm_tc(A, a_off, a_sm, a_sk, Bm, b_off, b_sn, b_sk, M, N, K, out, c_off=0, ldc=None, bias=None, taps=1, tap_pad=0,
-            T=0, a_kshift=0, b_kshift=0, b_stap=0, split_k=1, act=0, slope=0.0, b_img=None):
-    """Raw strided call of slu_gemm_tc (see include/slu_b200.h).  `out` must be zero-filled when split_k > 1."""
-    _lib.call("slu_gemm_tc", _eptr(A, a_off), a_sm, a_sk, None if Bm is None else _eptr(Bm, b_off), b_sn, b_sk, b_stap,
-              None if b_img is None else b_img.data_ptr(), None if bias is None else _eptr(bias), _eptr(out, c_off),
-              N if ldc is None else ldc, M, N, K, taps, tap_pad, T, a_kshift, b_kshift, split_k, act, float(slope),
-              _lib.stream())
+def gemm_tc(A, lda, w_img, M, N, K, out, bias=None, taps=1, tap_pad=0, T=0, act=0, slope=0.0):
+    """out[M,N] = sum_tap A[(m+tap-tap_pad)*lda + k] * W(n,tap,k) (+bias)(LeakyReLU) -- slu_gemm_tc, see include/slu_b200.h."""
+    _lib.call("slu_gemm_tc", _eptr(A), lda, w_img.data_ptr(), None if bias is None else _eptr(bias), _eptr(out), N, M, N, K, taps,
+              tap_pad, T, act, float(slope), _lib.stream())
     return out
 
 
@@ -54,12 +51,6 @@ def wgrad_tc(G, g_off, ldg, M, X, x_off, ldx, N, B, T, out, o_off, s_m, s_n=1, s
     return out
 
 
-def _split_k(M, N, K, taps=1):
-    tiles = ((M + 127) // 128) * ((N + 127) // 128)          # weight-gradient tiles are 128 x <=128
-    kb = taps * ((K + 31) // 32)
-    return max(1, min(kb, 296 // max(1, tiles)))
-
-
 def linear_nt(x2, w, bias=None):
     """x2 [M,K] @ w[N,K]^T + bias -> [M,N]."""
     M, K = x2.shape
@@ -67,7 +58,7 @@ def linear_nt(x2, w, bias=None):
     if GEMM_IMPL != "tc":
         return torch.addmm(bias, x2, w.t()) if bias is not None else x2 @ w.t()
     out = torch.empty(M, N, device=x2.device, dtype=torch.float32)
-    return gemm_tc(x2, 0, K, 1, None, 0, 0, 0, M, N, K, out, bias=bias, b_img=presplit(w, 0, K, 1, 0, 1, N, K))
+    return gemm_tc(x2, K, presplit(w, 0, K, 1, 0, 1, N, K), M, N, K, out, bias=bias)
 
 
 def matmul_nn(a2, w):
@@ -77,7 +68,7 @@ def matmul_nn(a2, w):
     if GEMM_IMPL != "tc":
         return a2 @ w
     out = torch.empty(M, N, device=a2.device, dtype=torch.float32)
-    return gemm_tc(a2, 0, K, 1, None, 0, 0, 0, M, N, K, out, b_img=presplit(w, 0, 1, N, 0, 1, N, K))
+    return gemm_tc(a2, K, presplit(w, 0, 1, N, 0, 1, N, K), M, N, K, out)
 
 
 def matmul_tn(g2, x2):
@@ -100,8 +91,8 @@ class ConvBlock(torch.autograd.Function):
         Cout, _, k = weight.shape
         w = weight.detach().contiguous()
         out = torch.empty(B, T, Cout, device=x.device, dtype=torch.float32)
-        gemm_tc(x, 0, Cin, 1, None, 0, 0, 0, B * T, Cout, Cin, out, bias=bias.detach(), taps=k, tap_pad=k // 2, T=T,
-                act=1, slope=slope, b_img=presplit(w, 0, Cin * k, k, 1, k, Cout, Cin))
+        gemm_tc(x, Cin, presplit(w, 0, Cin * k, k, 1, k, Cout, Cin), B * T, Cout, Cin, out, bias=bias.detach(), taps=k,
+                tap_pad=k // 2, T=T, act=1, slope=slope)
         ctx.save_for_backward(x, w, out)
         ctx.slope = slope
         return out
@@ -116,8 +107,7 @@ class ConvBlock(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, Cin, device=x.device, dtype=torch.float32)
             # dX[b,t,ci] = sum_d sum_co dpre[b,t-(d-k//2),co] W[co,ci,d]; tap' = k-1-d walks the kernel backwards
-            gemm_tc(dpre, 0, Cout, 1, None, 0, 0, 0, B * T, Cin, Cout, dx, taps=k, tap_pad=k // 2, T=T,
-                    b_img=presplit(w, k - 1, k, Cin * k, -1, k, Cin, Cout))
+            gemm_tc(dpre, Cout, presplit(w, k - 1, k, Cin * k, -1, k, Cin, Cout), B * T, Cin, Cout, dx, taps=k, tap_pad=k // 2, T=T)
         if ctx.needs_input_grad[1]:      # all k taps in one launch, written straight into the [Cout][Cin][k] weight layout
             dw = torch.zeros(Cout, Cin, k, device=x.device, dtype=torch.float32)
             wgrad_tc(dpre, 0, Cout, Cout, x, 0, Cin, Cin, B, T, dw, 0, Cin * k, k, 1, taps=k, shift0=-(k // 2))

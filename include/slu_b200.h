@@ -72,17 +72,14 @@ int slu_set_gru_precision(int mode);
 int slu_debug_gru_phase_clocks(long long* buf);
 
 /* Dense "tap-GEMM" on tcgen05 (fp32 in/out, 3-pass bf16 split, fp32 accumulate in TMEM) -- replaces the cuBLAS / cuDNN
- * calls behind nn.GRU's input projection (models.py:232/262/686), nn.Conv1d (models.py:200) and their autograd:
- *   C[m][n] (+)= sum_tap sum_k A(m,tap,k) * B(n,tap,k) (+ bias[n]) (LeakyReLU if act==1)
- *   A(m,tap,k) = A[(m + tap - tap_pad)*a_sm + k*a_sk]   (a_sk==1; rows leaving their T-frame utterance read as 0), or,
- *                when a_sk != 1 (reduction over frames): A[m*a_sm + (k + a_kshift)*a_sk], 0 if frame k%T + a_kshift leaves [0,T)
- *   B(n,tap,k) = B[n*b_sn + k*b_sk + tap*b_stap]        (b_sk != 1: frame-shifted by b_kshift like A)
- * b_img (optional): the B operand pre-split by slu_presplit_bf16 (then B/b_s* are ignored).
- * split_k > 1 accumulates with fp32 atomics into a caller-zeroed C. */
-int slu_gemm_tc(const float* A, long a_sm, long a_sk, const float* B, long b_sn, long b_sk, long b_stap, const void* b_img,
-                const float* bias, float* C, long ldc, int M, int N, int K, int taps, int tap_pad, int T, int a_kshift,
-                int b_kshift, int split_k, int act, float slope, void* stream);
-/* Weights (any strides) -> bf16 hi/lo image [2][taps][N][Kp], Kp = K rounded up to 32 (img: 2*taps*N*Kp bf16 values). */
+ * calls behind nn.GRU's input projection (models.py:232/262/686), nn.Conv1d (models.py:200) and their input gradients:
+ *   C[m][n] = sum_tap sum_k A[(m + tap - tap_pad)*lda + k] * W(n, tap, k) (+ bias[n]) (LeakyReLU(slope) if act == 1)
+ * Rows are frames of utterances of T frames (T = 0: no boundary); rows shifted out of their utterance read as 0 (conv padding).
+ * w_img = the weight operand pre-split by slu_presplit_bf16. */
+int slu_gemm_tc(const float* A, long lda, const void* w_img, const float* bias, float* C, long ldc, int M, int N, int K, int taps,
+                int tap_pad, int T, int act, float slope, void* stream);
+/* Weights W(n, tap, k) = W[n*sn + k*sk + tap*stap] (any strides, so transposed / reversed-tap views cost nothing) -> bf16 hi/lo
+ * image [2][taps][N][Kp], Kp = K rounded up to 32 (img: 2*taps*N*Kp bf16 values). */
 int slu_presplit_bf16(const float* W, long sn, long sk, long stap, int taps, int N, int K, void* img, void* stream);
 
 /* Weight-gradient GEMM (reduction over frames) with MN-major tcgen05 operands and TMEM-resident accumulators:
