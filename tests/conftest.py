@@ -18,3 +18,10 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_library_is_built():
+    """Build (or refresh) the in-tree C-ABI library before any test touches it; a no-op when it is up to date."""
+    import __graft_entry__ as g
+    g.build()
