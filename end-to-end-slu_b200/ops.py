@@ -13,9 +13,6 @@ H = 128
 # Which persistent-GRU kernel family runs the recurrence: "tc" = tcgen05 (weights stationary in TMEM),
 # "simt" = fp32 CUDA-core variant.  Both are sm_100a kernels of this library with identical contracts.
 GRU_IMPL = os.environ.get("SLU_GRU_IMPL", "tc")
-# Dense contractions (x-projection, CNN tail, weight/input gradients): "tc" = this library's tcgen05 tap-GEMM,
-# "lib" = cuBLAS fp32 through torch (plain library GEMMs).
-GEMM_IMPL = os.environ.get("SLU_GEMM_IMPL", "tc")
 # SincConv: "tc" = tcgen05 6-tap framing GEMM, "simt" = fp32 CUDA-core kernel.
 SINC_IMPL = os.environ.get("SLU_SINC_IMPL", "tc")
 
@@ -55,8 +52,6 @@ def linear_nt(x2, w, bias=None):
     """x2 [M,K] @ w[N,K]^T + bias -> [M,N]."""
     M, K = x2.shape
     N = w.shape[0]
-    if GEMM_IMPL != "tc":
-        return torch.addmm(bias, x2, w.t()) if bias is not None else x2 @ w.t()
     out = torch.empty(M, N, device=x2.device, dtype=torch.float32)
     return gemm_tc(x2, K, presplit(w, 0, K, 1, 0, 1, N, K), M, N, K, out, bias=bias)
 
@@ -65,18 +60,14 @@ def matmul_nn(a2, w):
     """a2 [M,K] @ w[K,N] -> [M,N]  (w row-major, i.e. the 'transposed weight' operand of an input gradient)."""
     M, K = a2.shape
     N = w.shape[1]
-    if GEMM_IMPL != "tc":
-        return a2 @ w
     out = torch.empty(M, N, device=a2.device, dtype=torch.float32)
     return gemm_tc(a2, K, presplit(w, 0, 1, N, 0, 1, N, K), M, N, K, out)
 
 
 def matmul_tn(g2, x2):
-    """g2[R,M]^T @ x2[R,N] -> [M,N]: weight gradient, reduction over the R frames (split-K + fp32 atomics)."""
+    """g2[R,M]^T @ x2[R,N] -> [M,N]: weight gradient, reduction over the R frames."""
     R, M = g2.shape
     N = x2.shape[1]
-    if GEMM_IMPL != "tc":
-        return g2.t() @ x2
     out = torch.zeros(M, N, device=g2.device, dtype=torch.float32)
     return wgrad_tc(g2, 0, M, M, x2, 0, N, N, 1, R, out, 0, N)
 
@@ -117,9 +108,7 @@ class ConvBlock(torch.autograd.Function):
 
 
 def conv_block(x, weight, bias, slope):
-    if GEMM_IMPL == "tc":
-        return ConvBlock.apply(x, weight, bias, slope)
-    return conv_block_nlc(x, weight, bias, slope)
+    return ConvBlock.apply(x, weight, bias, slope)
 
 
 def set_gru_precision(mode):
@@ -181,18 +170,6 @@ def sinc_filters(filt_b1, filt_band):
     return W
 
 
-def conv_block_nlc(x, weight, bias, negative_slope=0.2):
-    """Conv1d(k, pad=k//2) + LeakyReLU on NLC input (models.py:200-220), as one dense GEMM over
-    the k time-shifted views.  x [B,T,Cin], weight [Cout,Cin,k] (reference layout) -> [B,T,Cout]."""
-    B, T, Cin = x.shape
-    Cout, _, k = weight.shape
-    xp = torch.nn.functional.pad(x, (0, 0, k // 2, k // 2))
-    cols = torch.cat([xp[:, d:d + T, :] for d in range(k)], dim=2)            # [B,T,k*Cin]
-    wm = weight.permute(2, 1, 0).reshape(k * Cin, Cout)
-    out = torch.addmm(bias, cols.reshape(B * T, k * Cin), wm).view(B, T, Cout)
-    return torch.nn.functional.leaky_relu(out, negative_slope)
-
-
 class BiGRU(torch.autograd.Function):
     """Bidirectional single-layer GRU (H=128, h0=0) + Dropout(mask) + Downsample(avg 2 | none 1).
     Reference: nn.GRU at models.py:232/262/686, RNNSelect :138-149, Dropout :246, Downsample :26-46.
@@ -237,29 +214,14 @@ class BiGRU(torch.autograd.Function):
         dx = matmul_nn(dgx2, w_ih_cat.contiguous()).view(B, T, I) if ni[0] else None
         grads = [None] * 8
         if any(ni[1:9]):
-            x2 = x.view(B * T, I)
-            if GEMM_IMPL == "tc":
-                dw_ih = wgrad_tc(dgx, 0, 768, 768, x, 0, I, I, B, T, torch.zeros(768, I, device=dev, dtype=torch.float32), 0, I)
-            else:
-                dw_ih = matmul_tn(dgx2, x2)                                     # [768, I]
-            if GEMM_IMPL == "tc":
-                R = B * T
-                dw_hh_cat = torch.zeros(2, 384, H, device=dev, dtype=torch.float32)
-                for d in range(2):      # dW_hh[d] = [dr,dz | dhn]^T . h_{t-1}  (h_{t+1} for the reverse direction)
-                    sh = 1 if d else -1
-                    wgrad_tc(dgx, d * 384, 768, 256, y_full, d * H, 256, H, B, T, dw_hh_cat, d * 384 * H, H, shift0=sh)
-                    wgrad_tc(dhn, d * H, 256, H, y_full, d * H, 256, H, B, T, dw_hh_cat, (d * 384 + 256) * H, H, shift0=sh)
-            zero = torch.zeros(B, 1, H, device=dev, dtype=torch.float32)
-            for d in range(2):
-                if GEMM_IMPL == "tc":
-                    dw_hh = dw_hh_cat[d]
-                else:
-                    hd = y_full[:, :, d * H:(d + 1) * H]
-                    hprev = torch.cat([zero, hd[:, :-1]], 1) if d == 0 else torch.cat([hd[:, 1:], zero], 1)
-                    gd = torch.cat([dgx[:, :, d * 384:d * 384 + 256], dhn[:, :, d * H:(d + 1) * H]], 2).reshape(B * T, 384)
-                    dw_hh = gd.t() @ hprev.reshape(B * T, H)
+            dw_ih = wgrad_tc(dgx, 0, 768, 768, x, 0, I, I, B, T, torch.zeros(768, I, device=dev, dtype=torch.float32), 0, I)
+            dw_hh = torch.zeros(2, 384, H, device=dev, dtype=torch.float32)
+            for d in range(2):          # dW_hh[d] = [dr,dz | dhn]^T . h_{t-1}  (h_{t+1} for the reverse direction)
+                sh = 1 if d else -1
+                wgrad_tc(dgx, d * 384, 768, 256, y_full, d * H, 256, H, B, T, dw_hh, d * 384 * H, H, shift0=sh)
+                wgrad_tc(dhn, d * H, 256, H, y_full, d * H, 256, H, B, T, dw_hh, (d * 384 + 256) * H, H, shift0=sh)
                 grads[4 * d + 0] = dw_ih[d * 384:(d + 1) * 384]
-                grads[4 * d + 1] = dw_hh
+                grads[4 * d + 1] = dw_hh[d]
                 grads[4 * d + 2] = dbias[d, :3].reshape(384)                                   # b_ih: dr, dz, dn
                 grads[4 * d + 3] = torch.cat([dbias[d, :2].reshape(256), dbias[d, 3]])         # b_hh: dr, dz, dhn
         return (dx, *grads, None, None)

@@ -129,13 +129,11 @@ def test_sinc_frontend_fwd_bwd(pkg, monkeypatch, impl, B, T):
         assert (got - ref_g).abs().max().item() < tol, ((got - ref_g).abs().max().item(), scale)
 
 
-@pytest.mark.parametrize("gemm", ["lib", "tc"])
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("B,T,I,ds,use_mask", [(3, 7, 60, 2, False), (17, 9, 256, 2, True), (40, 5, 60, 1, False), (4, 24, 256, 2, True), (5, 23, 256, 1, True),
                                                (1, 1, 256, 2, False), (9, 50, 60, 2, False), (2, 360, 60, 2, False)])
-def test_bigru_fwd_bwd(pkg, monkeypatch, gemm, impl, B, T, I, ds, use_mask):
+def test_bigru_fwd_bwd(pkg, monkeypatch, impl, B, T, I, ds, use_mask):
     monkeypatch.setattr(pkg.ops, "GRU_IMPL", impl)
-    monkeypatch.setattr(pkg.ops, "GEMM_IMPL", gemm)
     rs = np.random.RandomState(B * 100 + T)
     gru = torch.nn.GRU(I, 128, batch_first=True, bidirectional=True)
     with torch.no_grad():
@@ -164,7 +162,6 @@ def test_bigru_fwd_bwd(pkg, monkeypatch, gemm, impl, B, T, I, ds, use_mask):
 
 @pytest.mark.parametrize("M,K,N", [(300, 60, 768), (257, 256, 768), (128, 256, 24), (1000, 768, 60), (130, 768, 256)])
 def test_gemm_tc_linear_and_input_grad(pkg, monkeypatch, M, K, N):
-    monkeypatch.setattr(pkg.ops, "GEMM_IMPL", "tc")
     rs = np.random.RandomState(M + K + N)
     x = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).cuda()
     w = torch.from_numpy(rs.standard_normal((N, K)).astype(np.float32)).cuda()
@@ -177,7 +174,6 @@ def test_gemm_tc_linear_and_input_grad(pkg, monkeypatch, M, K, N):
 
 @pytest.mark.parametrize("R,M,N", [(1000, 768, 60), (5000, 768, 256), (333, 60, 80), (4096, 256, 128)])
 def test_gemm_tc_weight_grad_splitk(pkg, monkeypatch, R, M, N):
-    monkeypatch.setattr(pkg.ops, "GEMM_IMPL", "tc")
     rs = np.random.RandomState(R + M + N)
     g = torch.from_numpy(rs.standard_normal((R, M)).astype(np.float32)).cuda()
     x = torch.from_numpy(rs.standard_normal((R, N)).astype(np.float32)).cuda()
@@ -187,7 +183,6 @@ def test_gemm_tc_weight_grad_splitk(pkg, monkeypatch, R, M, N):
 
 @pytest.mark.parametrize("B,T,Cin,Cout", [(3, 37, 80, 60), (2, 1, 60, 60), (5, 400, 60, 60), (1, 130, 80, 60)])
 def test_conv_block_tc_fwd_bwd(pkg, monkeypatch, B, T, Cin, Cout):
-    monkeypatch.setattr(pkg.ops, "GEMM_IMPL", "tc")
     rs = np.random.RandomState(B * 1000 + T)
     x = torch.from_numpy(rs.standard_normal((B, Cin, T)).astype(np.float32)).requires_grad_(True)
     w = torch.from_numpy(rs.uniform(-0.1, 0.1, (Cout, Cin, 5)).astype(np.float32)).requires_grad_(True)
@@ -227,12 +222,3 @@ def test_bigru_fp16_single_pass_mode(pkg, monkeypatch, B, T, I, ds):
             assert rel_err(v.grad.cpu(), gru.get_parameter(k).grad) < 1e-2, k
     finally:
         pkg.ops.set_gru_precision("bf16x3")
-
-
-def test_conv_block_nlc(pkg):
-    rs = np.random.RandomState(5)
-    x = torch.from_numpy(rs.standard_normal((3, 80, 37)).astype(np.float32))
-    w = torch.from_numpy(rs.uniform(-0.1, 0.1, (60, 80, 5)).astype(np.float32)); b = torch.from_numpy(rs.uniform(-0.1, 0.1, 60).astype(np.float32))
-    ref = R.conv_block(x, w, b).transpose(1, 2)
-    out = pkg.ops.conv_block_nlc(x.transpose(1, 2).contiguous().cuda(), w.cuda(), b.cuda())
-    assert rel_err(out.cpu(), ref) < FWD_TOL
