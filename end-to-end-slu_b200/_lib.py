@@ -27,6 +27,7 @@ SIGNATURES = {
     "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_set_gru_precision": [_I],
     "slu_debug_gru_phase_clocks": [_P],
+    "slu_dropout_mask": [_P, _L, _F, ctypes.c_ulonglong, _P],
     "slu_gemm_tc": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "slu_presplit_bf16": [_P, _L, _L, _L, _I, _I, _I, _P, _P],
     "slu_wgrad_tc": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P],

@@ -1,0 +1,65 @@
+// Dropout keep-mask generator (nn.Dropout at reference models.py:246/276/700, training mode).
+// One pass: Philox4x32-10 keyed by a 64-bit seed, counter = index of the float4 -> four Bernoulli(1-p) draws, written
+// already scaled by 1/(1-p) as the fp32 mask rows the persistent-GRU kernels stream through their TMA ring.
+// HBM-bound: 4 B written per element, nothing read.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  c[0] = hi1 ^ c[1] ^ k0;
+  c[1] = lo1;
+  c[2] = hi0 ^ c[3] ^ k1;
+  c[3] = lo0;
+}
+
+__device__ __forceinline__ void philox4x32_10(uint64_t ctr, uint64_t seed, uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+
+__global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ mask, long n, uint32_t keep_threshold, float scale,
+                                                           uint64_t seed) {
+  const long n4 = (n + 3) >> 2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    uint32_t r[4];
+    philox4x32_10((uint64_t)i, seed, r);
+    float4 v;
+    v.x = r[0] < keep_threshold ? scale : 0.f;     // P(keep) = keep_threshold / 2^32
+    v.y = r[1] < keep_threshold ? scale : 0.f;
+    v.z = r[2] < keep_threshold ? scale : 0.f;
+    v.w = r[3] < keep_threshold ? scale : 0.f;
+    if (4 * i + 3 < n) {
+      reinterpret_cast<float4*>(mask)[i] = v;
+    } else {
+      const float t[4] = {v.x, v.y, v.z, v.w};
+      for (long j = 4 * i; j < n; ++j) mask[j] = t[j - 4 * i];
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int slu_dropout_mask(float* mask, long n, float p, unsigned long long seed, void* stream) {
+  if (n <= 0) return 0;
+  if (!(p >= 0.f && p < 1.f)) return (int)cudaErrorInvalidValue;
+  const double keep = 1.0 - (double)p;
+  const double th = keep * 4294967296.0;
+  const uint32_t threshold = th >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)th;
+  const long n4 = (n + 3) >> 2;
+  long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dropout_mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, n, threshold, (float)(1.0 / keep), seed);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}

@@ -7,7 +7,7 @@ no silent fallback to library kernels or to the CPU.
 """
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 class Plan:
@@ -80,7 +80,10 @@ def downsample_factor(down):
 def _drop_mask(shape, p, training, device):
     if not training or p <= 0.0:
         return None
-    return torch.empty(shape, device=device, dtype=torch.float32).bernoulli_(1.0 - p).div_(1.0 - p)
+    mask = torch.empty(shape, device=device, dtype=torch.float32)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())        # host draw from torch's CPU generator: follows torch.manual_seed
+    _lib.call("slu_dropout_mask", _lib.ptr(mask), mask.numel(), float(p), seed, _lib.stream())
+    return mask
 
 
 def _run_rnns(out, rnns, training):

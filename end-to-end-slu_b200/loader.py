@@ -1,0 +1,54 @@
+"""Device prefetch for the Trainer's batch loop (the H2D copy either side of the path).
+
+The reference moves each batch inside `forward` (`models.py:300-303`, `351-352`: `x = x.cuda()`), a synchronous pageable
+copy in front of every step.  `DevicePrefetcher` wraps any iterable of batches (the `DataLoader` `training.py:57/92`
+iterates): it pins each host tensor and copies batch i+1 on a copy stream while batch i computes, handing the step
+device tensors (`forward` accepts those unchanged, as in the README snippet).  Host logic only -- no kernels.
+"""
+import torch
+
+
+class DevicePrefetcher:
+    def __init__(self, loader, device=None, depth=1):
+        self.loader = loader
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.depth = max(1, depth)
+        self.h2d_bytes = 0
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _stage(self, batch, stream):
+        with torch.cuda.stream(stream):
+            out = []
+            for t in batch:
+                if torch.is_tensor(t) and not t.is_cuda:
+                    if not t.is_pinned():
+                        t = t.pin_memory()
+                    self.h2d_bytes += t.numel() * t.element_size()
+                    t = t.to(self.device, non_blocking=True)
+                out.append(t)
+            return tuple(out), stream.record_event()
+
+    def __iter__(self):
+        stream = torch.cuda.Stream(device=self.device)
+        it = iter(self.loader)
+        staged = []
+        try:
+            while len(staged) < self.depth:
+                staged.append(self._stage(next(it), stream))
+        except StopIteration:
+            it = None
+        while staged:
+            batch, ready = staged.pop(0)
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ready)
+            for t in batch:
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(cur)              # allocated on the copy stream, consumed on the compute stream
+            if it is not None:
+                try:
+                    staged.append(self._stage(next(it), stream))
+                except StopIteration:
+                    it = None
+            yield batch

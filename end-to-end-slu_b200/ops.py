@@ -17,6 +17,40 @@ GRU_IMPL = os.environ.get("SLU_GRU_IMPL", "tc")
 SINC_IMPL = os.environ.get("SLU_SINC_IMPL", "tc")
 
 
+# Weight-gradient launches of one layer are independent of each other and of the input-gradient GEMM: they go to side
+# streams (forked after the producer kernel, joined before the autograd node returns), so the small grids share the GPU.
+OVERLAP = os.environ.get("SLU_OVERLAP", "1") != "0"
+_side = {}
+
+
+class _Fork:
+    """fork(): side streams wait for everything queued on the current stream; run(i, fn): fn's launches go to side stream
+    i; join(): the current stream waits for the side streams.  All tensors involved are allocated on the current stream
+    BEFORE the fork and stay referenced until after the join, so the caching allocator never sees cross-stream reuse."""
+
+    def __init__(self, device, n=4):
+        self.main = torch.cuda.current_stream(device)
+        self.streams = []
+        if OVERLAP:
+            pool = _side.setdefault(device.index, [])
+            while len(pool) < n:
+                pool.append(torch.cuda.Stream(device=device))
+            self.streams = pool[:n]
+            ev = self.main.record_event()
+            for st in self.streams:
+                st.wait_event(ev)
+
+    def run(self, i, fn):
+        if not self.streams:
+            return fn()
+        with torch.cuda.stream(self.streams[i % len(self.streams)]):
+            return fn()
+
+    def join(self):
+        for st in self.streams:
+            self.main.wait_stream(st)
+
+
 def _f32(t):
     return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
 
@@ -94,16 +128,19 @@ class ConvBlock(torch.autograd.Function):
         B, T, Cin = x.shape
         Cout, _, k = w.shape
         dpre = torch.where(out > 0, gy, gy * ctx.slope).contiguous()
-        dx = dw = db = None
+        dx = dw = db = fork = None
+        if ctx.needs_input_grad[1]:      # all k taps in one launch, written straight into the [Cout][Cin][k] weight layout
+            dw = torch.zeros(Cout, Cin, k, device=x.device, dtype=torch.float32)
+            fork = _Fork(x.device, 1)
+            fork.run(0, lambda: wgrad_tc(dpre, 0, Cout, Cout, x, 0, Cin, Cin, B, T, dw, 0, Cin * k, k, 1, taps=k, shift0=-(k // 2)))
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, Cin, device=x.device, dtype=torch.float32)
             # dX[b,t,ci] = sum_d sum_co dpre[b,t-(d-k//2),co] W[co,ci,d]; tap' = k-1-d walks the kernel backwards
             gemm_tc(dpre, Cout, presplit(w, k - 1, k, Cin * k, -1, k, Cin, Cout), B * T, Cin, Cout, dx, taps=k, tap_pad=k // 2, T=T)
-        if ctx.needs_input_grad[1]:      # all k taps in one launch, written straight into the [Cout][Cin][k] weight layout
-            dw = torch.zeros(Cout, Cin, k, device=x.device, dtype=torch.float32)
-            wgrad_tc(dpre, 0, Cout, Cout, x, 0, Cin, Cin, B, T, dw, 0, Cin * k, k, 1, taps=k, shift0=-(k // 2))
         if ctx.needs_input_grad[2]:
             db = dpre.sum((0, 1))
+        if fork is not None:
+            fork.join()
         return dx, dw, db, None
 
 
@@ -170,6 +207,15 @@ def sinc_filters(filt_b1, filt_band):
     return W
 
 
+_gather_idx = {}
+
+
+def _bias_gather(dev):
+    if dev.index not in _gather_idx:
+        _gather_idx[dev.index] = torch.tensor([0, 1, 2, 0, 1, 3], device=dev)
+    return _gather_idx[dev.index]
+
+
 class BiGRU(torch.autograd.Function):
     """Bidirectional single-layer GRU (H=128, h0=0) + Dropout(mask) + Downsample(avg 2 | none 1).
     Reference: nn.GRU at models.py:232/262/686, RNNSelect :138-149, Dropout :246, Downsample :26-46.
@@ -206,24 +252,35 @@ class BiGRU(torch.autograd.Function):
         gy = _f32(gy)
         dgx = torch.empty(B, T, 768, device=dev, dtype=torch.float32)
         dhn = torch.empty(B, T, 256, device=dev, dtype=torch.float32)
-        dbias = torch.zeros(2, 4, H, device=dev, dtype=torch.float32)          # sums of dr, dz, dn, dhn per direction
+        ni = ctx.needs_input_grad
+        wg = any(ni[1:9])
+        # one zero-filled buffer: dW_ih [768,I] | dW_hh [2,384,H] | column sums of dr, dz, dn, dhn per direction [2,4,H]
+        n_ih, n_hh = 768 * I, 2 * 384 * H
+        zbuf = torch.zeros((n_ih + n_hh if wg else 0) + 2 * 4 * H, device=dev, dtype=torch.float32)
+        dbias = zbuf[-2 * 4 * H:].view(2, 4, H)
         _lib.call("slu_gru_bwd_" + GRU_IMPL, _lib.ptr(gy), _lib.ptr(mask), _lib.ptr(y_full), _lib.ptr(stash), _lib.ptr(w_hh_cat),
                   B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), _lib.ptr(dbias), _lib.stream())
-        ni = ctx.needs_input_grad
-        dgx2 = dgx.view(B * T, 768)
-        dx = matmul_nn(dgx2, w_ih_cat.contiguous()).view(B, T, I) if ni[0] else None
         grads = [None] * 8
-        if any(ni[1:9]):
-            dw_ih = wgrad_tc(dgx, 0, 768, 768, x, 0, I, I, B, T, torch.zeros(768, I, device=dev, dtype=torch.float32), 0, I)
-            dw_hh = torch.zeros(2, 384, H, device=dev, dtype=torch.float32)
+        fork = None
+        if wg:
+            dw_ih, dw_hh = zbuf[:n_ih].view(768, I), zbuf[n_ih:n_ih + n_hh].view(2, 384, H)
+            fork = _Fork(dev, 5)
+            fork.run(0, lambda: wgrad_tc(dgx, 0, 768, 768, x, 0, I, I, B, T, dw_ih, 0, I))
             for d in range(2):          # dW_hh[d] = [dr,dz | dhn]^T . h_{t-1}  (h_{t+1} for the reverse direction)
                 sh = 1 if d else -1
-                wgrad_tc(dgx, d * 384, 768, 256, y_full, d * H, 256, H, B, T, dw_hh, d * 384 * H, H, shift0=sh)
-                wgrad_tc(dhn, d * H, 256, H, y_full, d * H, 256, H, B, T, dw_hh, (d * 384 + 256) * H, H, shift0=sh)
+                fork.run(1 + d, lambda d=d, sh=sh: wgrad_tc(dgx, d * 384, 768, 256, y_full, d * H, 256, H, B, T, dw_hh, d * 384 * H, H,
+                                                            shift0=sh))
+                fork.run(3 + d, lambda d=d, sh=sh: wgrad_tc(dhn, d * H, 256, H, y_full, d * H, 256, H, B, T, dw_hh,
+                                                            (d * 384 + 256) * H, H, shift0=sh))
+        dx = matmul_nn(dgx.view(B * T, 768), w_ih_cat.contiguous()).view(B, T, I) if ni[0] else None
+        if wg:
+            db6 = dbias.index_select(1, _bias_gather(dev))                     # (dr, dz, dn | dr, dz, dhn) per direction
+            for d in range(2):
                 grads[4 * d + 0] = dw_ih[d * 384:(d + 1) * 384]
                 grads[4 * d + 1] = dw_hh[d]
-                grads[4 * d + 2] = dbias[d, :3].reshape(384)                                   # b_ih: dr, dz, dn
-                grads[4 * d + 3] = torch.cat([dbias[d, :2].reshape(256), dbias[d, 3]])         # b_hh: dr, dz, dhn
+                grads[4 * d + 2] = db6[d, :3].reshape(384)                     # b_ih
+                grads[4 * d + 3] = db6[d, 3:].reshape(384)                     # b_hh
+            fork.join()
         return (dx, *grads, None, None)
 
 

@@ -71,6 +71,10 @@ int slu_set_gru_precision(int mode);
 /* Developer tool: accumulate clock64() per step phase of slu_gru_fwd_tc (CTA 0, threads 0 and 128) into buf[2][8]. */
 int slu_debug_gru_phase_clocks(long long* buf);
 
+/* Dropout keep-mask (nn.Dropout, models.py:246/276/700, training mode): mask[i] = Bernoulli(1-p) / (1-p), i < n, from
+ * Philox4x32-10 keyed by `seed` (counter = i/4).  `mask` must be 16-byte aligned.  The GRU kernels multiply by it. */
+int slu_dropout_mask(float* mask, long n, float p, unsigned long long seed, void* stream);
+
 /* Dense "tap-GEMM" on tcgen05 (fp32 in/out, 3-pass bf16 split, fp32 accumulate in TMEM) -- replaces the cuBLAS / cuDNN
  * calls behind nn.GRU's input projection (models.py:232/262/686), nn.Conv1d (models.py:200) and their input gradients:
  *   C[m][n] = sum_tap sum_k A[(m + tap - tap_pad)*lda + k] * W(n, tap, k) (+ bias[n]) (LeakyReLU(slope) if act == 1)

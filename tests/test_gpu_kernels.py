@@ -131,7 +131,9 @@ def test_sinc_frontend_fwd_bwd(pkg, monkeypatch, impl, B, T):
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("B,T,I,ds,use_mask", [(3, 7, 60, 2, False), (17, 9, 256, 2, True), (40, 5, 60, 1, False), (4, 24, 256, 2, True), (5, 23, 256, 1, True),
-                                               (1, 1, 256, 2, False), (9, 50, 60, 2, False), (2, 360, 60, 2, False)])
+                                               (1, 1, 256, 2, False), (9, 50, 60, 2, False), (2, 360, 60, 2, False),
+                                               # B >= 592 / >= 1184 select the 8- and 16-rows-per-CTA instantiations
+                                               (601, 6, 60, 2, True), (1187, 5, 256, 1, False)])
 def test_bigru_fwd_bwd(pkg, monkeypatch, impl, B, T, I, ds, use_mask):
     monkeypatch.setattr(pkg.ops, "GRU_IMPL", impl)
     rs = np.random.RandomState(B * 100 + T)
@@ -222,3 +224,31 @@ def test_bigru_fp16_single_pass_mode(pkg, monkeypatch, B, T, I, ds):
             assert rel_err(v.grad.cpu(), gru.get_parameter(k).grad) < 1e-2, k
     finally:
         pkg.ops.set_gru_precision("bf16x3")
+
+
+@pytest.mark.parametrize("n,p", [(1 << 20, 0.5), (1000003, 0.25), (7, 0.5), (3, 0.0)])
+def test_dropout_mask_kernel(pkg, n, p):
+    """nn.Dropout's training-mode mask (models.py:246): values in {0, 1/(1-p)}, keep rate 1-p, reproducible per seed."""
+    L = pkg._lib
+
+    def draw(seed):
+        buf = torch.full((n + 8,), -1.0, device="cuda")
+        L.call("slu_dropout_mask", L.ptr(buf), n, float(p), seed, L.stream())
+        torch.cuda.synchronize()
+        assert (buf[n:] == -1).all()                      # nothing written past n
+        return buf[:n].cpu()
+    a, b, c = draw(1234), draw(1234), draw(1235)
+    scale = 1.0 / (1.0 - p)
+    assert torch.equal(a, b)
+    assert ((a == 0) | ((a - scale).abs() < 1e-6)).all()
+    if n > 1000:
+        keep = (a != 0).float()
+        sigma = (p * (1 - p) / n) ** 0.5
+        assert abs(keep.mean().item() - (1 - p)) < 5 * sigma
+        assert not torch.equal(a, c)
+        k0 = keep - keep.mean()
+        for lag in (1, 2, 4, 256):                        # no visible correlation inside / across Philox counters
+            corr = (k0[:-lag] * k0[lag:]).mean().item() / (p * (1 - p))
+            assert abs(corr) < 5 / n ** 0.5, (lag, corr)
+    if p == 0.0:
+        assert (a == 1).all()

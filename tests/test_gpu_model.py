@@ -180,6 +180,31 @@ def test_asr_pretraining_forward_on_gpu():
     assert rel_err(ph.detach().cpu(), g["phoneme_logits"]) < 1e-3
 
 
+def test_asr_15s_long_sequence_matches_oracle():
+    """BASELINE config 4 shape: 15 s @16 kHz -> 1500/750/375/188 sequential GRU steps (long-sequence stress of the
+    persistent kernels and of the sinc front end's tiling); losses and posteriors against the CPU oracle."""
+    cfg = make_config(pretraining_type=2)
+    pm = models.PretrainedModel(cfg).eval()
+    p = R.synthetic_params(seed=12, asr=True)
+    sd = pm.state_dict()
+    sd.update({k[len(R.P):]: v for k, v in p.items() if k.startswith(R.P)})
+    pm.load_state_dict(sd)
+    x, _ = R.synthetic_batch(2, 240000, seed=21)
+    rs = np.random.RandomState(5)
+    yp = torch.from_numpy(rs.randint(-1, 42, size=(2, 375)))
+    yw = torch.from_numpy(rs.randint(-1, 10000, size=(2, 94)))
+    with torch.no_grad():
+        ref = R.asr_forward(x, yp, yw, {k[len(R.P):]: v for k, v in p.items() if k.startswith(R.P)})
+        feats_ref = R.compute_features(x, p)
+        pl, wl, pa, wa = pm(x, yp, yw)
+        feats = pm.compute_features(x)
+    assert feats.shape == (2, 94, 256)
+    assert rel_err(feats.cpu(), feats_ref) < LOGIT_TOL / 10
+    assert abs(pl.item() - ref[0].item()) < 1e-4 * ref[0].item()
+    assert abs(wl.item() - ref[1].item()) < 1e-4 * ref[1].item()
+    assert abs(pa.item() - ref[2].item()) < 1e-6
+
+
 def test_seq2seq_model_on_gpu_matches_its_cpu_execution():
     """BASELINE config 5: the seq2seq intent module on top of the encoder kernels (decoder = torch ops)."""
     cfg = make_config("seq2seq")
@@ -203,3 +228,19 @@ def test_seq2seq_model_on_gpu_matches_its_cpu_execution():
     m.cuda(); m.is_cuda = True
     out = m.decode_intents(x[:1])           # beam search on the device (short alphabet, 200 steps)
     assert isinstance(out, list) and isinstance(out[0], str)
+
+
+def test_device_prefetcher_feeds_the_step_in_order():
+    pkg = importlib.import_module("end-to-end-slu_b200")
+    host = [(torch.full((4, 1000), float(i)), torch.full((4, 3), i, dtype=torch.int64)) for i in range(5)]
+    pf = pkg.loader.DevicePrefetcher(host)
+    seen = []
+    for x, y in pf:
+        assert x.is_cuda and y.is_cuda
+        seen.append((x.mean().item(), int(y[0, 0].item())))
+    assert seen == [(float(i), i) for i in range(5)]
+    assert pf.h2d_bytes == 5 * (4 * 1000 * 4 + 4 * 3 * 8)
+    m = gpu_model(R.synthetic_params(seed=6))
+    xb, yb = R.synthetic_batch(2, 8000, seed=7)
+    (xd, yd), = list(pkg.loader.DevicePrefetcher([(xb, yb)]))
+    assert abs(m(xd, yd)[0].item() - m(xb, yb)[0].item()) < 1e-6
