@@ -27,6 +27,10 @@ SIGNATURES = {
     "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_set_gru_precision": [_I],
     "slu_debug_gru_phase_clocks": [_P],
+    "slu_intent_head_fwd": [_P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+    "slu_intent_head_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P],
+    "slu_stream_fork": [_P, _I, _P],
+    "slu_stream_join": [_P, _I],
     "slu_dropout_mask": [_P, _L, _F, ctypes.c_ulonglong, _P],
     "slu_gemm_tc": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "slu_presplit_bf16": [_P, _L, _L, _L, _I, _I, _I, _P, _P],
@@ -60,24 +64,45 @@ def ptr(t):
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current stream on the current device (what every launch of this library is queued on)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 stats = {"calls": 0}        # number of C-ABI kernel launches issued by this process
 _prof = None                # name -> [(start_event, end_event)] while profiling
+_fn = {}
+_HOST_ONLY = ("slu_stream_fork", "slu_stream_join", "slu_set_gru_precision", "slu_debug_gru_phase_clocks")
 
 
 def call(name, *args):
-    stats["calls"] += 1
-    if _prof is not None:
+    fn = _fn.get(name)
+    if fn is None:
+        fn = _fn[name] = getattr(load(), name)
+    if name not in _HOST_ONLY:
+        stats["calls"] += 1
+    if _prof is not None and name not in _HOST_ONLY:
+        st = torch.cuda.ExternalStream(args[-1]) if args[-1] else torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-    err = getattr(load(), name)(*args)
+        e0.record(st)
+        err = fn(*args)
+        e1.record(st)
+        _prof.setdefault(name, []).append((e0, e1))
+    else:
+        err = fn(*args)
     if err != 0:
         raise RuntimeError("slu_b200: %s failed with cudaError %d" % (name, err))
-    if _prof is not None:
-        e1.record()
-        _prof.setdefault(name, []).append((e0, e1))
+
+
+def fork(n):
+    """-> (main stream handle, [n side-stream handles]) with the side streams waiting on the current stream."""
+    main = stream()
+    side = (ctypes.c_void_p * n)()
+    call("slu_stream_fork", main, n, side)
+    return main, list(side)
+
+
+def join(main, n):
+    call("slu_stream_join", main, n)
 
 
 def profile_begin():

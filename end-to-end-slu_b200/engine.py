@@ -115,6 +115,21 @@ def intent_logits(model, feats):
     """intent GRU(s) -> Linear -> max over time (models.py:806-809)."""
     out = _run_rnns(feats, model._intent_rnns, model.training)
     lin = model._final_classifier
+    if ops.intent_head_supported(lin.weight, (lin.weight.shape[0],)):
+        return ops.intent_head_logits(out, lin.weight, lin.bias)
     B, T, C = out.shape
     logits = torch.addmm(lin.bias, out.reshape(B * T, C), lin.weight.t()).view(B, T, -1)
     return logits.max(dim=1)[0]
+
+
+def intent_loss_acc(model, x, y_intent):
+    """Training tail of Model.forward (models.py:806-823) as one kernel per direction: intent GRU(s) -> Linear -> max over
+    time -> summed per-slot cross-entropy and all-slots-right accuracy.  Returns None when the head does not fit the kernel
+    (more than 128 values / 16 slots), and the caller composes it from library ops."""
+    lin = model._final_classifier
+    slots = tuple(int(n) for n in model.values_per_slot)
+    if not (ops.intent_head_supported(lin.weight, slots) and y_intent.dtype == torch.int64 and y_intent.dim() == 2):
+        return None
+    out = _run_rnns(model.pretrained_model.compute_features(x), model._intent_rnns, model.training)
+    loss, acc, _ = ops.IntentHead.apply(out, lin.weight, lin.bias, y_intent, slots)
+    return loss, acc

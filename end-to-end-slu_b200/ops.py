@@ -3,6 +3,7 @@
 Layouts are the library's own (time-major NLC everywhere):
   waveform [B,T] -> sinc frames [B,L1,80] -> conv blocks [B,L1,60] -> GRU stacks [B,T_l,256].
 """
+import ctypes
 import os
 
 import torch
@@ -20,35 +21,26 @@ SINC_IMPL = os.environ.get("SLU_SINC_IMPL", "tc")
 # Weight-gradient launches of one layer are independent of each other and of the input-gradient GEMM: they go to side
 # streams (forked after the producer kernel, joined before the autograd node returns), so the small grids share the GPU.
 OVERLAP = os.environ.get("SLU_OVERLAP", "1") != "0"
-_side = {}
 
 
 class _Fork:
-    """fork(): side streams wait for everything queued on the current stream; run(i, fn): fn's launches go to side stream
-    i; join(): the current stream waits for the side streams.  All tensors involved are allocated on the current stream
-    BEFORE the fork and stay referenced until after the join, so the caching allocator never sees cross-stream reuse."""
+    """Side streams of the library (slu_stream_fork / slu_stream_join): `stream(i)` is where independent launch i goes.
+    All tensors involved are allocated on the current stream BEFORE the fork and stay referenced until after the join,
+    so the caching allocator never sees cross-stream reuse."""
 
-    def __init__(self, device, n=4):
-        self.main = torch.cuda.current_stream(device)
-        self.streams = []
-        if OVERLAP:
-            pool = _side.setdefault(device.index, [])
-            while len(pool) < n:
-                pool.append(torch.cuda.Stream(device=device))
-            self.streams = pool[:n]
-            ev = self.main.record_event()
-            for st in self.streams:
-                st.wait_event(ev)
+    def __init__(self, n):
+        self.n = n if OVERLAP else 0
+        if self.n:
+            self.main, self.side = _lib.fork(self.n)
+        else:
+            self.main, self.side = _lib.stream(), []
 
-    def run(self, i, fn):
-        if not self.streams:
-            return fn()
-        with torch.cuda.stream(self.streams[i % len(self.streams)]):
-            return fn()
+    def stream(self, i):
+        return self.side[i % self.n] if self.n else self.main
 
     def join(self):
-        for st in self.streams:
-            self.main.wait_stream(st)
+        if self.n:
+            _lib.join(self.main, self.n)
 
 
 def _f32(t):
@@ -75,10 +67,10 @@ def presplit(W, w_off, sn, sk, stap, taps, N, K):
     return img
 
 
-def wgrad_tc(G, g_off, ldg, M, X, x_off, ldx, N, B, T, out, o_off, s_m, s_n=1, s_tap=0, taps=1, shift0=0):
+def wgrad_tc(G, g_off, ldg, M, X, x_off, ldx, N, B, T, out, o_off, s_m, s_n=1, s_tap=0, taps=1, shift0=0, stream=None):
     """out[...] += G^T . X over frames (slu_wgrad_tc); `out` must be pre-zeroed for a plain gradient."""
     _lib.call("slu_wgrad_tc", _eptr(G, g_off), ldg, M, _eptr(X, x_off), ldx, N, B, T, taps, shift0, _eptr(out, o_off), s_m, s_n,
-              s_tap, _lib.stream())
+              s_tap, _lib.stream() if stream is None else stream)
     return out
 
 
@@ -131,8 +123,8 @@ class ConvBlock(torch.autograd.Function):
         dx = dw = db = fork = None
         if ctx.needs_input_grad[1]:      # all k taps in one launch, written straight into the [Cout][Cin][k] weight layout
             dw = torch.zeros(Cout, Cin, k, device=x.device, dtype=torch.float32)
-            fork = _Fork(x.device, 1)
-            fork.run(0, lambda: wgrad_tc(dpre, 0, Cout, Cout, x, 0, Cin, Cin, B, T, dw, 0, Cin * k, k, 1, taps=k, shift0=-(k // 2)))
+            fork = _Fork(1)
+            wgrad_tc(dpre, 0, Cout, Cout, x, 0, Cin, Cin, B, T, dw, 0, Cin * k, k, 1, taps=k, shift0=-(k // 2), stream=fork.stream(0))
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, Cin, device=x.device, dtype=torch.float32)
             # dX[b,t,ci] = sum_d sum_co dpre[b,t-(d-k//2),co] W[co,ci,d]; tap' = k-1-d walks the kernel backwards
@@ -264,14 +256,14 @@ class BiGRU(torch.autograd.Function):
         fork = None
         if wg:
             dw_ih, dw_hh = zbuf[:n_ih].view(768, I), zbuf[n_ih:n_ih + n_hh].view(2, 384, H)
-            fork = _Fork(dev, 5)
-            fork.run(0, lambda: wgrad_tc(dgx, 0, 768, 768, x, 0, I, I, B, T, dw_ih, 0, I))
+            fork = _Fork(5)
+            wgrad_tc(dgx, 0, 768, 768, x, 0, I, I, B, T, dw_ih, 0, I, stream=fork.stream(0))
             for d in range(2):          # dW_hh[d] = [dr,dz | dhn]^T . h_{t-1}  (h_{t+1} for the reverse direction)
                 sh = 1 if d else -1
-                fork.run(1 + d, lambda d=d, sh=sh: wgrad_tc(dgx, d * 384, 768, 256, y_full, d * H, 256, H, B, T, dw_hh, d * 384 * H, H,
-                                                            shift0=sh))
-                fork.run(3 + d, lambda d=d, sh=sh: wgrad_tc(dhn, d * H, 256, H, y_full, d * H, 256, H, B, T, dw_hh,
-                                                            (d * 384 + 256) * H, H, shift0=sh))
+                wgrad_tc(dgx, d * 384, 768, 256, y_full, d * H, 256, H, B, T, dw_hh, d * 384 * H, H, shift0=sh,
+                         stream=fork.stream(1 + d))
+                wgrad_tc(dhn, d * H, 256, H, y_full, d * H, 256, H, B, T, dw_hh, (d * 384 + 256) * H, H, shift0=sh,
+                         stream=fork.stream(3 + d))
         dx = matmul_nn(dgx.view(B * T, 768), w_ih_cat.contiguous()).view(B, T, I) if ni[0] else None
         if wg:
             db6 = dbias.index_select(1, _bias_gather(dev))                     # (dr, dz, dn | dr, dz, dhn) per direction
@@ -289,3 +281,69 @@ def bigru(x, gru, mask=None, ds=1):
     return BiGRU.apply(x, gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0,
                        gru.weight_ih_l0_reverse, gru.weight_hh_l0_reverse, gru.bias_ih_l0_reverse,
                        gru.bias_hh_l0_reverse, mask, ds)
+
+
+_tickets = {}
+
+
+def _ticket(dev):
+    if dev.index not in _tickets:
+        _tickets[dev.index] = torch.zeros(1, device=dev, dtype=torch.int32)
+    return _tickets[dev.index]
+
+
+def intent_head_supported(weight, slots):
+    return weight.shape[1] == 2 * H and weight.shape[0] <= 128 and 1 <= len(slots) <= 16 and sum(slots) == weight.shape[0]
+
+
+def _head_fwd(feats, w, b, y, slots):
+    B, T, _ = feats.shape
+    C = w.shape[0]
+    dev = feats.device
+    fbuf = torch.empty(B * C + 2 * B + 2, device=dev, dtype=torch.float32)
+    tstar = torch.empty(B, C, device=dev, dtype=torch.int32)
+    logits = fbuf[:B * C].view(B, C)
+    sl = (ctypes.c_int * len(slots))(*slots)
+    _lib.call("slu_intent_head_fwd", _lib.ptr(feats), _lib.ptr(w), _lib.ptr(b), None if y is None else _lib.ptr(y), B, T, C, sl,
+              len(slots), logits.data_ptr(), _lib.ptr(tstar), fbuf[B * C:].data_ptr(), fbuf[B * C + B:].data_ptr(),
+              fbuf[B * C + 2 * B:].data_ptr(), _lib.ptr(_ticket(dev)), _lib.stream())
+    return fbuf, logits, tstar
+
+
+def intent_head_logits(feats, weight, bias):
+    """Linear + max over time -> logits [B,C] (no labels, no autograd): models.py:806-809 on the predict path."""
+    C = weight.shape[0]
+    return _head_fwd(_f32(feats.detach()), weight.detach().contiguous(), bias.detach().contiguous(), None, (C,))[1]
+
+
+class IntentHead(torch.autograd.Function):
+    """feats [B,T,256] -> (loss, acc, logits): Linear(256->C), max over time, summed per-slot cross-entropy, accuracy.
+    Reference: models.py:709, :112-123, :811-823."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, bias, y, slots):
+        feats = _f32(feats)
+        w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        y = y.contiguous()
+        assert y.dtype == torch.int64 and y.shape == (feats.shape[0], len(slots))
+        fbuf, logits, tstar = _head_fwd(feats, w, b, y, slots)
+        ctx.save_for_backward(feats, w, y, logits, tstar)
+        ctx.slots = slots
+        loss, acc = fbuf[-2], fbuf[-1]
+        ctx.mark_non_differentiable(acc, logits)
+        return loss, acc, logits
+
+    @staticmethod
+    def backward(ctx, g_loss, g_acc, g_logits):
+        feats, w, y, logits, tstar = ctx.saved_tensors
+        slots = ctx.slots
+        B, T, _ = feats.shape
+        C = w.shape[0]
+        dev = feats.device
+        g = _f32(g_loss).reshape(1)
+        dfeats = torch.empty(B, T, 2 * H, device=dev, dtype=torch.float32)
+        zb = torch.zeros(C * 2 * H + C, device=dev, dtype=torch.float32)
+        sl = (ctypes.c_int * len(slots))(*slots)
+        _lib.call("slu_intent_head_bwd", _lib.ptr(g), _lib.ptr(feats), _lib.ptr(w), _lib.ptr(y), _lib.ptr(logits), _lib.ptr(tstar),
+                  B, T, C, sl, len(slots), _lib.ptr(dfeats), zb.data_ptr(), zb[C * 2 * H:].data_ptr(), _lib.stream())
+        return dfeats, zb[:C * 2 * H].view(C, 2 * H), zb[C * 2 * H:], None, None

@@ -71,6 +71,26 @@ int slu_set_gru_precision(int mode);
 /* Developer tool: accumulate clock64() per step phase of slu_gru_fwd_tc (CTA 0, threads 0 and 128) into buf[2][8]. */
 int slu_debug_gru_phase_clocks(long long* buf);
 
+/* Intent head (models.py:709 Linear(256 -> C), :112-123 FinalPool max over time, :811-823 summed per-slot cross-entropy and
+ * all-slots-right accuracy), one launch per direction.  feats [B][T][256]; W [C][256]; y [B][n_slots] int64 class indices
+ * (NULL: logits only); values_per_slot = n_slots HOST ints summing to C (C <= 128, n_slots <= 16).
+ * fwd writes logits [B][C], tstar [B][C] (arg-max frame), row_loss/row_ok [B] scratch and loss_acc[2] = {loss, accuracy};
+ * `ticket` is one zero-initialised device word the kernel uses and resets.
+ * bwd: gloss = dL/dloss (one device float); writes dfeats [B][T][256], ACCUMULATES into dW [C][256] and dbias [C]. */
+int slu_intent_head_fwd(const float* feats, const float* W, const float* bias, const long long* y, int B, int T, int C,
+                        const int* values_per_slot, int n_slots, float* logits, int* tstar, float* row_loss, float* row_ok,
+                        float* loss_acc, unsigned int* ticket, void* stream);
+int slu_intent_head_bwd(const float* gloss, const float* feats, const float* W, const long long* y, const float* logits,
+                        const int* tstar, int B, int T, int C, const int* values_per_slot, int n_slots, float* dfeats, float* dW,
+                        float* dbias, void* stream);
+
+/* Fork / join of independent launches (host-side stream plumbing, no kernels): after slu_stream_fork the n (<= 8)
+ * streams returned in side_streams[] wait for everything queued on main_stream so far; after slu_stream_join work queued
+ * on main_stream waits for everything queued on those n side streams.  Used to run one layer's weight-gradient GEMMs
+ * next to its input-gradient GEMM.  Buffers must stay alive until the join has been passed on main_stream. */
+int slu_stream_fork(void* main_stream, int n, void** side_streams);
+int slu_stream_join(void* main_stream, int n);
+
 /* Dropout keep-mask (nn.Dropout, models.py:246/276/700, training mode): mask[i] = Bernoulli(1-p) / (1-p), i < n, from
  * Philox4x32-10 keyed by `seed` (counter = i/4).  `mask` must be 16-byte aligned.  The GRU kernels multiply by it. */
 int slu_dropout_mask(float* mask, long n, float p, unsigned long long seed, void* stream);

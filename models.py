@@ -384,6 +384,10 @@ class Model(torch.nn.Module):
             out = self.encoder(self.pretrained_model.compute_features(x))
             log_probs = self.decoder(out, y_intent)
             return -log_probs.mean(), torch.tensor([0.])
+        if on_gpu:                                  # fused head: Linear + max over time + slot CE + accuracy, one kernel
+            fused = _engine().intent_loss_acc(self, x, y_intent)
+            if fused is not None:
+                return fused
         logits = self._intent_logits(x)
         loss, start = 0., 0
         for slot, n in enumerate(self.values_per_slot):

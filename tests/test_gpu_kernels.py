@@ -252,3 +252,35 @@ def test_dropout_mask_kernel(pkg, n, p):
             assert abs(corr) < 5 / n ** 0.5, (lag, corr)
     if p == 0.0:
         assert (a == 1).all()
+
+
+@pytest.mark.parametrize("B,T,slots", [(5, 7, (6, 14, 4)), (300, 25, (6, 14, 4)), (3, 94, (3, 5)), (9, 33, (7,)), (2, 1, (2, 2, 2, 2, 121))])
+def test_intent_head_fwd_bwd(pkg, B, T, slots):
+    """Fused Linear + max-over-time + per-slot CE + accuracy (models.py:709, 112-123, 811-823) against torch ops in fp64."""
+    rs = np.random.RandomState(B * 7 + T)
+    C = sum(slots)
+    feats = torch.from_numpy(rs.standard_normal((B, T, 256)).astype(np.float32))
+    W = torch.from_numpy(rs.uniform(-0.1, 0.1, size=(C, 256)).astype(np.float32))
+    bias = torch.from_numpy(rs.uniform(-0.1, 0.1, size=(C,)).astype(np.float32))
+    y = torch.stack([torch.from_numpy(rs.randint(0, n, size=(B,))) for n in slots], 1)
+    f64, w64, b64 = (t.double().requires_grad_(True) for t in (feats, W, bias))
+    logits_ref = (f64 @ w64.t() + b64).max(dim=1)[0]
+    loss_ref, start, ok = 0.0, 0, torch.ones(B, dtype=torch.bool)
+    for s, n in enumerate(slots):
+        loss_ref = loss_ref + torch.nn.functional.cross_entropy(logits_ref[:, start:start + n], y[:, s])
+        ok &= logits_ref[:, start:start + n].max(1)[1] == y[:, s]
+        start += n
+    (loss_ref * 1.7).backward()
+    fc, wc, bc = (t.cuda().requires_grad_(True) for t in (feats, W, bias))
+    loss, acc, logits = pkg.ops.IntentHead.apply(fc, wc, bc, y.cuda(), slots)
+    assert loss.dim() == 0 and acc.dim() == 0 and not acc.requires_grad
+    (loss * 1.7).backward()
+    assert rel_err(logits.cpu(), logits_ref.detach().float()) < 1e-5
+    assert abs(loss.item() - loss_ref.item()) < 1e-5 * abs(loss_ref.item())
+    assert abs(acc.item() - ok.float().mean().item()) < 1e-6
+    assert rel_err(fc.grad.cpu(), f64.grad.float()) < 1e-4
+    assert rel_err(wc.grad.cpu(), w64.grad.float()) < 1e-4
+    assert rel_err(bc.grad.cpu(), b64.grad.float()) < 1e-4
+    again = pkg.ops.IntentHead.apply(fc, wc, bc, y.cuda(), slots)[0]
+    assert again.item() == loss.item()                                   # fixed-order batch reduction: bit-reproducible
+    assert rel_err(pkg.ops.intent_head_logits(fc, wc, bc).cpu(), logits_ref.detach().float()) < 1e-5
