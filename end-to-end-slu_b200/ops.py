@@ -214,15 +214,18 @@ class BiGRU(torch.autograd.Function):
     x [B,T,I] -> [B, ceil(T/ds), 256]."""
 
     @staticmethod
-    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, mask, ds):
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, mask, ds, packed=None):
         x = _f32(x)
         B, T, I = x.shape
         dev = x.device
-        w_ih_cat = torch.cat([w_ih, w_ih_r], 0).detach()                       # [768, I]
-        b_ih_cat = torch.cat([b_ih, b_ih_r], 0).detach()
-        w_hh_cat = torch.stack([w_hh, w_hh_r], 0).detach().contiguous()       # [2,384,128]
-        b_hh_cat = torch.stack([b_hh, b_hh_r], 0).detach().contiguous()
-        gx = linear_nt(x.view(B * T, I), w_ih_cat.contiguous(), b_ih_cat)       # x-projection, both directions
+        if packed is not None:      # both directions already adjacent in memory (packed_params): no gather launches
+            w_ih_cat, b_ih_cat, w_hh_cat, b_hh_cat = packed
+        else:
+            w_ih_cat = torch.cat([w_ih, w_ih_r], 0).detach()                   # [768, I]
+            b_ih_cat = torch.cat([b_ih, b_ih_r], 0).detach()
+            w_hh_cat = torch.stack([w_hh, w_hh_r], 0).detach().contiguous()   # [2,384,128]
+            b_hh_cat = torch.stack([b_hh, b_hh_r], 0).detach().contiguous()
+        gx = linear_nt(x.view(B * T, I), w_ih_cat, b_ih_cat)                    # x-projection, both directions
         T2 = (T + ds - 1) // ds
         y_full = torch.empty(B, T, 256, device=dev, dtype=torch.float32)
         y_out = torch.empty(B, T2, 256, device=dev, dtype=torch.float32) if (ds != 1 or mask is not None) else y_full
@@ -264,7 +267,7 @@ class BiGRU(torch.autograd.Function):
                          stream=fork.stream(1 + d))
                 wgrad_tc(dhn, d * H, 256, H, y_full, d * H, 256, H, B, T, dw_hh, (d * 384 + 256) * H, H, shift0=sh,
                          stream=fork.stream(3 + d))
-        dx = matmul_nn(dgx.view(B * T, 768), w_ih_cat.contiguous()).view(B, T, I) if ni[0] else None
+        dx = matmul_nn(dgx.view(B * T, 768), w_ih_cat).view(B, T, I) if ni[0] else None
         if wg:
             db6 = dbias.index_select(1, _bias_gather(dev))                     # (dr, dz, dn | dr, dz, dhn) per direction
             for d in range(2):
@@ -273,14 +276,51 @@ class BiGRU(torch.autograd.Function):
                 grads[4 * d + 2] = db6[d, :3].reshape(384)                     # b_ih
                 grads[4 * d + 3] = db6[d, 3:].reshape(384)                     # b_hh
             fork.join()
-        return (dx, *grads, None, None)
+        return (dx, *grads, None, None, None)
+
+
+_PACK_ORDER = ("weight_ih_l0", "weight_ih_l0_reverse", "weight_hh_l0", "weight_hh_l0_reverse",
+               "bias_ih_l0", "bias_ih_l0_reverse", "bias_hh_l0", "bias_hh_l0_reverse")
+
+
+def packed_params(gru):
+    """Keep the 8 parameter tensors of a bidirectional nn.GRU holder in ONE buffer laid out as the kernels read them
+    (W_ih both directions [768,I] | W_hh [2,384,128] | b_ih [768] | b_hh [2,384]) and return those four views.
+    The Parameters stay the same objects (only their storage moves, as nn.GRU.flatten_parameters does for cuDNN), so
+    optimizers, state_dict and checkpoints are unaffected; if something re-homed them (`.cuda()`, `.to()`), re-pack."""
+    ps = [getattr(gru, n) for n in _PACK_ORDER]
+    flat = getattr(gru, "_slu_flat", None)
+    ok = flat is not None and flat.device == ps[0].device
+    if ok:
+        off = flat.data_ptr()
+        for p in ps:
+            if p.data_ptr() != off:
+                ok = False
+                break
+            off += 4 * p.numel()
+    if not ok:
+        if any(p.dtype != torch.float32 for p in ps):
+            return None
+        flat = torch.empty(sum(p.numel() for p in ps), device=ps[0].device, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p in ps:
+                v = flat[off:off + p.numel()].view(p.shape)
+                v.copy_(p)
+                p.data = v
+                off += p.numel()
+        I = gru.input_size
+        n1, n2 = 768 * I, 768 * I + 2 * 384 * H
+        gru._slu_flat = flat
+        gru._slu_views = (flat[:n1].view(768, I), flat[n2:n2 + 768], flat[n1:n2].view(2, 384, H), flat[n2 + 768:].view(2, 384))
+    return gru._slu_views
 
 
 def bigru(x, gru, mask=None, ds=1):
     """Run BiGRU on the parameters of an nn.GRU holder module."""
     return BiGRU.apply(x, gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0,
                        gru.weight_ih_l0_reverse, gru.weight_hh_l0_reverse, gru.bias_ih_l0_reverse,
-                       gru.bias_hh_l0_reverse, mask, ds)
+                       gru.bias_hh_l0_reverse, mask, ds, packed_params(gru))
 
 
 _tickets = {}

@@ -212,3 +212,33 @@ def test_seq2seq_surface_matches_reference(reference):
     s_n, b_n = new.decoder.infer(enc_n, cfg.Sy_intent, B=4, y_lengths=[6])
     assert rel_err(s_n, s_r) < 1e-4 and torch.equal(b_r.argmax(-1), b_n.argmax(-1))
     assert ref.one_hot_to_string(b_r[0, 0], cfg.Sy_intent) == new.one_hot_to_string(b_n[0, 0], cfg.Sy_intent)
+
+
+def test_packed_gru_parameters_keep_identity_values_and_checkpoints():
+    """ops.packed_params re-homes the 8 tensors of a bidirectional GRU into one buffer in kernel order (host logic only):
+    Parameter objects, values, optimizer updates, load_state_dict and nn.GRU's own CPU forward must be unaffected."""
+    import importlib
+    ops = importlib.import_module("end-to-end-slu_b200").ops
+    g = torch.nn.GRU(60, 128, batch_first=True, bidirectional=True)
+    sd = {k: v.clone() for k, v in g.state_dict().items()}
+    ids = [id(p) for p in g.parameters()]
+    x = torch.randn(2, 5, 60)
+    y0 = g(x)[0].detach().clone()
+    v = ops.packed_params(g)
+    assert [id(p) for p in g.parameters()] == ids
+    assert all(torch.equal(t, sd[k]) for k, t in g.state_dict().items())
+    assert torch.equal(v[0], torch.cat([g.weight_ih_l0, g.weight_ih_l0_reverse]))
+    assert torch.equal(v[1], torch.cat([g.bias_ih_l0, g.bias_ih_l0_reverse]))
+    assert torch.equal(v[2], torch.stack([g.weight_hh_l0, g.weight_hh_l0_reverse]))
+    assert torch.equal(v[3], torch.stack([g.bias_hh_l0, g.bias_hh_l0_reverse]))
+    assert torch.equal(g(x)[0], y0)
+    assert ops.packed_params(g) is v                                   # still aliased: nothing to do
+    opt = torch.optim.Adam(g.parameters(), lr=0.1)
+    g(x)[0].sum().backward()
+    opt.step()
+    assert ops.packed_params(g) is v and torch.equal(v[0], torch.cat([g.weight_ih_l0, g.weight_ih_l0_reverse]))
+    g.load_state_dict(sd)
+    assert torch.equal(v[0][:384], sd["weight_ih_l0"])
+    g.double(); g.float()                                              # Module._apply re-homes the parameters
+    v2 = ops.packed_params(g)
+    assert v2 is not v and torch.equal(v2[0][:384], sd["weight_ih_l0"]) and torch.equal(g(x)[0], y0)
