@@ -23,7 +23,7 @@ constexpr int FWD_RING = 4, BWD_RING = 3;
 // Optional phase timing (developer tool, tools/gru_phase_timing.py): when set, CTA (0,0) accumulates clock64() deltas of the
 // step phases for threads 0 and 128 into this buffer [2][8].
 __device__ long long* g_phase_clk = nullptr;
-#define PHASE(i) do { if (dbg) { const long long now_ = clock64(); dbg[i] += now_ - tprev_; tprev_ = now_; } } while (0)   // depth of the TMA input rings (steps in flight)
+#define PHASE(i) do { if (NR == 4 && dbg) { const long long now_ = clock64(); ph_acc[i] += now_ - tprev_; tprev_ = now_; } } while (0)   // depth of the TMA input rings (steps in flight)
 
 // Load W rows (this thread's lane) into TMEM as split bf16 A-operands.  src: 3 blocks of [128][128] fp32 with
 // element (row j, k) at src[g*block_stride + j*row_stride + k*k_stride].
@@ -158,6 +158,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
 
   long long* dbg = (g_phase_clk && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 128)) ? g_phase_clk + (tid ? 8 : 0) : nullptr;
   long long tprev_ = clock64();
+  long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // register accumulators (4-row instantiations only): no memory traffic in the loop
   for (int s = 0; s < T; ++s) {
     const int t = t_first + dt * s;
     float ar[NC], az[NC], an[NC];
@@ -236,6 +237,8 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       off[c] += dt * 256;
     }
   }
+  if (NR == 4 && dbg)
+    for (int i = 0; i < 8; ++i) dbg[i] += ph_acc[i];
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
