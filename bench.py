@@ -50,9 +50,18 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.lo, self.hi = [], None, index, 0, None
 
     def __enter__(self):
+        self.lo = len(self.rows)             # rows from here on were sampled inside the timed region
+        return self
+
+    def __exit__(self, *a):
+        time.sleep(0.12)                     # at least one 100 ms sample lands inside short regions
+        self.hi = len(self.rows)
+
+    def start(self):
+        """Launch nvidia-smi ahead of the timed region (its start-up takes longer than a short run)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -62,16 +71,20 @@ class ClockSampler:
             self.proc = None
         return self
 
-    def __exit__(self, *a):
+    def stop(self):
         if self.proc:
-            time.sleep(0.15)
             self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)    # gone before anything else is timed
+            except Exception:
+                self.proc.kill()
             self.thread.join(timeout=2)
+            self.proc = None
 
     def summary(self):
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.rows:
+        for l in self.rows[self.lo:self.hi]:
             f = [v.strip() for v in l.split(",")]
             try:
                 sm.append(float(f[0])); mx = max(mx, float(f[1]))
@@ -189,12 +202,20 @@ def main():
             ms = t.item()
         return ms
 
+    clk = ClockSampler(local).start()
     for i in range(max(args.warmup, 3)):
         step(xs_dev[i % NB], ys_dev[i % NB])
+    timed(3, host="prefetch")                                # untimed warm-up of the host-fed paths too (copy stream, its
+    timed(3, host="serial")                                  # allocator pool, pinned staging)
+    for _ in range(30):                                      # nvidia-smi is up and sampling before the timed region starts
+        if clk.rows or clk.proc is None:
+            break
+        time.sleep(0.1)
     calls0 = pkg._lib.stats["calls"]
-    with ClockSampler(local) as clk:
+    with clk:
         ms_dev = timed(args.steps, host=None)
     launches = pkg._lib.stats["calls"] - calls0
+    clk.stop()
     ms_e2e = timed(args.steps, host="prefetch")
     ms_e2e_serial = timed(args.steps, host="serial")
     per_step = ms_dev / args.steps

@@ -8,13 +8,21 @@
 //   * the CNN tail  Conv1d(k=5,pad=2)+bias+LeakyReLU as 5 accumulating taps over the NLC activations
 //                   (models.py:200-220) and its dX (taps walked backwards)
 // (weight gradients live in wgrad_tc.cu, the SincNet front end in sinc_tc.cu).
-// All 8 warps of a CTA stage operands (software pipeline, 2 stages, register prefetch of the next k-block): activations
-// are read as fp32, split into bf16 hi + lo in registers and stored K-major (no swizzle, padded leading-byte-offset) in
-// shared memory; weights are PRE-SPLIT once per call (slu_presplit_bf16, any strides / tap order) so their tile is a
-// plain 16-byte copy.  One elected thread issues hi*hi + hi*lo + lo*hi tcgen05.mma per K=16 step into a [128 x BN] fp32
-// accumulator in TMEM (async; it overlaps the staging of the next k-block); the epilogue reads TMEM (tcgen05.ld),
-// transposes through shared memory and stores coalesced 16-byte row segments.  Rows shifted out of their utterance
-// (conv padding) read as zero.
+//
+// Persistent, warp-specialised kernel: one CTA per SM walks [128 x BN] output tiles (n fastest, so the activation rows of
+// a tile row are re-read from L2).  Roles (14 warps):
+//   warps 9-12 activation loaders: every k-block's [128 rows x 128 B] fp32 tile is fetched with 16-byte cp.async copies
+//              (coalesced full lines, zero-fill for rows shifted out of their utterance / the K tail) into a ring of
+//              staging slots -- several k-blocks in flight, no registers held; completion arrives on an mbarrier;
+//   warps 4-7  converters: staging slot -> bf16 hi + lo, stored K-major (no swizzle, padded leading-byte-offset) into the
+//              operand ring;
+//   warp 8     weight loader: the weights are PRE-SPLIT once per call (slu_presplit_bf16) into a k-chunk-major image, so
+//              a stage's weight tile is 8 TMA bulk copies, no thread work;
+//   warp 13    MMA issuer: hi*hi + hi*lo + lo*hi tcgen05.mma per K=16 step into one of TWO [128 x BN] fp32 accumulators
+//              in TMEM; tcgen05.commit frees the operand stage / publishes the accumulator;
+//   warps 0-3  epilogue: tcgen05.ld, bias / LeakyReLU, transpose through shared memory, coalesced 16-byte row stores;
+//              the accumulator is released right after its last tcgen05.ld, so tile i+1's MMAs overlap tile i's stores.
+// Contract of the 16-byte copies: A 16-byte aligned, lda and K multiples of 4 floats (every call site of the model).
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -34,211 +42,285 @@ struct GemmParams {
   float slope;
 };
 
-constexpr int BM = 128, BK = 32, STAGES = 2, THREADS = 256;
+constexpr int BM = 128, BK = 32;
 
 __host__ __device__ constexpr uint32_t tmem_cols(int bn) { return bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256)); }
 
+constexpr int EPI_WARPS = 4, CONV_WARPS = 4;                          // warps 0-3 epilogue (TMEM lane quarters), 4-7 converters
+constexpr int ALOAD_WARPS = 4;
+constexpr int WLOAD_WARP = EPI_WARPS + CONV_WARPS, ALOAD_WARP = WLOAD_WARP + 1, MMA_WARP = ALOAD_WARP + ALOAD_WARPS;
+constexpr int THREADS = (MMA_WARP + 1) * 32;                          // 448
+constexpr int CONV_THREADS = CONV_WARPS * 32, EPI_THREADS = EPI_WARPS * 32, ALOAD_THREADS = ALOAD_WARPS * 32;
+constexpr uint32_t STG_ROW = BK * 4 + 16;                             // staged fp32 row segment + pad: conflict-free 16-byte reads
+constexpr uint32_t STG_SLOT = BM * STG_ROW;
+
 template <int BN>
 struct Smem {
+  static constexpr int STAGES = BN > 128 ? 3 : 4;                     // operand ring (bf16 hi/lo A + B tiles)
+  static constexpr int NSTG = BN > 128 ? 3 : 4;                       // fp32 staging ring of the activation loader
   static constexpr uint32_t LBO_A = BM * 16 + 16, LBO_B = BN * 16 + 16;
   static constexpr uint32_t A_PART = (BK / 8) * LBO_A, B_PART = (BK / 8) * LBO_B;      // one of hi / lo
   static constexpr uint32_t STAGE = 2 * A_PART + 2 * B_PART;
   static constexpr uint32_t PIPE = STAGES * STAGE;
-  static constexpr uint32_t TRANS = 8 * 32 * 33 * 4;                                    // epilogue transpose buffers
-  static constexpr uint32_t TOTAL = PIPE > TRANS ? PIPE : TRANS;
+  static constexpr uint32_t STG = NSTG * STG_SLOT;
+  static constexpr uint32_t TRANS = EPI_WARPS * 32 * 33 * 4;                            // epilogue transpose buffers
+  static constexpr uint32_t TOTAL = PIPE + STG + TRANS;
 };
-
-// 8 consecutive-k fp32 values of one K-contiguous operand row (two 16-byte loads when possible).
-__device__ __forceinline__ void load8_kc(const float* base, int k0, int K, bool row_ok, float* v) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = 0.f;
-  if (!row_ok || k0 >= K) return;
-  const float* p = base + k0;
-  if (k0 + 8 <= K && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) if (k0 + i < K) v[i] = __ldg(p + i);
-  }
-}
 
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using S = Smem<BN>;
+  constexpr int STAGES = S::STAGES, NSTG = S::NSTG;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t empty_bar[STAGES], acc_bar;
+  __shared__ uint64_t full_a[STAGES], full_b[STAGES], empty_bar[STAGES], stg_full[NSTG], stg_empty[NSTG], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int kb_per_tap = (p.K + BK - 1) / BK;
   const int nkb = p.taps * kb_per_tap;
+  const int ntiles_n = (p.N + BN - 1) / BN;
+  const int ntiles = ((p.M + BM - 1) / BM) * ntiles_n;
+  uint8_t* const stg_base = smem + S::PIPE;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
-    mbar_init(&acc_bar, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_a[s], CONV_THREADS);
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < NSTG; ++s) {
+      mbar_init(&stg_full[s], ALOAD_THREADS);       // one (asynchronous) arrival per loader thread
+      mbar_init(&stg_empty[s], CONV_THREADS);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], EPI_THREADS);
+    }
     fence_mbar_init();
   }
   __syncwarp();
-  if (warp == 0) tmem_alloc(&tmem_base, tmem_cols(BN));
+  if (warp == 0) tmem_alloc(&tmem_base, 2 * tmem_cols(BN));
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base;
-  const uint32_t idesc = idesc_bf16_f32(BM, BN);
 
-  // per-thread chunk assignment (fixed across k-blocks): A 2 chunks, B up to 4 chunks of 8 consecutive k
-  constexpr int A_CH = BM * (BK / 8) / THREADS;
-  constexpr int B_TOT = BN * (BK / 8);
-  constexpr int B_CH = (B_TOT + THREADS - 1) / THREADS;
-  int a_r[A_CH], a_kc[A_CH], a_t[A_CH];
-#pragma unroll
-  for (int u = 0; u < A_CH; ++u) {
-    const int c = tid + u * THREADS;
-    a_kc[u] = c & 3; a_r[u] = c >> 2;
-    a_t[u] = p.T ? (m0 + a_r[u]) % p.T : 0;              // frame of this row inside its utterance (tap boundaries)
-  }
-
-  // Register-prefetch pipeline: the global loads of k-block i+1 are issued right after k-block i has been
-  // converted into its shared-memory stage, so their latency hides behind the barrier / MMA issue.
-  float va[A_CH][8];
-  uint4 ib_hi[B_CH], ib_lo[B_CH];
-  auto prefetch = [&](int kb) {
-    const int tap = kb / kb_per_tap, k0 = (kb % kb_per_tap) * BK;
-#pragma unroll
-    for (int u = 0; u < A_CH; ++u) {
-      const int m = m0 + a_r[u];
-      bool ok = m < p.M;
-      long row = m;
-      if (p.taps > 1 || p.tap_pad) {
-        const int sh = tap - p.tap_pad;
-        const int t = a_t[u] + sh;
-        ok = ok && (p.T == 0 || (t >= 0 && t < p.T));
-        row = (long)m + sh;
-      }
-      load8_kc(p.A + row * p.lda, k0 + a_kc[u] * 8, p.K, ok, va[u]);
+  // Is row `r` of the tile at m0 a real row for tap shift `sh`, and where does it start?  (shared by loader and converters)
+  auto row_src = [&](int m0, int r, int a_t, int sh, long& row) -> bool {
+    const int m = m0 + r;
+    bool ok = m < p.M;
+    row = m;
+    if (p.taps > 1 || p.tap_pad) {
+      const int t = a_t + sh;
+      ok = ok && (p.T == 0 || (t >= 0 && t < p.T));
+      row = (long)m + sh;
     }
-#pragma unroll
-    for (int u = 0; u < B_CH; ++u) {
-      const int c = tid + u * THREADS;
-      const int kc = c & 3, r = c >> 2, n = n0 + r;
-      ib_hi[u] = make_uint4(0, 0, 0, 0); ib_lo[u] = ib_hi[u];
-      if (c < B_TOT && n < p.N) {
-        const size_t e = ((size_t)tap * p.N + n) * p.Kp + k0 + kc * 8;
-        ib_hi[u] = __ldg(reinterpret_cast<const uint4*>(p.Wimg + e));
-        ib_lo[u] = __ldg(reinterpret_cast<const uint4*>(p.Wimg + (size_t)p.taps * p.N * p.Kp + e));
-      }
-    }
+    return ok;
   };
-  prefetch(0);
 
-  for (int i = 0; i < nkb; ++i) {
-    const int s = i % STAGES;
-    if (i >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((i / STAGES) - 1) & 1));
-    const int k0 = (i % kb_per_tap) * BK;
-    uint8_t* st = smem + s * S::STAGE;
-    uint8_t* a_hi = st; uint8_t* a_lo = st + S::A_PART;
-    uint8_t* b_hi = st + 2 * S::A_PART; uint8_t* b_lo = b_hi + S::B_PART;
+  if (warp >= ALOAD_WARP && warp < MMA_WARP) {
+    // ================= activation loaders: [128 rows x 128 B] per k-block as 16-byte cp.async copies =================
+    const int lt = tid - ALOAD_WARP * 32;
+    constexpr int PER = BM * (BK / 4) / ALOAD_THREADS;               // 8 pieces of 16 B per thread and k-block
+    const int piece = lt & 7, r0 = lt >> 3;                          // rows r0 + 16 u: a warp covers 4 full 128-byte lines
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int m0 = (tile / ntiles_n) * BM;
+      int a_t[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) a_t[u] = p.T ? (m0 + r0 + 16 * u) % p.T : 0;     // frame of the row inside its utterance
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int slot = it % NSTG;
+        if (it >= NSTG) mbar_wait(&stg_empty[slot], (uint32_t)(((it / NSTG) - 1) & 1));
+        const int tap = kb / kb_per_tap, k0 = (kb % kb_per_tap) * BK;
+        const int kvalid = min(4, max(0, p.K - k0 - piece * 4)) * 4;  // bytes of this piece inside the row (K % 4 == 0: 0 or 16)
+        uint8_t* dst = stg_base + slot * STG_SLOT + piece * 16;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+          long row;
+          const bool ok = row_src(m0, r0 + 16 * u, a_t[u], tap - p.tap_pad, row);
+          const uint32_t nbytes = ok ? (uint32_t)kvalid : 0u;
+          cp_async16(dst + (r0 + 16 * u) * STG_ROW, nbytes ? p.A + row * p.lda + k0 + piece * 4 : p.A, nbytes);
+        }
+        cp_async_mbar_arrive_noinc(&stg_full[slot]);
+      }
+    }
+  } else if (warp >= EPI_WARPS && warp < WLOAD_WARP) {
+    // ================= converters: fp32 staging slot -> bf16 hi/lo K-major operand stage =================
+    const int ptid = tid - EPI_THREADS;
+    constexpr int A_CH = BM * (BK / 8) / CONV_THREADS;              // 4 chunks of 8 consecutive k per thread and k-block
+    int a_r[A_CH], a_kc[A_CH];
 #pragma unroll
     for (int u = 0; u < A_CH; ++u) {
-      uint4 hi, lo; split8(va[u], hi, lo);
-      const uint32_t off = (uint32_t)a_kc[u] * S::LBO_A + (uint32_t)a_r[u] * 16;
-      *reinterpret_cast<uint4*>(a_hi + off) = hi;
-      *reinterpret_cast<uint4*>(a_lo + off) = lo;
+      const int c = ptid + u * CONV_THREADS;
+      a_kc[u] = c & 3; a_r[u] = c >> 2;
     }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES, slot = it % NSTG;
+        mbar_wait(&stg_full[slot], (uint32_t)((it / NSTG) & 1));                       // this k-block's rows have landed
+        const uint8_t* src = stg_base + slot * STG_SLOT;
+        float va[A_CH][8];
 #pragma unroll
-    for (int u = 0; u < B_CH; ++u) {
-      const int c = tid + u * THREADS;
-      if (c < B_TOT) {
-        const uint32_t off = (uint32_t)(c & 3) * S::LBO_B + (uint32_t)(c >> 2) * 16;
-        *reinterpret_cast<uint4*>(b_hi + off) = ib_hi[u];
-        *reinterpret_cast<uint4*>(b_lo + off) = ib_lo[u];
+        for (int u = 0; u < A_CH; ++u) {
+          const float4 x0 = *reinterpret_cast<const float4*>(src + a_r[u] * STG_ROW + a_kc[u] * 32);
+          const float4 x1 = *reinterpret_cast<const float4*>(src + a_r[u] * STG_ROW + a_kc[u] * 32 + 16);
+          va[u][0] = x0.x; va[u][1] = x0.y; va[u][2] = x0.z; va[u][3] = x0.w;      // zero-filled by the loaders where invalid
+          va[u][4] = x1.x; va[u][5] = x1.y; va[u][6] = x1.z; va[u][7] = x1.w;
+        }
+        mbar_arrive(&stg_empty[slot]);                              // values are in registers: the loader may refill the slot
+        if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((it / STAGES) - 1) & 1));
+        uint8_t* a_hi = smem + s * S::STAGE;
+        uint8_t* a_lo = a_hi + S::A_PART;
+#pragma unroll
+        for (int u = 0; u < A_CH; ++u) {
+          uint4 hi, lo; split8(va[u], hi, lo);
+          const uint32_t off = (uint32_t)a_kc[u] * S::LBO_A + (uint32_t)a_r[u] * 16;
+          *reinterpret_cast<uint4*>(a_hi + off) = hi;
+          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+        }
+        fence_async_smem();               // generic-proxy stores -> visible to the tensor core
+        mbar_arrive(&full_a[s]);
       }
     }
-    fence_async_smem();                   // before the prefetch: a proxy fence waits for this thread's outstanding loads
-    if (i + 1 < nkb) prefetch(i + 1);
-    __syncthreads();
-    // ---- one elected thread issues this k-block's MMAs (async: they overlap the staging of the next k-block)
-    if (warp == 0) {
-      if (elect_one()) {
+  } else if (warp == WLOAD_WARP) {
+    // ================= weight loader: 8 TMA bulk copies per stage from the k-chunk-major image =================
+    const int KC = p.Kp / 8;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int n0 = (tile % ntiles_n) * BN;
+      const int rows = min(BN, p.N - n0);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((it / STAGES) - 1) & 1));
+        if (elect_one()) {
+          const int tap = kb / kb_per_tap, kc0 = (kb % kb_per_tap) * (BK / 8);
+          uint8_t* b_hi = smem + s * S::STAGE + 2 * S::A_PART;
+          mbar_arrive_expect_tx(&full_b[s], (uint32_t)(2 * (BK / 8) * rows * 16));
+#pragma unroll
+          for (int part = 0; part < 2; ++part)
+#pragma unroll
+            for (int kc = 0; kc < BK / 8; ++kc) {
+              const size_t e = ((((size_t)part * p.taps + tap) * KC + kc0 + kc) * p.N + n0) * 8;
+              tma_load_1d(b_hi + part * S::B_PART + kc * S::LBO_B, p.Wimg + e, (uint32_t)rows * 16u, &full_b[s]);
+            }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = idesc_bf16_f32(BM, BN);
+    int it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      if (ti >= 2) mbar_wait(&acc_empty[buf], (uint32_t)(((ti >> 1) - 1) & 1));   // epilogue has drained this accumulator
+      fence_after_sync();
+      const uint32_t d_tmem = tmem + (uint32_t)buf * tmem_cols(BN);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        mbar_wait(&full_a[s], ph);
+        mbar_wait(&full_b[s], ph);
         fence_after_sync();
-        const int nk16 = min(BK / 16, (p.K - k0 + 15) / 16);
-        const uint32_t sa = smem_u32(st);
-        const uint64_t ah0 = smem_desc(sa, S::LBO_A, 128), al0 = smem_desc(sa + S::A_PART, S::LBO_A, 128);
-        const uint64_t bh0 = smem_desc(sa + 2 * S::A_PART, S::LBO_B, 128), bl0 = smem_desc(sa + 2 * S::A_PART + S::B_PART, S::LBO_B, 128);
-        uint32_t acc = i > 0 ? 1u : 0u;
+        if (elect_one()) {
+          const int k0 = (kb % kb_per_tap) * BK;
+          const int nk16 = min(BK / 16, (p.K - k0 + 15) / 16);
+          const uint32_t sa = smem_u32(smem + s * S::STAGE);
+          const uint64_t ah0 = smem_desc(sa, S::LBO_A, 128), al0 = smem_desc(sa + S::A_PART, S::LBO_A, 128);
+          const uint64_t bh0 = smem_desc(sa + 2 * S::A_PART, S::LBO_B, 128), bl0 = smem_desc(sa + 2 * S::A_PART + S::B_PART, S::LBO_B, 128);
+          uint32_t acc = kb > 0 ? 1u : 0u;
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          if (kk < nk16) {
-            const uint64_t ah = desc_advance(ah0, kk * 2 * S::LBO_A), al = desc_advance(al0, kk * 2 * S::LBO_A);
-            const uint64_t bh = desc_advance(bh0, kk * 2 * S::LBO_B), bl = desc_advance(bl0, kk * 2 * S::LBO_B);
-            mma_bf16(tmem, ah, bh, idesc, acc); acc = 1u;
-            mma_bf16(tmem, ah, bl, idesc, 1u);
-            mma_bf16(tmem, al, bh, idesc, 1u);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            if (kk < nk16) {
+              const uint64_t ah = desc_advance(ah0, kk * 2 * S::LBO_A), al = desc_advance(al0, kk * 2 * S::LBO_A);
+              const uint64_t bh = desc_advance(bh0, kk * 2 * S::LBO_B), bl = desc_advance(bl0, kk * 2 * S::LBO_B);
+              mma_bf16(d_tmem, ah, bh, idesc, acc); acc = 1u;
+              mma_bf16(d_tmem, ah, bl, idesc, 1u);
+              mma_bf16(d_tmem, al, bh, idesc, 1u);
+            }
           }
+          mma_commit(&empty_bar[s]);                        // stage s may be refilled once these MMAs have read it
+          if (kb == nkb - 1) mma_commit(&acc_full[buf]);    // accumulator complete
         }
-        mma_commit(&empty_bar[s]);
-        if (i == nkb - 1) mma_commit(&acc_bar);
+        __syncwarp();
       }
-      __syncwarp();
     }
-  }
-
-  // ================= epilogue: TMEM -> registers -> smem transpose -> coalesced global rows =================
-  mbar_wait(&acc_bar, 0);
-  fence_after_sync();
-  {
-    const int q = warp & 3, half = warp >> 2;                      // TMEM lane quarter, column half
-    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33); // the pipeline buffers are free once acc_bar fired
-    constexpr int CW = BN / 2;                                     // columns per warp (32, 64 or 128)
+  } else {
+    // ================= epilogue: TMEM -> registers -> smem transpose -> coalesced global rows =================
+    const int q = warp;                                            // TMEM lane quarter == rows 32q .. 32q+31 of the tile
+    float* tr = reinterpret_cast<float*>(smem + S::PIPE + S::STG) + warp * (32 * 33);
+    const bool vec_ok = (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      const int m0 = (tile / ntiles_n) * BM, n0 = (tile % ntiles_n) * BN;
+      const int ncols = min(BN, p.N - n0);
+      const int nchunks = (ncols + 31) / 32;
+      mbar_wait(&acc_full[buf], (uint32_t)((ti >> 1) & 1));
+      fence_after_sync();
+      const uint32_t t_acc = tmem + (uint32_t)buf * tmem_cols(BN) + ((uint32_t)(q * 32) << 16);
+      const int rows = min(32, p.M - (m0 + q * 32));               // may be <= 0 for the tail tile
 #pragma unroll 1
-    for (int cc = 0; cc < CW; cc += 32) {
-      const int c0 = half * CW + cc;
-      if (n0 + c0 >= p.N) break;
-      float v[32];
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0 + 16, v + 16);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
-      __syncwarp();
-      const int rows = min(32, p.M - (m0 + q * 32));
-      if (rows == 32 && n0 + c0 + 32 <= p.N && (p.ldc & 3) == 0 && ((n0 + c0) & 3) == 0 &&
-          (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
-        // fast path: 16-byte stores, a warp instruction writes 4 rows x 128 B
-        const int cq = (lane & 7) * 4, r0 = lane >> 3;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + cq));
-        float* dst4 = p.C + (long)(m0 + q * 32) * p.ldc + n0 + c0 + cq;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 4 * i;
-          float4 x;
-          x.x = tr[r * 33 + cq] + b4.x; x.y = tr[r * 33 + cq + 1] + b4.y; x.z = tr[r * 33 + cq + 2] + b4.z; x.w = tr[r * 33 + cq + 3] + b4.w;
-          if (p.act == 1) {
-            x.x = x.x > 0.f ? x.x : x.x * p.slope; x.y = x.y > 0.f ? x.y : x.y * p.slope;
-            x.z = x.z > 0.f ? x.z : x.z * p.slope; x.w = x.w > 0.f ? x.w : x.w * p.slope;
-          }
-          *reinterpret_cast<float4*>(dst4 + (long)r * p.ldc) = x;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = ch * 32;
+        float v[32];
+        tmem_ld16(t_acc + c0, v);
+        tmem_ld16(t_acc + c0 + 16, v + 16);
+        tmem_ld_wait();
+        if (ch == nchunks - 1) {          // last read of this accumulator: hand it back to the MMA warp
+          fence_before_sync();
+          mbar_arrive(&acc_empty[buf]);
         }
-      } else {
-        const int n = n0 + c0 + lane;
-        if (n < p.N) {
-          const float bias = p.bias ? __ldg(p.bias + n) : 0.f;
-          float* dst = p.C + (long)(m0 + q * 32) * p.ldc + n;
-          for (int r = 0; r < rows; ++r) {
-            float x = tr[r * 33 + lane] + bias;
-            if (p.act == 1) x = x > 0.f ? x : x * p.slope;
-            dst[(long)r * p.ldc] = x;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
+        __syncwarp();
+        if (rows == 32 && c0 + 32 <= ncols && vec_ok && ((n0 + c0) & 3) == 0) {
+          // fast path: 16-byte stores, a warp instruction writes 4 rows x 128 B
+          const int cq = (lane & 7) * 4, r0 = lane >> 3;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + cq));
+          float* dst4 = p.C + (long)(m0 + q * 32) * p.ldc + n0 + c0 + cq;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 4 * i;
+            float4 x;
+            x.x = tr[r * 33 + cq] + b4.x; x.y = tr[r * 33 + cq + 1] + b4.y; x.z = tr[r * 33 + cq + 2] + b4.z; x.w = tr[r * 33 + cq + 3] + b4.w;
+            if (p.act == 1) {
+              x.x = x.x > 0.f ? x.x : x.x * p.slope; x.y = x.y > 0.f ? x.y : x.y * p.slope;
+              x.z = x.z > 0.f ? x.z : x.z * p.slope; x.w = x.w > 0.f ? x.w : x.w * p.slope;
+            }
+            *reinterpret_cast<float4*>(dst4 + (long)r * p.ldc) = x;
+          }
+        } else {
+          const int n = n0 + c0 + lane;
+          if (c0 + lane < ncols) {
+            const float bias = p.bias ? __ldg(p.bias + n) : 0.f;
+            float* dst = p.C + (long)(m0 + q * 32) * p.ldc + n;
+            for (int r = 0; r < rows; ++r) {
+              float x = tr[r * 33 + lane] + bias;
+              if (p.act == 1) x = x > 0.f ? x : x * p.slope;
+              dst[(long)r * p.ldc] = x;
+            }
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, tmem_cols(BN));
+  if (warp == 0) tmem_dealloc(tmem, 2 * tmem_cols(BN));
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
 }
 
 template <int BN>
@@ -246,19 +328,33 @@ int launch(const GemmParams& p, cudaStream_t stream) {
   const size_t smem = Smem<BN>::TOTAL;
   static int attr = slu_set_smem((const void*)gemm_tc_kernel<BN>, smem);
   if (attr) return attr;
-  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<BN><<<grid, THREADS, smem, stream>>>(p);
   return (int)cudaGetLastError();
 }
 
 // fp32 strided weights -> bf16 hi / lo images [2][taps][N][Kp] (zero padded to Kp, a multiple of 32)
+// CHUNK_MAJOR: image [2][taps][Kp/8][N][8] (every 8-element k-chunk of all N rows contiguous = what one TMA bulk copy of the
+// GEMM's weight loader moves); otherwise row-major [2][taps][N][Kp].
+template <bool CHUNK_MAJOR>
 __global__ void presplit_kernel(const float* __restrict__ W, long sn, long sk, long stap, int taps, int N, int K, int Kp,
                                 int row_len, __nv_bfloat16* __restrict__ img) {
   const size_t total = (size_t)taps * N * Kp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % Kp);
-    const size_t tn = i / Kp;
-    const int n = (int)(tn % N), tap = (int)(tn / N);
+    int k, n, tap;
+    if (CHUNK_MAJOR) {
+      const int e = (int)(i & 7);
+      const size_t r = i >> 3;
+      n = (int)(r % N);
+      const size_t c = r / N;
+      k = (int)(c % (Kp / 8)) * 8 + e;
+      tap = (int)(c / (Kp / 8));
+    } else {
+      k = (int)(i % Kp);
+      const size_t tn = i / Kp;
+      n = (int)(tn % N); tap = (int)(tn / N);
+    }
     float v = 0.f;
     if (k < K && (row_len == 0 || (long)k * sk + (long)tap * stap < row_len)) v = W[(long)n * sn + (long)k * sk + (long)tap * stap];
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -276,14 +372,20 @@ int slu_presplit_rows(const float* W, long sn, long sk, long stap, int taps, int
   const size_t total = (size_t)taps * N * Kp;
   int grid = (int)((total + 255) / 256);
   if (grid > 1184) grid = 1184;
-  presplit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, sn, sk, stap, taps, N, K, Kp, row_len, (__nv_bfloat16*)img);
+  presplit_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(W, sn, sk, stap, taps, N, K, Kp, row_len, (__nv_bfloat16*)img);
   return (int)cudaGetLastError();
 }
 
-// Pre-split a (strided) fp32 weight operand W(n, tap, k) = W[n*sn + k*sk + tap*stap] into the bf16 hi/lo image the GEMM's
-// weight side copies verbatim.  img must hold 2 * taps * N * Kp bf16 values, Kp = K rounded up to a multiple of 32.
+// Pre-split a (strided) fp32 weight operand W(n, tap, k) = W[n*sn + k*sk + tap*stap] into the k-chunk-major bf16 hi/lo image the
+// GEMM's weight loader copies verbatim.  img must hold 2 * taps * N * Kp bf16 values, Kp = K rounded up to a multiple of 32.
 extern "C" int slu_presplit_bf16(const float* W, long sn, long sk, long stap, int taps, int N, int K, void* img, void* stream) {
-  return slu_presplit_rows(W, sn, sk, stap, taps, N, K, 0, img, stream);
+  if (taps <= 0 || N <= 0 || K <= 0) return (int)cudaErrorInvalidValue;
+  const int Kp = (K + 31) / 32 * 32;
+  const size_t total = (size_t)taps * N * Kp;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 1184) grid = 1184;
+  presplit_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(W, sn, sk, stap, taps, N, K, Kp, 0, (__nv_bfloat16*)img);
+  return (int)cudaGetLastError();
 }
 
 // C[m][n] = sum_tap sum_k A[(m + tap - tap_pad)*lda + k] * W(n, tap, k) (+ bias[n]) (LeakyReLU if act == 1); see include/slu_b200.h
@@ -293,8 +395,22 @@ extern "C" int slu_gemm_tc(const float* A, long lda, const void* w_img, const fl
   GemmParams p;
   p.A = A; p.lda = lda; p.Wimg = (const __nv_bfloat16*)w_img; p.Kp = (K + 31) / 32 * 32; p.bias = bias;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.taps = taps; p.tap_pad = tap_pad; p.T = T; p.act = act; p.slope = slope;
+  // TMA source alignment: 16-byte aligned operands, row pitch and K in whole 16-byte units
+  if ((reinterpret_cast<uintptr_t>(w_img) & 15) != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0 || (lda & 3) != 0 || (K & 3) != 0)
+    return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
-  if (N <= 64) return launch<64>(p, st);
-  if (N <= 128) return launch<128>(p, st);
+  // Column-tile width: the widest tile unless a narrower one needs clearly fewer waves of the persistent grid (short
+  // sequences / small batches).  Cost model per wave: max(BN, 128) -- below 128 columns the producers bound a k-block.
+  const int mt = (M + BM - 1) / BM, sms = sm_count();
+  int best_bn = 0;
+  long best_cost = 0;
+  for (int bn = 256; bn >= 64; bn >>= 1) {
+    if (bn > 64 && N <= bn / 2) continue;                     // tile would be mostly padding
+    const long tiles = (long)mt * ((N + bn - 1) / bn);
+    const long cost = ((tiles + sms - 1) / sms) * (bn > 128 ? bn : 128);
+    if (best_bn == 0 || cost * 10 < best_cost * 9) { best_bn = bn; best_cost = cost; }
+  }
+  if (best_bn == 64) return launch<64>(p, st);
+  if (best_bn == 128) return launch<128>(p, st);
   return launch<256>(p, st);
 }

@@ -38,7 +38,7 @@ __device__ __forceinline__ void load_weights_to_tmem(uint32_t tmem, uint32_t lan
 #pragma unroll 8
     for (int k = 0; k < KW; ++k) row[k] = __ldg(p + (size_t)k * k_stride);
     const uint32_t t_hi = tmem + lane_base + (uint32_t)(g * 64 + half * (KW / 2));
-    if (PASSES == 3) tmem_store_row_split(t_hi, t_hi + 192, row, KW);
+    if (PASSES != 1) tmem_store_row_split(t_hi, t_hi + 192, row, KW);
     else tmem_store_row_f16(t_hi, row, KW);
   }
 }
@@ -46,7 +46,7 @@ __device__ __forceinline__ void load_weights_to_tmem(uint32_t tmem, uint32_t lan
 // Operand copy of one activation value into the K-major B tile: bf16 hi + lo (3-pass) or a single fp16 (1-pass).
 template <int PASSES>
 __device__ __forceinline__ void store_operand(uint8_t* hi, uint8_t* lo, float v) {
-  if (PASSES == 3) {
+  if (PASSES != 1) {
     const __nv_bfloat16 hh = __float2bfloat16_rn(v);
     *reinterpret_cast<__nv_bfloat16*>(hi) = hh;
     *reinterpret_cast<__nv_bfloat16*>(lo) = __float2bfloat16_rn(v - __bfloat162float(hh));
@@ -55,7 +55,12 @@ __device__ __forceinline__ void store_operand(uint8_t* hi, uint8_t* lo, float v)
   }
 }
 
-// The 8 K-steps of one [128 x NB] += A(tmem) . B(smem)^T product: 24 MMAs (bf16 hi*hi + hi*lo + lo*hi) or 8 (fp16).
+// The 8 K-steps of one [128 x NB] += A(tmem) . B(smem)^T product:
+//   PASSES 3: 24 MMAs, bf16 hi*hi + hi*lo + lo*hi with separate hi / lo activation tiles;
+//   PASSES 2: 16 MMAs -- the activation tile STACKS its hi rows (0..NR-1) and lo rows (NR..2NR-1) along N, so W_hi.[hi;lo]
+//             and W_lo.[hi;lo] accumulate all four partial products; the epilogue adds accumulator column c + NR to column c
+//             (needs 2*NR <= NB; the latency-critical small-batch tiles);
+//   PASSES 1: 8 MMAs, single fp16 pass.
 template <int PASSES>
 __device__ __forceinline__ void issue_product(uint32_t dacc, uint32_t a_hi, uint32_t a_lo, uint64_t bdesc_hi, uint64_t bdesc_lo,
                                               uint32_t k_byte0, uint32_t lbo, uint32_t idesc) {
@@ -63,6 +68,7 @@ __device__ __forceinline__ void issue_product(uint32_t dacc, uint32_t a_hi, uint
   for (int kk = 0; kk < 8; ++kk) {
     const uint64_t bh = desc_advance(bdesc_hi, k_byte0 + kk * 2 * lbo);
     mma_bf16_ts(dacc, a_hi + kk * 8, bh, idesc, kk > 0 ? 1u : 0u);
+    if (PASSES == 2) mma_bf16_ts(dacc, a_lo + kk * 8, bh, idesc, 1u);
     if (PASSES == 3) {
       const uint64_t bl = desc_advance(bdesc_lo, k_byte0 + kk * 2 * lbo);
       mma_bf16_ts(dacc, a_hi + kk * 8, bl, idesc, 1u);
@@ -149,12 +155,12 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   float hprev[NC], pend[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) { hprev[c] = 0.f; pend[c] = 0.f; }
-  const uint32_t idesc = PASSES == 3 ? idesc_bf16_f32(128, NB) : idesc_f16_f32(128, NB);
+  const uint32_t idesc = PASSES != 1 ? idesc_bf16_f32(128, NB) : idesc_f16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
   const uint64_t bdesc_hi = smem_desc(smem_u32(h_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(h_lo), LBO, 128);
   // byte offset of element (k = j) inside a k-chunk-major row b: (j/8)*LBO + b*16 + (j%8)*2
   uint8_t* h_hi_j = h_hi + (uint32_t)(j >> 3) * LBO + (uint32_t)(j & 7) * 2 + c0 * 16;
-  uint8_t* h_lo_j = h_hi_j + 16 * LBO;
+  uint8_t* h_lo_j = PASSES == 2 ? h_hi_j + NR * 16 : h_hi_j + 16 * LBO;     // stacked: lo rows follow the NR hi rows of the same tile
 
   long long* dbg = (g_phase_clk && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 128)) ? g_phase_clk + (tid ? 8 : 0) : nullptr;
   long long tprev_ = clock64();
@@ -163,6 +169,18 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
     const int t = t_first + dt * s;
     float ar[NC], az[NC], an[NC];
     PHASE(7);
+    // Step inputs first: they landed long ago, so their barrier wait and shared-memory reads hide under the MMAs that are
+    // still running; only the accumulator-dependent part of the gate math stays behind the MMA barrier.
+    mbar_wait(&in_bar[s % FWD_RING], (uint32_t)((s / FWD_RING) & 1));       // this step's gx / mask rows have landed
+    const float* gxs = in_ring + (s % FWD_RING) * SLOT + c0 * 384 + j;
+    const float* mks = in_ring + (s % FWD_RING) * SLOT + NR * 384 + c0 * 128 + j;
+    float xr[NC], xz[NC], xn[NC], mk[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      xr[c] = gxs[c * 384] + bhr; xz[c] = gxs[c * 384 + 128] + bhz; xn[c] = gxs[c * 384 + 256];
+      mk[c] = mask ? mks[c * 128] : 1.f;
+    }
+    PHASE(2);                        // TMA ring wait + input reads
     if (s == 0) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) ar[c] = az[c] = an[c] = 0.f;       // h_{-1} = 0
@@ -171,7 +189,15 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       fence_after_sync();
       PHASE(0);                      // mbarrier wait for the MMAs
       tmem_ld<NC>(acc_addr, ar); tmem_ld<NC>(acc_addr + NB, az); tmem_ld<NC>(acc_addr + 2 * NB, an);
-      tmem_ld_wait();
+      if (PASSES == 2) {             // stacked operand: the lo-row partial products sit NR columns to the right
+        float br[NC], bz[NC], bn[NC];
+        tmem_ld<NC>(acc_addr + NR, br); tmem_ld<NC>(acc_addr + NB + NR, bz); tmem_ld<NC>(acc_addr + 2 * NB + NR, bn);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { ar[c] += br[c]; az[c] += bz[c]; an[c] += bn[c]; }
+      } else {
+        tmem_ld_wait();
+      }
       PHASE(1);                      // tcgen05.ld
     }
     // Downsample(avg,2) bookkeeping, uniform per step: `single` = odd tail frame (divisor 1, ceil_mode),
@@ -179,25 +205,21 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
     const bool single = (ds == 1) || (((t & 1) == 0) && (t == T - 1));
     const bool first = !single && ((t & 1) == (d ? 1 : 0));
     const int to = (ds == 2 ? (t >> 1) : t) * 256;
-    mbar_wait(&in_bar[s % FWD_RING], (uint32_t)((s / FWD_RING) & 1));       // this step's gx / mask rows have landed
-    PHASE(2);                        // TMA ring wait
-    const float* gxs = in_ring + (s % FWD_RING) * SLOT + c0 * 384 + j;
-    const float* mks = in_ring + (s % FWD_RING) * SLOT + NR * 384 + c0 * 128 + j;
     float o_h[NC], o_out[NC], o_r[NC], o_z[NC], o_n[NC], o_hn[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       // r, z share one reciprocal:  r = (1+v)/((1+u)(1+v)), z = (1+u)/((1+u)(1+v)),  u = e^-pr, v = e^-pz
-      const float pr = fmaxf(gxs[c * 384] + (ar[c] + bhr), -40.f);     // lower clamp keeps (1+u)(1+v) finite
-      const float pz = fmaxf(gxs[c * 384 + 128] + (az[c] + bhz), -40.f);
+      const float pr = fmaxf(xr[c] + ar[c], -40.f);     // lower clamp keeps (1+u)(1+v) finite
+      const float pz = fmaxf(xz[c] + az[c], -40.f);
       const float su = 1.f + ex2_approx(-kLog2e * pr), sv = 1.f + ex2_approx(-kLog2e * pz);
       const float w = rcp_approx(su * sv);
       const float r = w * sv, z = w * su;
       const float hn = an[c] + bhn;
-      const float n = 2.f * rcp_approx(1.f + ex2_approx(-2.f * kLog2e * (gxs[c * 384 + 256] + r * hn))) - 1.f;   // tanh; inf-safe
+      const float n = 2.f * rcp_approx(1.f + ex2_approx(-2.f * kLog2e * (xn[c] + r * hn))) - 1.f;   // tanh; inf-safe
       const float hnew = n + z * (hprev[c] - n);
       hprev[c] = hnew;
       store_operand<PASSES>(h_hi_j + c * 16, h_lo_j + c * 16, hnew);
-      const float val = mask ? hnew * mks[c * 128] : hnew;
+      const float val = hnew * mk[c];
       o_out[c] = single ? val : 0.5f * (pend[c] + val);
       pend[c] = val;
       o_h[c] = hnew;
@@ -313,11 +335,11 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   };
   if (warp == 3 && elect_one())
     for (int s = 0; s < BWD_RING && s < T; ++s) tma_issue(s);
-  const uint32_t idesc = PASSES == 3 ? idesc_bf16_f32(128, NB) : idesc_f16_f32(128, NB);
+  const uint32_t idesc = PASSES != 1 ? idesc_bf16_f32(128, NB) : idesc_f16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
   const uint64_t bdesc_hi = smem_desc(smem_u32(g_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(g_lo), LBO, 128);
   uint8_t* g_hi_j = g_hi + (uint32_t)(j >> 3) * LBO + (uint32_t)(j & 7) * 2 + c0 * 16;     // + gate*16*LBO + c*16
-  uint8_t* g_lo_j = g_hi_j + 48 * LBO;
+  uint8_t* g_lo_j = PASSES == 2 ? g_hi_j + NR * 16 : g_hi_j + 48 * LBO;
   float dh_direct[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) dh_direct[c] = 0.f;
@@ -325,19 +347,8 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
 
   for (int s = 0; s < T; ++s) {
     const int t = t_first + dt * s;
-    float rec[NC];
-    if (s == 0) {
-#pragma unroll
-      for (int c = 0; c < NC; ++c) rec[c] = 0.f;
-    } else {
-      mbar_wait(&bar, (uint32_t)((s - 1) & 1));
-      fence_after_sync();
-      float r1[NC], r2[NC];                 // three partial accumulators (one per gate-row chunk / issuing warp)
-      tmem_ld<NC>(acc_addr, rec); tmem_ld<NC>(acc_addr + NB, r1); tmem_ld<NC>(acc_addr + 2 * NB, r2);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < NC; ++c) rec[c] += r1[c] + r2[c];
-    }
+    // Step inputs and every factor that does not depend on the recurrent term come first: the barrier wait, the
+    // shared-memory reads and this arithmetic hide under the MMAs that are still running.
     const int tp = t + dt;
     const float hp_on = (tp >= 0 && tp < T) ? 1.f : 0.f;
     const float dscale = (ds == 2 && !((t & 1) == 0 && t == T - 1)) ? 0.5f : 1.f;
@@ -347,17 +358,47 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
     const float* hps = sl + NR * 512 + c0 * 128 + j;
     const float* dys = sl + NR * 640 + c0 * 128 + j;
     const float* mks = sl + NR * 768 + c0 * 128 + j;
-    float o_r[NC], o_z[NC], o_n[NC], o_hn[NC];
+    float base[NC], zc[NC], f_n[NC], f_z[NC], f_r[NC], rc[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const float mkv = mask ? mks[c * 128] : 1.f;
-      const float dh = rec[c] + dh_direct[c] + dys[c * 128] * (dscale * mkv);
       const float r = sts[c * 512], z = sts[c * 512 + 128], n = sts[c * 512 + 256];
-      const float dn_pre = dh * (1.f - z) * (1.f - n * n);
-      const float dz_pre = dh * (hps[c * 128] * hp_on - n) * z * (1.f - z);
-      const float dhn = dn_pre * r;
-      const float dr_pre = dn_pre * sts[c * 512 + 384] * r * (1.f - r);
-      dh_direct[c] = dh * z;
+      base[c] = dh_direct[c] + dys[c * 128] * (dscale * mkv);            // dL/dh without the recurrent part
+      zc[c] = z; rc[c] = r;
+      f_n[c] = (1.f - z) * (1.f - n * n);                                // dn_pre = dh * f_n
+      f_z[c] = (hps[c * 128] * hp_on - n) * z * (1.f - z);               // dz_pre = dh * f_z
+      f_r[c] = sts[c * 512 + 384] * r * (1.f - r);                       // dr_pre = dn_pre * f_r
+    }
+    float rec[NC];
+    if (s == 0) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) rec[c] = 0.f;
+    } else {
+      mbar_wait(&bar, (uint32_t)((s - 1) & 1));
+      fence_after_sync();
+      float r1[NC], r2[NC];                 // three partial accumulators (one per gate-row chunk / issuing warp)
+      tmem_ld<NC>(acc_addr, rec); tmem_ld<NC>(acc_addr + NB, r1); tmem_ld<NC>(acc_addr + 2 * NB, r2);
+      if (PASSES == 2) {                    // stacked operand: the lo-row partial products sit NR columns to the right
+        float q0[NC], q1[NC], q2[NC];
+        tmem_ld<NC>(acc_addr + NR, q0); tmem_ld<NC>(acc_addr + NB + NR, q1); tmem_ld<NC>(acc_addr + 2 * NB + NR, q2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < NC; ++c) rec[c] += (r1[c] + r2[c]) + (q0[c] + q1[c] + q2[c]);
+      } else {
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < NC; ++c) rec[c] += r1[c] + r2[c];
+      }
+    }
+    float o_r[NC], o_z[NC], o_n[NC], o_hn[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float dh = rec[c] + base[c];
+      const float dn_pre = dh * f_n[c];
+      const float dz_pre = dh * f_z[c];
+      const float dhn = dn_pre * rc[c];
+      const float dr_pre = dn_pre * f_r[c];
+      dh_direct[c] = dh * zc[c];
       const float gv[3] = {dr_pre, dz_pre, dhn};
 #pragma unroll
       for (int g = 0; g < 3; ++g)
@@ -405,11 +446,13 @@ extern "C" int slu_debug_gru_phase_clocks(long long* buf) {   // developer tool;
   return (int)cudaMemcpyToSymbol(g_phase_clk, &buf, sizeof(buf));
 }
 
-// 0 = bf16 hi/lo 3-pass (fp32-class accuracy, default), 1 = single fp16 pass (11-bit operands; logits stay inside the
-// 1e-3 tolerance, see oracle/precision_study.py) -- 3x fewer MMAs on the step-critical path.
+// 0 = bf16 hi/lo split, fp32-class accuracy (default): hi/lo rows stacked along N (2 MMAs per K step) on the 4- and 8-row
+//     tiles, three separate passes on the 16-row tile;
+// 1 = single fp16 pass (11-bit operands; logits stay inside the 1e-3 tolerance, see oracle/precision_study.py);
+// 2 = bf16 hi/lo as three separate passes on every tile (the un-stacked form, kept for A/B checks).
 static int g_gru_mode = 0;
 extern "C" int slu_set_gru_precision(int mode) {
-  if (mode != 0 && mode != 1) return (int)cudaErrorInvalidValue;
+  if (mode < 0 || mode > 2) return (int)cudaErrorInvalidValue;
   g_gru_mode = mode;
   return 0;
 }
@@ -422,10 +465,13 @@ template <int NR, bool STASH, bool FULL>
 static void launch_fwd(dim3 grid, cudaStream_t st, const float* gx, const float* w_hh, const float* b_hh, const float* mask,
                        int B, int T, int ds, int tile0, float* y_full, float* y_out, float* stash) {
   constexpr size_t smem = (size_t)FWD_RING * NR * 512 * sizeof(float);
+  constexpr int P = 2 * NR <= 16 ? 2 : 3;            // stacked hi/lo rows fit the 16-wide MMA tile
   static int a3 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, 3>, smem);
+  static int a2 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, P>, smem);
   static int a1 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, 1>, smem);
-  (void)a3; (void)a1;
-  if (g_gru_mode == 0) gru_fwd_tc_kernel<16, NR, STASH, FULL, 3><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
+  (void)a3; (void)a2; (void)a1;
+  if (g_gru_mode == 0) gru_fwd_tc_kernel<16, NR, STASH, FULL, P><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
+  else if (g_gru_mode == 2) gru_fwd_tc_kernel<16, NR, STASH, FULL, 3><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
   else gru_fwd_tc_kernel<16, NR, STASH, FULL, 1><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
 }
 
@@ -460,10 +506,13 @@ template <int NR, bool FULL>
 static void launch_bwd(dim3 grid, cudaStream_t st, const float* dy_out, const float* mask, const float* y_full, const float* stash,
                        const float* w_hh, int B, int T, int ds, int tile0, float* dgx, float* dhn, float* dbias) {
   constexpr size_t smem = (size_t)BWD_RING * NR * 896 * sizeof(float);
+  constexpr int P = 2 * NR <= 16 ? 2 : 3;
   static int a3 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, 3>, smem);
+  static int a2 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, P>, smem);
   static int a1 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, 1>, smem);
-  (void)a3; (void)a1;
-  if (g_gru_mode == 0) gru_bwd_tc_kernel<16, NR, FULL, 3><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
+  (void)a3; (void)a2; (void)a1;
+  if (g_gru_mode == 0) gru_bwd_tc_kernel<16, NR, FULL, P><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
+  else if (g_gru_mode == 2) gru_bwd_tc_kernel<16, NR, FULL, 3><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
   else gru_bwd_tc_kernel<16, NR, FULL, 1><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
 }
 

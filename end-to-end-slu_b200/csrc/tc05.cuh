@@ -60,6 +60,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
+// ---- Ampere-style 16-byte async copy global -> shared (SASS: LDGSTS), zero-filling beyond src_bytes, and its
+// completion hook: the mbarrier receives one of its expected arrivals once all prior cp.async of this thread have landed.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---- fences ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

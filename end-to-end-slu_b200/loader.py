@@ -8,6 +8,16 @@ device tensors (`forward` accepts those unchanged, as in the README snippet).  H
 import torch
 
 
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    """One copy stream per device for the life of the process (creating a stream per epoch is not free)."""
+    if device.index not in _copy_streams:
+        _copy_streams[device.index] = torch.cuda.Stream(device=device)
+    return _copy_streams[device.index]
+
+
 class DevicePrefetcher:
     def __init__(self, loader, device=None, depth=1):
         self.loader = loader
@@ -31,7 +41,7 @@ class DevicePrefetcher:
             return tuple(out), stream.record_event()
 
     def __iter__(self):
-        stream = torch.cuda.Stream(device=self.device)
+        stream = _copy_stream(self.device)
         it = iter(self.loader)
         staged = []
         try:

@@ -141,8 +141,9 @@ def conv_block(x, weight, bias, slope):
 
 
 def set_gru_precision(mode):
-    """'bf16x3' (default, fp32-class) or 'fp16' (single pass) operand format of the tcgen05 recurrence."""
-    _lib.load().slu_set_gru_precision({"bf16x3": 0, "fp16": 1}[mode])
+    """Operand format of the tcgen05 recurrence: 'bf16x3' (default, fp32-class bf16 hi/lo split; hi/lo rows stacked along N
+    on the small-batch tiles), 'fp16' (single pass), 'bf16x3-separate' (three separate passes everywhere, for A/B checks)."""
+    _lib.load().slu_set_gru_precision({"bf16x3": 0, "fp16": 1, "bf16x3-separate": 2}[mode])
 
 
 class SincFrontend(torch.autograd.Function):

@@ -64,8 +64,12 @@ int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const 
 int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
                    const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* dbias, void* stream);
 
-/* Operand format of the tcgen05 recurrence: 0 = bf16 hi/lo 3-pass (fp32-class accuracy, default), 1 = one fp16 pass
- * (11-bit operands: 3x fewer MMAs per step; intent logits stay within the 1e-3 parity tolerance). */
+/* Operand format of the tcgen05 recurrence:
+ *   0 = bf16 hi/lo split, fp32-class accuracy (default).  On the 4- and 8-row batch tiles the hi and lo rows of the activation
+ *       tile are stacked along the MMA's N dimension, so 2 MMAs per K step (W_hi, W_lo) accumulate all four partial products;
+ *       the 16-row tile issues hi*hi + hi*lo + lo*hi as three passes;
+ *   1 = one fp16 pass (11-bit operands; intent logits stay within the 1e-3 parity tolerance);
+ *   2 = three separate bf16 passes on every tile (un-stacked form, for A/B checks). */
 int slu_set_gru_precision(int mode);
 
 /* Developer tool: accumulate clock64() per step phase of slu_gru_fwd_tc (CTA 0, threads 0 and 128) into buf[2][8]. */

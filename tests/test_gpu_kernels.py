@@ -201,11 +201,13 @@ def test_conv_block_tc_fwd_bwd(pkg, monkeypatch, B, T, Cin, Cout):
     assert rel_err(wc.grad.cpu(), w.grad) < GRAD_TOL and rel_err(bc.grad.cpu(), b.grad) < GRAD_TOL
 
 
+@pytest.mark.parametrize("mode,ftol,gtol", [("fp16", 2e-3, 1e-2), ("bf16x3-separate", FWD_TOL, GRAD_TOL)])
 @pytest.mark.parametrize("B,T,I,ds", [(16, 40, 256, 2), (5, 23, 60, 1)])
-def test_bigru_fp16_single_pass_mode(pkg, monkeypatch, B, T, I, ds):
-    """Optional operand format of the recurrence (one fp16 pass): looser per-layer tolerance, same semantics."""
+def test_bigru_alternative_operand_formats(pkg, monkeypatch, B, T, I, ds, mode, ftol, gtol):
+    """Other operand formats of the recurrence: one fp16 pass (looser per-layer tolerance) and the un-stacked three-pass
+    bf16 split (same tolerance as the default stacked form)."""
     monkeypatch.setattr(pkg.ops, "GRU_IMPL", "tc")
-    pkg.ops.set_gru_precision("fp16")
+    pkg.ops.set_gru_precision(mode)
     try:
         rs = np.random.RandomState(B + T)
         gru = torch.nn.GRU(I, 128, batch_first=True, bidirectional=True)
@@ -217,11 +219,11 @@ def test_bigru_fp16_single_pass_mode(pkg, monkeypatch, B, T, I, ds):
         gru_c.load_state_dict(gru.state_dict())
         xc = x.detach().cuda().requires_grad_(True)
         yc = pkg.ops.bigru(xc, gru_c, None, ds)
-        assert rel_err(yc.detach().cpu(), y.detach()) < 2e-3
+        assert rel_err(yc.detach().cpu(), y.detach()) < ftol
         yc.backward(gy.cuda())
-        assert rel_err(xc.grad.cpu(), x.grad) < 1e-2
+        assert rel_err(xc.grad.cpu(), x.grad) < gtol
         for k, v in gru_c.named_parameters():
-            assert rel_err(v.grad.cpu(), gru.get_parameter(k).grad) < 1e-2, k
+            assert rel_err(v.grad.cpu(), gru.get_parameter(k).grad) < gtol, k
     finally:
         pkg.ops.set_gru_precision("bf16x3")
 
