@@ -127,6 +127,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=8)
+    ap.add_argument("--launch-detail", action="store_true", help="print every launch of one step with its sizes and device time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-gpu", action="store_true", help="also time the reference-structured port on this GPU (cuDNN)")
     ap.add_argument("--eval-dropout", action="store_true", help="disable dropout (debug)")
@@ -224,9 +225,13 @@ def main():
 
     # ---- per-kernel device time (CUDA events around every C-ABI launch, separate untimed pass) -----
     pkg.ops.OVERLAP = False                                  # serialise the side-stream launches: clean per-kernel durations
-    pkg._lib.profile_begin()
+    pkg._lib.profile_begin(detail=args.launch_detail)
     for i in range(3):
         step(xs_dev[i % NB], ys_dev[i % NB])
+    if args.launch_detail and rank == 0:                     # per-launch table (sizes, ms) of the last profiled step -> stderr
+        det = pkg._lib.profile_detail()
+        for n, a, ms in det[2 * len(det) // 3:]:
+            print("launch %-22s %-60s %8.1f us" % (n, a, ms * 1e3), file=sys.stderr)
     prof = pkg._lib.profile_end()                            # {name: [ms, ...]}
     pkg.ops.OVERLAP = True
     hbm_peak, tf_burst, tf_sust, how = peaks()

@@ -70,6 +70,7 @@ def stream():
 
 stats = {"calls": 0}        # number of C-ABI kernel launches issued by this process
 _prof = None                # name -> [(start_event, end_event)] while profiling
+_prof_detail = None         # [(name, small-int args, start, end)] per launch, when asked for
 _fn = {}
 _HOST_ONLY = ("slu_stream_fork", "slu_stream_join", "slu_set_gru_precision", "slu_debug_gru_phase_clocks")
 
@@ -87,6 +88,8 @@ def call(name, *args):
         err = fn(*args)
         e1.record(st)
         _prof.setdefault(name, []).append((e0, e1))
+        if _prof_detail is not None:
+            _prof_detail.append((name, tuple(a for a in args if isinstance(a, int) and 0 <= a < (1 << 24)), e0, e1))
     else:
         err = fn(*args)
     if err != 0:
@@ -105,10 +108,17 @@ def join(main, n):
     call("slu_stream_join", main, n)
 
 
-def profile_begin():
-    """Start recording CUDA events around every launch (on the current stream)."""
-    global _prof
+def profile_begin(detail=False):
+    """Start recording CUDA events around every launch (on the stream it is queued on)."""
+    global _prof, _prof_detail
     _prof = {}
+    _prof_detail = [] if detail else None
+
+
+def profile_detail():
+    """-> [(entry point, (small integer arguments: sizes / strides), device ms)] in launch order; call before profile_end."""
+    torch.cuda.synchronize()
+    return [(n, a, e0.elapsed_time(e1)) for n, a, e0, e1 in (_prof_detail or [])]
 
 
 def profile_end():

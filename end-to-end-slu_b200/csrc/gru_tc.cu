@@ -17,7 +17,12 @@
 namespace {
 using namespace tc05;
 
-constexpr int TC_THREADS = 512;       // 16 warps: warp w owns TMEM lanes 32*(w%4).., batch columns (w/4)*NC ..
+constexpr int TC_THREADS = 512;       // 16 compute warps: warp w owns TMEM lanes 32*(w%4).., batch columns (w/4)*NC ..
+// The 4-row (small-batch, latency-critical) instantiations add 4 SERVICE warps: warps 16-18 issue the MMAs of gate r / z / n
+// (dW chunk 0 / 1 / 2 in the backward kernel) and warp 19 refills the TMA input ring, so no compute warp is late at the
+// per-step barrier because it was issuing; the larger tiles keep those roles on compute warps 0-2 and 3 (register budget).
+__host__ __device__ constexpr int svc_warps(int nr) { return nr == 4 ? 4 : 0; }
+__host__ __device__ constexpr int block_threads(int nr) { return TC_THREADS + 32 * svc_warps(nr); }
 constexpr uint32_t ACC_COL = 384;     // accumulators start after the 384 weight columns
 constexpr int FWD_RING = 4, BWD_RING = 3;
 // Optional phase timing (developer tool, tools/gru_phase_timing.py): when set, CTA (0,0) accumulates clock64() deltas of the
@@ -87,7 +92,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 // access costs a single IMAD.WIDE.  FULL = all NB rows of this CTA exist (stores unpredicated); the ragged last tile
 // is launched separately with FULL = false.
 template <int NB, int NR, bool STASH, bool FULL, int PASSES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(block_threads(NR), 1)
 gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                   const float* __restrict__ mask, int B, int T, int ds, int tile0, float* __restrict__ y_full,
                   float* __restrict__ y_out, float* __restrict__ stash) {
@@ -100,6 +105,11 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   constexpr int SLOT = NR * 512;                            // floats per ring slot
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int d = blockIdx.y, b0 = (tile0 + blockIdx.x) * NR;
+  constexpr bool SVC = svc_warps(NR) > 0;
+  const bool is_compute = warp < TC_THREADS / 32;
+  const int issue_w = SVC ? warp - TC_THREADS / 32 : warp;                       // 0..2: issuer of gate r / z / n
+  const bool is_issuer = issue_w >= 0 && issue_w < 3;
+  const bool is_tma = SVC ? warp == TC_THREADS / 32 + 3 : warp == 3;
   const int j = (warp & 3) * 32 + lane;              // hidden unit == TMEM lane
   const int c0 = (warp >> 2) * NC;                   // first batch column of this thread
   uint8_t* h_hi = h_tile;
@@ -118,7 +128,8 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   fence_after_sync();
   const uint32_t tmem = tmem_base;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  load_weights_to_tmem<PASSES>(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, SLU_H, 1, j, warp >> 2);
+  if (is_compute)
+    load_weights_to_tmem<PASSES>(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, SLU_H, 1, j, warp >> 2);
 
   const float bhr = b_hh[d * SLU_G3 + j], bhz = b_hh[d * SLU_G3 + 128 + j], bhn = b_hh[d * SLU_G3 + 256 + j];
   const int T2 = (T + ds - 1) / ds;
@@ -149,7 +160,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       if (mask) tma_load_1d(dst + NR * 384 + c * 128, mask + bt * 256 + d * SLU_H, 512, &in_bar[slot]);
     }
   };
-  if (warp == 3 && elect_one())
+  if (is_tma && elect_one())
     for (int s = 0; s < FWD_RING && s < T; ++s) tma_issue(s);
 
   float hprev[NC], pend[NC];
@@ -165,6 +176,23 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   long long* dbg = (g_phase_clk && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 128)) ? g_phase_clk + (tid ? 8 : 0) : nullptr;
   long long tprev_ = clock64();
   long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // register accumulators (4-row instantiations only): no memory traffic in the loop
+  if (SVC && !is_compute) {
+    // service warps: one barrier per step like everybody else, then issue -- they are back at the next barrier long
+    // before the compute warps have finished their gate math
+    for (int s = 0; s + 1 < T; ++s) {
+      __syncthreads();
+      if (is_issuer) {
+        if (elect_one()) {
+          fence_after_sync();
+          issue_product<PASSES>(tmem + ACC_COL + issue_w * NB, tmem + issue_w * 64, tmem + issue_w * 64 + 192, bdesc_hi, bdesc_lo, 0, LBO, idesc);
+          mma_commit(&bar);
+        }
+        __syncwarp();
+      } else if (s + FWD_RING < T && elect_one()) {
+        tma_issue(s + FWD_RING);          // slot s % FWD_RING has been read by every compute thread (barrier above)
+      }
+    }
+  } else
   for (int s = 0; s < T; ++s) {
     const int t = t_first + dt * s;
     float ar[NC], az[NC], an[NC];
@@ -234,7 +262,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       PHASE(4);                    // fences
       __syncthreads();
       PHASE(5);                    // barrier
-      if (warp < 3) {              // warps 0,1,2 (three different SM sub-partitions) issue gate r, z, n concurrently
+      if (!SVC && is_issuer) {     // warps 0,1,2 (three different SM sub-partitions) issue gate r, z, n concurrently
         if (elect_one()) {
           fence_after_sync();
           issue_product<PASSES>(tmem + ACC_COL + warp * NB, tmem + warp * 64, tmem + warp * 64 + 192, bdesc_hi, bdesc_lo, 0, LBO, idesc);
@@ -244,7 +272,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       }
       PHASE(6);                    // MMA issue
       // slot s % FWD_RING has been read by every thread (barrier above): refill it for step s + FWD_RING
-      if (warp == 3 && s + FWD_RING < T && elect_one()) tma_issue(s + FWD_RING);
+      if (!SVC && is_tma && s + FWD_RING < T && elect_one()) tma_issue(s + FWD_RING);
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -269,7 +297,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
 // Backward through time on tensor cores.  dh_{t-1}[k] += sum_row W_hh[row][k] * dG[row]:  M = 128 (k), K = 384 (gate rows),
 // N = NB.  W_hh^T (hi/lo) is stationary in TMEM (2 x 192 columns); dG = (dr, dz, dhn) is the shared-memory B tile.
 template <int NB, int NR, bool FULL, int PASSES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(block_threads(NR), 1)
 gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, const float* __restrict__ y_full,
                   const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds, int tile0,
                   float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ dbias) {
@@ -282,6 +310,11 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   constexpr int SLOT = NR * 896;
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int d = blockIdx.y, b0 = (tile0 + blockIdx.x) * NR;
+  constexpr bool SVC = svc_warps(NR) > 0;
+  const bool is_compute = warp < TC_THREADS / 32;
+  const int issue_w = SVC ? warp - TC_THREADS / 32 : warp;                       // 0..2: issuer of gate-row chunk 0 / 1 / 2
+  const bool is_issuer = issue_w >= 0 && issue_w < 3;
+  const bool is_tma = SVC ? warp == TC_THREADS / 32 + 3 : warp == 3;
   const int j = (warp & 3) * 32 + lane;
   const int c0 = (warp >> 2) * NC;
   uint8_t* g_hi = g_tile;
@@ -300,7 +333,8 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   const uint32_t tmem = tmem_base;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   // A[k=j][K index = row]: element (lane j, kk = g*128 + i) = W_hh[d][g*128 + i][j]  -> block stride 128*128, "row" stride 1, k stride 128
-  load_weights_to_tmem<PASSES>(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, 1, SLU_H, j, warp >> 2);
+  if (is_compute)
+    load_weights_to_tmem<PASSES>(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, 1, SLU_H, j, warp >> 2);
 
   const int T2 = (T + ds - 1) / ds;
   const int t_first = d ? 0 : T - 1, dt = d ? 1 : -1;       // walk time against the forward direction
@@ -333,7 +367,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
       if (mask) tma_load_1d(dst + NR * 768 + c * 128, mask + (bc * T + t) * 256 + d * SLU_H, 512, &in_bar[slot]);
     }
   };
-  if (warp == 3 && elect_one())
+  if (is_tma && elect_one())
     for (int s = 0; s < BWD_RING && s < T; ++s) tma_issue(s);
   const uint32_t idesc = PASSES != 1 ? idesc_bf16_f32(128, NB) : idesc_f16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
@@ -345,6 +379,22 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   for (int c = 0; c < NC; ++c) dh_direct[c] = 0.f;
   float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_hn = 0.f;    // bias gradients: sums over this thread's columns and all steps
 
+  if (SVC && !is_compute) {          // service warps (see the forward kernel)
+    for (int s = 0; s + 1 < T; ++s) {
+      __syncthreads();
+      if (is_issuer) {
+        if (elect_one()) {
+          fence_after_sync();
+          issue_product<PASSES>(tmem + ACC_COL + issue_w * NB, tmem + issue_w * 64, tmem + issue_w * 64 + 192, bdesc_hi, bdesc_lo,
+                                (uint32_t)(issue_w * 8) * 2 * LBO, LBO, idesc);
+          mma_commit(&bar);
+        }
+        __syncwarp();
+      } else if (s + BWD_RING < T && elect_one()) {
+        tma_issue(s + BWD_RING);
+      }
+    }
+  } else
   for (int s = 0; s < T; ++s) {
     const int t = t_first + dt * s;
     // Step inputs and every factor that does not depend on the recurrent term come first: the barrier wait, the
@@ -410,7 +460,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
       fence_async_smem();             // before any global store of this step is issued (see the forward kernel)
       fence_before_sync();
       __syncthreads();
-      if (warp < 3) {                 // warp g reduces gate-row chunk g (K steps 8g..8g+7) into its own accumulator
+      if (!SVC && is_issuer) {        // warp g reduces gate-row chunk g (K steps 8g..8g+7) into its own accumulator
         if (elect_one()) {
           fence_after_sync();
           issue_product<PASSES>(tmem + ACC_COL + warp * NB, tmem + warp * 64, tmem + warp * 64 + 192, bdesc_hi, bdesc_lo,
@@ -419,7 +469,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
         }
         __syncwarp();
       }
-      if (warp == 3 && s + BWD_RING < T && elect_one()) tma_issue(s + BWD_RING);   // slot fully read: refill
+      if (!SVC && is_tma && s + BWD_RING < T && elect_one()) tma_issue(s + BWD_RING);   // slot fully read: refill
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -431,7 +481,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
       off[c] += dt * 256;
     }
   }
-  if (dbias) {     // dbias[d][4][128]: sums of dr, dz, dn (-> b_ih and b_hh r/z rows), dhn (-> b_hh n rows)
+  if (dbias && is_compute) {     // dbias[d][4][128]: sums of dr, dz, dn (-> b_ih and b_hh r/z rows), dhn (-> b_hh n rows)
     float* pb = dbias + d * 512 + j;
     atomicAdd(pb, sb_r); atomicAdd(pb + 128, sb_z); atomicAdd(pb + 256, sb_n); atomicAdd(pb + 384, sb_hn);
   }
@@ -470,9 +520,9 @@ static void launch_fwd(dim3 grid, cudaStream_t st, const float* gx, const float*
   static int a2 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, P>, smem);
   static int a1 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, 1>, smem);
   (void)a3; (void)a2; (void)a1;
-  if (g_gru_mode == 0) gru_fwd_tc_kernel<16, NR, STASH, FULL, P><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
-  else if (g_gru_mode == 2) gru_fwd_tc_kernel<16, NR, STASH, FULL, 3><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
-  else gru_fwd_tc_kernel<16, NR, STASH, FULL, 1><<<grid, TC_THREADS, smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
+  if (g_gru_mode == 0) gru_fwd_tc_kernel<16, NR, STASH, FULL, P><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
+  else if (g_gru_mode == 2) gru_fwd_tc_kernel<16, NR, STASH, FULL, 3><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
+  else gru_fwd_tc_kernel<16, NR, STASH, FULL, 1><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
 }
 
 template <int NR>
@@ -511,9 +561,9 @@ static void launch_bwd(dim3 grid, cudaStream_t st, const float* dy_out, const fl
   static int a2 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, P>, smem);
   static int a1 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, 1>, smem);
   (void)a3; (void)a2; (void)a1;
-  if (g_gru_mode == 0) gru_bwd_tc_kernel<16, NR, FULL, P><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
-  else if (g_gru_mode == 2) gru_bwd_tc_kernel<16, NR, FULL, 3><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
-  else gru_bwd_tc_kernel<16, NR, FULL, 1><<<grid, TC_THREADS, smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
+  if (g_gru_mode == 0) gru_bwd_tc_kernel<16, NR, FULL, P><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
+  else if (g_gru_mode == 2) gru_bwd_tc_kernel<16, NR, FULL, 3><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
+  else gru_bwd_tc_kernel<16, NR, FULL, 1><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
 }
 
 template <int NR>
