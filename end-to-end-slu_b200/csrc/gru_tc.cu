@@ -48,6 +48,36 @@ __device__ __forceinline__ void load_weights_to_tmem(uint32_t tmem, uint32_t lan
   }
 }
 
+// Same TMEM image for ROW-MAJOR blocks (element (row j, k) at src[g*block_stride + j*128 + k], the forward kernel's W_hh):
+// a thread-per-row read would touch 32 different lines per load instruction, so each warp fetches its [32 rows x 32 k]
+// sub-block with coalesced 16-byte loads (full 128-byte row segments) and transposes it through a private
+// shared-memory buffer `tbuf` (32 x 33 floats) before the TMEM stores.
+constexpr int WT_BUF = 32 * 33;       // floats per warp
+template <int PASSES>
+__device__ __forceinline__ void load_weights_rowmajor_to_tmem(uint32_t tmem, uint32_t lane_base, const float* src, size_t block_stride,
+                                                              int warp, int lane, float* tbuf) {
+  const int q = warp & 3, part = warp >> 2;              // TMEM lane quarter (rows 32q..), K quarter (k = 32 part ..)
+  for (int g = 0; g < 3; ++g) {
+    const float* blk = src + g * block_stride + (size_t)(q * 32) * SLU_H + part * 32;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(blk + (size_t)(i * 4 + (lane >> 3)) * SLU_H + (lane & 7) * 4));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float* d = tbuf + (i * 4 + (lane >> 3)) * 33 + (lane & 7) * 4;
+      d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
+    }
+    __syncwarp();
+    float row[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) row[k] = tbuf[lane * 33 + k];
+    __syncwarp();
+    const uint32_t t_hi = tmem + lane_base + (uint32_t)(g * 64 + part * 16);
+    if (PASSES != 1) tmem_store_row_split(t_hi, t_hi + 192, row, 32);
+    else tmem_store_row_f16(t_hi, row, 32);
+  }
+}
+
 // Operand copy of one activation value into the K-major B tile: bf16 hi + lo (3-pass) or a single fp16 (1-pass).
 template <int PASSES>
 __device__ __forceinline__ void store_operand(uint8_t* hi, uint8_t* lo, float v) {
@@ -129,7 +159,8 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   const uint32_t tmem = tmem_base;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   if (is_compute)
-    load_weights_to_tmem<PASSES>(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, SLU_H, 1, j, warp >> 2);
+    load_weights_rowmajor_to_tmem<PASSES>(tmem, lane_base, w_hh + (size_t)d * SLU_G3 * SLU_H, (size_t)128 * SLU_H, warp, lane,
+                                          in_ring + FWD_RING * SLOT + warp * WT_BUF);
 
   const float bhr = b_hh[d * SLU_G3 + j], bhz = b_hh[d * SLU_G3 + 128 + j], bhn = b_hh[d * SLU_G3 + 256 + j];
   const int T2 = (T + ds - 1) / ds;
@@ -514,7 +545,7 @@ static int pick_rows(int B) { return B >= 1184 ? 16 : (B >= 592 ? 8 : 4); }
 template <int NR, bool STASH, bool FULL>
 static void launch_fwd(dim3 grid, cudaStream_t st, const float* gx, const float* w_hh, const float* b_hh, const float* mask,
                        int B, int T, int ds, int tile0, float* y_full, float* y_out, float* stash) {
-  constexpr size_t smem = (size_t)FWD_RING * NR * 512 * sizeof(float);
+  constexpr size_t smem = ((size_t)FWD_RING * NR * 512 + (size_t)(TC_THREADS / 32) * WT_BUF) * sizeof(float);   // input ring + weight transposers
   constexpr int P = 2 * NR <= 16 ? 2 : 3;            // stacked hi/lo rows fit the 16-wide MMA tile
   static int a3 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, 3>, smem);
   static int a2 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, P>, smem);

@@ -74,6 +74,13 @@ def wgrad_tc(G, g_off, ldg, M, X, x_off, ldx, N, B, T, out, o_off, s_m, s_n=1, s
     return out
 
 
+def wgrad2_tc(G0, g0_off, ldg0, m_split, G1, g1_off, ldg1, M, X, x_off, ldx, N, B, T, out, o_off, s_m, shift0=0, stream=None):
+    """Like wgrad_tc with the rows of G taken from two tensors (rows < m_split from G0, the rest from G1): slu_wgrad2_tc."""
+    _lib.call("slu_wgrad2_tc", _eptr(G0, g0_off), ldg0, m_split, _eptr(G1, g1_off), ldg1, M, _eptr(X, x_off), ldx, N, B, T, 1, shift0,
+              _eptr(out, o_off), s_m, 1, 0, _lib.stream() if stream is None else stream)
+    return out
+
+
 def linear_nt(x2, w, bias=None):
     """x2 [M,K] @ w[N,K]^T + bias -> [M,N]."""
     M, K = x2.shape
@@ -260,14 +267,11 @@ class BiGRU(torch.autograd.Function):
         fork = None
         if wg:
             dw_ih, dw_hh = zbuf[:n_ih].view(768, I), zbuf[n_ih:n_ih + n_hh].view(2, 384, H)
-            fork = _Fork(5)
+            fork = _Fork(3)
             wgrad_tc(dgx, 0, 768, 768, x, 0, I, I, B, T, dw_ih, 0, I, stream=fork.stream(0))
-            for d in range(2):          # dW_hh[d] = [dr,dz | dhn]^T . h_{t-1}  (h_{t+1} for the reverse direction)
-                sh = 1 if d else -1
-                wgrad_tc(dgx, d * 384, 768, 256, y_full, d * H, 256, H, B, T, dw_hh, d * 384 * H, H, shift0=sh,
-                         stream=fork.stream(1 + d))
-                wgrad_tc(dhn, d * H, 256, H, y_full, d * H, 256, H, B, T, dw_hh, (d * 384 + 256) * H, H, shift0=sh,
-                         stream=fork.stream(3 + d))
+            for d in range(2):          # dW_hh[d] = [dr,dz | dhn]^T . h_{t-1}  (h_{t+1} for the reverse direction), one launch
+                wgrad2_tc(dgx, d * 384, 768, 256, dhn, d * H, 256, 384, y_full, d * H, 256, H, B, T, dw_hh, d * 384 * H, H,
+                          shift0=1 if d else -1, stream=fork.stream(1 + d))
         dx = matmul_nn(dgx.view(B * T, 768), w_ih_cat).view(B, T, I) if ni[0] else None
         if wg:
             db6 = dbias.index_select(1, _bias_gather(dev))                     # (dr, dz, dn | dr, dz, dhn) per direction

@@ -111,9 +111,14 @@ int slu_gemm_tc(const float* A, long lda, const void* w_img, const float* bias, 
 int slu_presplit_bf16(const float* W, long sn, long sk, long stap, int taps, int N, int K, void* img, void* stream);
 
 /* Weight-gradient GEMM (reduction over frames) with MN-major tcgen05 operands and TMEM-resident accumulators:
- *   out[m*s_m + n*s_n + tap*s_tap] += sum_{b<B, t<T} G[(b*T+t)*ldg + m] * X[(b*T + t + shift0 + tap)*ldx + n]
+ *   out[m*s_m + n*s_n + tap*s_tap] += sum_{b<B, t<T} G[(b*T+t)][m] * X[(b*T + t + shift0 + tap)*ldx + n]
  * (frames outside [0,T) read 0; taps in {1, 5}).  Replaces the backward-weights kernels behind autograd of nn.GRU
- * (dW_ih, dW_hh with shift0 = -1/+1) and nn.Conv1d (5 taps, shift0 = -2, out in the [Cout][Cin][5] weight layout). */
+ * (dW_ih, dW_hh with shift0 = -1/+1) and nn.Conv1d (5 taps, shift0 = -2, out in the [Cout][Cin][5] weight layout).
+ * slu_wgrad2_tc takes the rows of G from two tensors: G[..][m] = G0[(b*T+t)*ldg0 + m] for m < m_split, else
+ * G1[(b*T+t)*ldg1 + m - m_split] (dW_hh = [dr, dz | dhn]^T . h in one launch).  Operands 16-byte aligned; ldg*, ldx, M, N,
+ * m_split multiples of 4. */
+int slu_wgrad2_tc(const float* G0, long ldg0, int m_split, const float* G1, long ldg1, int M, const float* X, long ldx, int N, int B,
+                  int T, int taps, int shift0, float* out, long s_m, long s_n, long s_tap, void* stream);
 int slu_wgrad_tc(const float* G, long ldg, int M, const float* X, long ldx, int N, int B, int T, int taps, int shift0, float* out,
                  long s_m, long s_n, long s_tap, void* stream);
 

@@ -286,3 +286,30 @@ def test_intent_head_fwd_bwd(pkg, B, T, slots):
     again = pkg.ops.IntentHead.apply(fc, wc, bc, y.cuda(), slots)[0]
     assert again.item() == loss.item()                                   # fixed-order batch reduction: bit-reproducible
     assert rel_err(pkg.ops.intent_head_logits(fc, wc, bc).cpu(), logits_ref.detach().float()) < 1e-5
+
+
+@pytest.mark.parametrize("B,T,shift", [(3, 37, -1), (2, 16, 1), (5, 1, -1), (4, 50, 0)])
+def test_wgrad_two_source_rows_and_frame_shift(pkg, B, T, shift):
+    """slu_wgrad2_tc as BiGRU.backward uses it: dW_hh[d] = [dgx[:, :, d*384 : d*384+256] | dhn[:, :, d*128 : +128]]^T . y shifted
+    by one frame inside each utterance (zero across utterance boundaries)."""
+    rs = np.random.RandomState(B * 10 + T)
+    dgx = torch.from_numpy(rs.standard_normal((B, T, 768)).astype(np.float32))
+    dhn = torch.from_numpy(rs.standard_normal((B, T, 256)).astype(np.float32))
+    y = torch.from_numpy(rs.standard_normal((B, T, 256)).astype(np.float32))
+    for d in range(2):
+        G = torch.cat([dgx[:, :, d * 384:d * 384 + 256], dhn[:, :, d * 128:(d + 1) * 128]], 2).double()      # [B,T,384]
+        Xs = torch.zeros(B, T, 128, dtype=torch.float64)
+        yy = y[:, :, d * 128:(d + 1) * 128].double()
+        if shift == -1:
+            Xs[:, 1:] = yy[:, :-1]
+        elif shift == 1:
+            Xs[:, :-1] = yy[:, 1:]
+        else:
+            Xs = yy
+        ref = torch.einsum("btm,btn->mn", G, Xs).float()
+        out = torch.zeros(2, 384, 128, device="cuda")
+        pkg.ops.wgrad2_tc(dgx.cuda(), d * 384, 768, 256, dhn.cuda(), d * 128, 256, 384, y.cuda(), d * 128, 256, 128, B, T, out,
+                          d * 384 * 128, 128, shift0=shift)
+        torch.cuda.synchronize()
+        assert out[1 - d].abs().max().item() == 0                        # the other direction's block is untouched
+        assert rel_err(out[d].cpu(), ref) < 1e-4, (d, rel_err(out[d].cpu(), ref))
