@@ -104,42 +104,41 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   fence_after_sync();
   const uint32_t tmem = tmem_base;
 
-  // Is row `r` of the tile at m0 a real row for tap shift `sh`, and where does it start?  (shared by loader and converters)
-  auto row_src = [&](int m0, int r, int a_t, int sh, long& row) -> bool {
-    const int m = m0 + r;
-    bool ok = m < p.M;
-    row = m;
-    if (p.taps > 1 || p.tap_pad) {
-      const int t = a_t + sh;
-      ok = ok && (p.T == 0 || (t >= 0 && t < p.T));
-      row = (long)m + sh;
-    }
-    return ok;
-  };
-
   if (warp >= ALOAD_WARP && warp < MMA_WARP) {
     // ================= activation loaders: [128 rows x 128 B] per k-block as 16-byte cp.async copies =================
     const int lt = tid - ALOAD_WARP * 32;
     constexpr int PER = BM * (BK / 4) / ALOAD_THREADS;               // 8 pieces of 16 B per thread and k-block
     const int piece = lt & 7, r0 = lt >> 3;                          // rows r0 + 16 u: a warp covers 4 full 128-byte lines
+    const bool shifted = p.taps > 1 || p.tap_pad != 0;
+    const uint32_t dst0 = smem_u32(stg_base) + (uint32_t)r0 * STG_ROW + (uint32_t)piece * 16;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int m0 = (tile / ntiles_n) * BM;
+      // per-tile row state: everything that does not depend on the k-block stays out of the inner loop
+      const float* rowp[PER];
       int a_t[PER];
+      bool okm[PER];
 #pragma unroll
-      for (int u = 0; u < PER; ++u) a_t[u] = p.T ? (m0 + r0 + 16 * u) % p.T : 0;     // frame of the row inside its utterance
+      for (int u = 0; u < PER; ++u) {
+        const int m = m0 + r0 + 16 * u;
+        okm[u] = m < p.M;
+        a_t[u] = (shifted && p.T) ? m % p.T : 0;                      // frame of the row inside its utterance
+        rowp[u] = p.A + (long)m * p.lda + piece * 4;
+      }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int slot = it % NSTG;
         if (it >= NSTG) mbar_wait(&stg_empty[slot], (uint32_t)(((it / NSTG) - 1) & 1));
-        const int tap = kb / kb_per_tap, k0 = (kb % kb_per_tap) * BK;
-        const int kvalid = min(4, max(0, p.K - k0 - piece * 4)) * 4;  // bytes of this piece inside the row (K % 4 == 0: 0 or 16)
-        uint8_t* dst = stg_base + slot * STG_SLOT + piece * 16;
+        const int tap = kb / kb_per_tap, k0 = (kb - tap * kb_per_tap) * BK;
+        const int sh = tap - p.tap_pad;
+        const long off = (long)sh * p.lda + k0;                      // same for every row of the k-block
+        const uint32_t nb = (p.K - k0 - piece * 4) > 0 ? 16u : 0u;    // K % 4 == 0: a piece is inside the row or beyond it
+        const uint32_t dst = dst0 + (uint32_t)slot * STG_SLOT;
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
-          long row;
-          const bool ok = row_src(m0, r0 + 16 * u, a_t[u], tap - p.tap_pad, row);
-          const uint32_t nbytes = ok ? (uint32_t)kvalid : 0u;
-          cp_async16(dst + (r0 + 16 * u) * STG_ROW, nbytes ? p.A + row * p.lda + k0 + piece * 4 : p.A, nbytes);
+          bool ok = okm[u];
+          if (shifted && p.T) { const int t = a_t[u] + sh; ok = ok && t >= 0 && t < p.T; }
+          const uint32_t nbytes = ok ? nb : 0u;
+          cp_async16_s(dst + (uint32_t)(16 * u) * STG_ROW, nbytes ? rowp[u] + off : p.A, nbytes);
         }
         cp_async_mbar_arrive_noinc(&stg_full[slot]);
       }

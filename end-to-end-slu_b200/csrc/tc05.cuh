@@ -65,6 +65,10 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(src_bytes) : "memory");
 }
+// same with the destination given as a 32-bit shared-memory address (hoisted out of inner loops)
+__device__ __forceinline__ void cp_async16_s(uint32_t dst_smem, const void* src_gmem, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src_gmem), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

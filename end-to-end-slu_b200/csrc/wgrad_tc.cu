@@ -41,6 +41,11 @@ struct WgradParams {
   float* out; long s_m, s_n, s_tap;     // out[m*s_m + n*s_n + tap*s_tap] += D_tap[m][n]
 };
 
+// fp32 x4 vector reduction to global memory (sm_90+): one L2 operation instead of four
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __host__ __device__ constexpr uint32_t idesc_mn(int M, int N) { return idesc_bf16_f32(M, N) | (1u << 15) | (1u << 16); }
 
 template <int MT, int NCH, int NTAPS>
@@ -91,31 +96,57 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
 
   if (warp >= CONV_WARPS && warp < MMA_WARP) {
     // ================= loaders: one tile = TF rows of G (MC columns) + XR rows of X (N columns), 16 bytes per copy =================
-    const int lt = tid - CONV_THREADS;
-    constexpr int GP = MC / 4, XP = N / 4;                 // 16-byte pieces per row
+    // A warp walks whole frame rows (frames lw, lw+4, ..), lanes walk 16-byte column pieces: one cp.async instruction
+    // moves 512 contiguous bytes.  Column state (source tensor, validity) is fixed per thread and hoisted out of the loops.
+    const int lw = warp - CONV_WARPS;
+    constexpr int GJ = MC / 128, XJ = (N / 4 + 31) / 32;     // pieces per lane and row: G (= MT), X
+    constexpr int GF = TF / LOAD_WARPS, XF = (XR + LOAD_WARPS - 1) / LOAD_WARPS;
+    const float* gcol[GJ]; long gld[GJ]; bool gok[GJ];
+#pragma unroll
+    for (int j = 0; j < GJ; ++j) {
+      const int c = (lane + 32 * j) * 4, m = m0 + c;           // block-relative / global G column of this piece
+      gok[j] = c < mv;
+      const bool first = m < p.m_split;
+      gcol[j] = first ? p.G0 + m : p.G1 + (m - p.m_split);
+      gld[j] = first ? p.ldg0 : p.ldg1;
+    }
+    const float* xcol[XJ]; bool xok[XJ];
+#pragma unroll
+    for (int j = 0; j < XJ; ++j) {
+      const int c = (lane + 32 * j) * 4;
+      xok[j] = c < nv && c < N;
+      xcol[j] = p.X + n0 + c;
+    }
+    const uint32_t stg0 = smem_u32(stg_base);
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int slot = it % NSTG;
       if (it >= NSTG) mbar_wait(&stg_empty[slot], (uint32_t)(((it / NSTG) - 1) & 1));
       const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TF;
-      uint8_t* dst = stg_base + slot * C::STG_SLOT;
-      for (int i = lt; i < TF * GP; i += LOAD_THREADS) {
-        const int f = i / GP, pc = i - f * GP;
-        const int t = t0 + f, m = m0 + pc * 4;                                   // global G column of this piece
-        const bool ok = t < p.T && pc * 4 < mv;
-        const float* src = p.G0;
-        if (ok) {
-          const long fr = (long)b * p.T + t;
-          src = m < p.m_split ? p.G0 + fr * p.ldg0 + m : p.G1 + fr * p.ldg1 + (m - p.m_split);
+      const long fr0 = (long)b * p.T;
+      const uint32_t dst = stg0 + (uint32_t)slot * C::STG_SLOT;
+#pragma unroll
+      for (int fi = 0; fi < GF; ++fi) {
+        const int f = lw + LOAD_WARPS * fi, t = t0 + f;
+        const bool okf = t < p.T;
+#pragma unroll
+        for (int j = 0; j < GJ; ++j) {
+          const bool ok = okf && gok[j];
+          cp_async16_s(dst + (uint32_t)f * C::PITCH_G + (uint32_t)(lane + 32 * j) * 16, ok ? gcol[j] + (fr0 + t) * gld[j] : p.G0, ok ? 16u : 0u);
         }
-        cp_async16(dst + f * C::PITCH_G + pc * 16, src, ok ? 16u : 0u);
       }
-      uint8_t* dstx = dst + C::STG_G;
-      for (int i = lt; i < XR * XP; i += LOAD_THREADS) {
-        const int f = i / XP, pc = i - f * XP;
-        const int t = t0 + p.shift0 + f;
-        const bool ok = t >= 0 && t < p.T && pc * 4 < nv;
-        cp_async16(dstx + f * C::PITCH_X + pc * 16, ok ? p.X + ((long)b * p.T + t) * p.ldx + n0 + pc * 4 : p.X, ok ? 16u : 0u);
+      const uint32_t dstx = dst + C::STG_G;
+#pragma unroll
+      for (int fi = 0; fi < XF; ++fi) {
+        const int f = lw + LOAD_WARPS * fi, t = t0 + p.shift0 + f;
+        const bool okf = f < XR && t >= 0 && t < p.T;
+#pragma unroll
+        for (int j = 0; j < XJ; ++j) {
+          if ((lane + 32 * j) * 4 < N && f < XR) {
+            const bool ok = okf && xok[j];
+            cp_async16_s(dstx + (uint32_t)f * C::PITCH_X + (uint32_t)(lane + 32 * j) * 16, ok ? xcol[j] + (fr0 + t) * p.ldx : p.X, ok ? 16u : 0u);
+          }
+        }
       }
       cp_async_mbar_arrive_noinc(&stg_full[slot]);
     }
@@ -196,6 +227,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     fence_after_sync();
     const int q = warp & 3, half = warp >> 2;          // two warps per TMEM lane quarter alternate 16-column groups
     float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 17);        // operand stages are idle once acc_bar fired
+    const bool vec_ok = p.s_n == 1 && (p.s_m & 3) == 0 && (p.s_tap & 3) == 0 && (n0 & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
     for (int c0 = half * 16; c0 < C::ACC; c0 += 32) {
       float v[16];
       tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
@@ -204,13 +237,27 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       for (int i = 0; i < 16; ++i) tr[lane * 17 + i] = v[i];
       __syncwarp();
       const int blk = c0 / N, mi = blk / NTAPS, tap = blk - mi * NTAPS;
-      const int nb = c0 - blk * N + (lane & 15);
-      if (nb < nv) {
-        float* dst = p.out + (long)(n0 + nb) * p.s_n + (long)tap * p.s_tap;
+      if (vec_ok) {
+        // 16-byte vector reductions (red.global.add.v4.f32): a lane adds 4 consecutive columns of one row
+        const int nb = c0 - blk * N + (lane & 3) * 4;
+        if (nb < nv) {
+          float* dst = p.out + (long)(n0 + nb) + (long)tap * p.s_tap;
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const int r = rr * 8 + (lane >> 2), m = mi * 128 + q * 32 + r;
+            const float* t4 = tr + r * 17 + (lane & 3) * 4;
+            if (m < mv) red_add_v4(dst + (long)(m0 + m) * p.s_m, t4[0], t4[1], t4[2], t4[3]);
+          }
+        }
+      } else {
+        const int nb = c0 - blk * N + (lane & 15);
+        if (nb < nv) {
+          float* dst = p.out + (long)(n0 + nb) * p.s_n + (long)tap * p.s_tap;
 #pragma unroll 4
-        for (int rr = 0; rr < 16; ++rr) {
-          const int m = mi * 128 + q * 32 + 2 * rr + (lane >> 4);
-          if (m < mv) atomicAdd(dst + (long)(m0 + m) * p.s_m, tr[(2 * rr + (lane >> 4)) * 17 + (lane & 15)]);
+          for (int rr = 0; rr < 16; ++rr) {
+            const int m = mi * 128 + q * 32 + 2 * rr + (lane >> 4);
+            if (m < mv) atomicAdd(dst + (long)(m0 + m) * p.s_m, tr[(2 * rr + (lane >> 4)) * 17 + (lane & 15)]);
+          }
         }
       }
       __syncwarp();
@@ -239,7 +286,7 @@ int launch(const WgradParams& p, cudaStream_t st) {
   const int m_groups = (p.m_valid + C::MC - 1) / C::MC, n_groups = (p.n_valid + C::N - 1) / C::N;
   const long n_tiles = (long)p.B * p.tiles_per_utt;
   int gx = sm_count_w() / (m_groups * n_groups);        // CTAs per output block: fill the SMs ...
-  if (gx > n_tiles / 8) gx = (int)(n_tiles / 8);        // ... but give every CTA >= 8 frame tiles per atomic flush
+  if (gx > n_tiles / 24) gx = (int)(n_tiles / 24);      // ... but give every CTA >= 24 frame tiles per atomic flush
   if (gx < 1) gx = 1;
   wgrad_tc_kernel<MT, NCH, NTAPS><<<dim3(gx, m_groups, n_groups), THREADS, C::TOTAL, st>>>(p);
   return (int)cudaGetLastError();
