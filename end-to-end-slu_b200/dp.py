@@ -30,16 +30,21 @@ def _flatten(grads):
     return torch.cat(parts)
 
 
-def _unflatten(flat, grads, scale):
+def _unflatten(flat, grads):
+    """Write the (already averaged) bucket back: one multi-tensor copy for the fp32 gradients."""
     off = 0
+    dst, src = [], []
     for g in grads:
         n = g.numel()
         if g.dtype == torch.float64:
-            g.copy_((flat[off:off + n].double() + flat[off + n:off + 2 * n].double()).view_as(g) * scale)
+            g.copy_((flat[off:off + n].double() + flat[off + n:off + 2 * n].double()).view_as(g))
             off += 2 * n
         else:
-            g.copy_(flat[off:off + n].view_as(g)).mul_(scale)
+            dst.append(g)
+            src.append(flat[off:off + n].view_as(g))
             off += n
+    if dst:
+        torch._foreach_copy_(dst, src)
 
 
 def allreduce_grads(params, group=None):
@@ -50,8 +55,12 @@ def allreduce_grads(params, group=None):
     if not grads:
         return 0
     flat = _flatten(grads)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    _unflatten(flat, grads, 1.0 / dist.get_world_size(group))
+    if flat.is_cuda:                                   # NCCL averages inside the collective
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / dist.get_world_size(group))
+    _unflatten(flat, grads)
     stats["allreduce_calls"] += 1
     stats["bucket_bytes"] = flat.numel() * 4
     return stats["bucket_bytes"]
