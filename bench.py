@@ -25,6 +25,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 T_SAMPLES = 64000            # 4 s @ 16 kHz
+WORKLOAD = ("experiments/unfreeze_all_layers.cfg SLU train step (all layers unfrozen, dropout 0.5, Adam), "
+            "4 s @16 kHz synthetic utterances")
 GRU_T = (400, 200, 100, 50, 25)
 GRU_I = (60, 256, 256, 256, 256)
 
@@ -95,6 +97,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Everything libraries print to fd 1 (NCCL's version banner, warnings) goes to stderr; the one JSON line is written to the
+    real stdout by _emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (oracle port with the
     reference's execution structure incl. its 80x conv loop), all host threads, bounded sample."""
@@ -105,18 +125,19 @@ def run_reference(args, rank, world):
     cores = host_threads()
     torch.set_num_threads(cores)
     B = args.ref_batch
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)      # a step = one train step on a bounded sample (ref_batch utterances)
     sec = ref_port.train_steps(R.synthetic_params(seed=0), B, T_SAMPLES, steps, warmup, device="cpu", loop80=True)
     val = B / sec
     line = {"impl": "reference", "metric": "utterances_per_sec_train_step", "value": val, "unit": "utt/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "unfreeze_all_layers SLU train step, 4 s @16 kHz", "batch_per_step": B},
+            "config": {"workload": WORKLOAD, "samples_per_utt": T_SAMPLES, "batch_per_step": B,
+                       "note": "bounded sample of the workload: the same train step on batch_per_step utterances per step"},
             "cpu_baseline": {"value": val, "unit": "utt/s", "cores": cores, "kind": "port",
                              "sample": "%d train steps of batch %d x 4 s (reference execution structure incl. 80x conv loop), "
                                        "torch CPU %d threads" % (steps, B, cores)},
             "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def main():
@@ -132,6 +153,7 @@ def main():
     ap.add_argument("--ref-gpu", action="store_true", help="also time the reference-structured port on this GPU (cuDNN)")
     ap.add_argument("--eval-dropout", action="store_true", help="disable dropout (debug)")
     args = ap.parse_args()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -291,8 +313,7 @@ def main():
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tensor-core contractions as bf16 hi/lo 3-pass split, fp32 accumulate)",
                 "data": "synthetic", "impl": "ours",
-                "config": {"workload": "experiments/unfreeze_all_layers.cfg SLU train step (all layers unfrozen, dropout 0.5), "
-                                       "4 s @16 kHz synthetic utterances", "batch_per_gpu": B, "global_batch": B * world,
+                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
                            "samples_per_utt": T_SAMPLES, "parallelism": "dp%d" % world,
                            "l2": "inputs rotate over 4 batches (262 MB) > 126 MB L2; activations ~1 GB/step"},
                 "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": B * T_SAMPLES * 4 + B * 3 * 8,
@@ -302,7 +323,7 @@ def main():
                 "gpu_launches": launches, "kernels": kern, "roofline": roofline, "cpu_baseline": cpu_base,
                 "clocks": clk.summary(), "allreduce": dict(pkg.dp.stats)}
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
