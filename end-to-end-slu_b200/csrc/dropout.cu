@@ -63,3 +63,53 @@ extern "C" int slu_dropout_mask(float* mask, long n, float p, unsigned long long
   SLU_CHECK_LAUNCH();
   return 0;
 }
+
+// ---- LeakyReLU backward + bias gradient of the conv blocks (autograd of models.py:211 LeakyReLU and the Conv1d bias) ------------
+//   dpre[r][c] = y[r][c] > 0 ? gy[r][c] : slope * gy[r][c];     db[c] += sum_r dpre[r][c]
+// One pass over the two inputs (HBM-bound: 12 B per element) instead of compare / multiply / select / reduce launches.
+// Rows are C floats (C % 4 == 0, C <= 1024); a block is (C/4) x RB threads, so every thread keeps the same 4 columns.
+namespace {
+
+__global__ void __launch_bounds__(256) leaky_bwd_bias_kernel(const float* __restrict__ y, const float* __restrict__ gy, float slope,
+                                                             float* __restrict__ dpre, float* __restrict__ db, long R, int C4, int RB) {
+  extern __shared__ float4 part[];                       // [RB][C4] block partials
+  const int tid = threadIdx.x;
+  const int cq = tid % C4, rl = tid / C4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < RB) {
+    for (long r = (long)blockIdx.x * RB + rl; r < R; r += (long)gridDim.x * RB) {
+      const long i = r * C4 + cq;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(y) + i), g = __ldg(reinterpret_cast<const float4*>(gy) + i);
+      float4 d;
+      d.x = a.x > 0.f ? g.x : g.x * slope; d.y = a.y > 0.f ? g.y : g.y * slope;
+      d.z = a.z > 0.f ? g.z : g.z * slope; d.w = a.w > 0.f ? g.w : g.w * slope;
+      reinterpret_cast<float4*>(dpre)[i] = d;
+      acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+    }
+    part[rl * C4 + cq] = acc;
+  }
+  __syncthreads();
+  if (tid < C4) {
+    float4 s = part[tid];
+    for (int k = 1; k < RB; ++k) {
+      const float4 v = part[k * C4 + tid];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    atomicAdd(db + 4 * tid, s.x); atomicAdd(db + 4 * tid + 1, s.y); atomicAdd(db + 4 * tid + 2, s.z); atomicAdd(db + 4 * tid + 3, s.w);
+  }
+}
+
+}  // namespace
+
+extern "C" int slu_leaky_bwd_bias(const float* y, const float* gy, float slope, float* dpre, float* db, long R, int C, void* stream) {
+  if (R <= 0) return 0;
+  if (C <= 0 || (C & 3) || C > 1024) return (int)cudaErrorInvalidValue;
+  if (((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(dpre)) & 15) != 0)
+    return (int)cudaErrorInvalidValue;
+  const int C4 = C / 4, RB = 256 / C4;
+  long blocks = (R + RB - 1) / RB;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  leaky_bwd_bias_kernel<<<(unsigned)blocks, 256, (size_t)RB * C4 * sizeof(float4), (cudaStream_t)stream>>>(y, gy, slope, dpre, db, R, C4, RB);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}

@@ -364,14 +364,14 @@ __global__ void presplit_kernel(const float* __restrict__ W, long sn, long sk, l
 
 }  // namespace
 
-// like slu_presplit_bf16, with elements whose in-row offset k*sk + tap*stap reaches row_len read as 0 (used by sinc_tc.cu)
-int slu_presplit_rows(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream) {
+// like slu_presplit_bf16, with elements whose in-row offset k*sk + tap*stap reaches row_len read as 0 (sinc_tc.cu's TMA-fed filter bank)
+int slu_presplit_rows_cm(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream) {
   if (taps <= 0 || N <= 0 || K <= 0) return (int)cudaErrorInvalidValue;
   const int Kp = (K + 31) / 32 * 32;
   const size_t total = (size_t)taps * N * Kp;
   int grid = (int)((total + 255) / 256);
   if (grid > 1184) grid = 1184;
-  presplit_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(W, sn, sk, stap, taps, N, K, Kp, row_len, (__nv_bfloat16*)img);
+  presplit_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(W, sn, sk, stap, taps, N, K, Kp, row_len, (__nv_bfloat16*)img);
   return (int)cudaGetLastError();
 }
 

@@ -26,7 +26,6 @@ constexpr uint32_t LBO_X = XROWS * 16 + 16;     // 2192: chunk-column stride of 
 constexpr uint32_t X_PART = KC * LBO_X;         // 21920 B (one of hi / lo)
 constexpr uint32_t LBO_W = SLU_NFILT * 16 + 16; // 1296: chunk-column stride of one tap's filter tile [80 n][80 k]
 constexpr uint32_t W_PART = KC * LBO_W;         // 12960 B
-constexpr int WKP = 96;                         // row pitch (elements) of the pre-split bank image
 
 // Instruction descriptor with selectable operand majors (bit 15: A is MN-major, bit 16: B is MN-major).
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
@@ -71,19 +70,27 @@ __device__ __forceinline__ void stage_wave_image(uint8_t* hi, uint8_t* lo, const
 // forward
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t FWD_SMEM = 2 * X_PART + 2 * 2 * W_PART;      // waveform image (hi, lo) + 2-slot ring of filter taps
+constexpr int WKC = 96 / 8;                                     // k-chunks per tap in the pre-split bank image (Kp = 96)
 
+// Filter taps arrive through a 2-slot TMA ring (the pre-split bank image is k-chunk-major: one bulk copy per 8-sample chunk
+// of all 80 filters), issued by one elected thread of warp 1 from the very start of the CTA -- they land while all warps
+// stage the waveform image; warp 0 issues the MMAs.  No block-wide barrier inside the tap loop.
 __global__ void __launch_bounds__(THREADS, 2)
 sincconv_fwd_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wimg, int T, int L0, int L1,
                        float* __restrict__ out, uint8_t* __restrict__ route) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t empty_bar[2], acc_bar;
+  __shared__ uint64_t full_bar[2], empty_bar[2], acc_bar;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
   const int b = blockIdx.y, t0 = blockIdx.x * TF;
   uint8_t* x_hi = smem; uint8_t* x_lo = smem + X_PART;
   uint8_t* w_ring = smem + 2 * X_PART;
 
-  if (tid == 0) { mbar_init(&empty_bar[0], 1); mbar_init(&empty_bar[1], 1); mbar_init(&acc_bar, 1); fence_mbar_init(); }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    fence_mbar_init();
+  }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_base, 128);
   fence_before_sync();
@@ -92,30 +99,44 @@ sincconv_fwd_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restr
   const uint32_t tmem = tmem_base;
   const uint32_t idesc = idesc_bf16(128, SLU_NFILT, false, false);
 
-  stage_wave_image(x_hi, x_lo, x + (size_t)b * T, t0, T, tid);
+  // tap `tap` of the bank -> ring slot tap & 1: 10 chunks x (hi, lo), 1280 B each.  Tap 5 has a single non-zero sample
+  // (k = 0): one K=16 step = chunks 0 and 1 (chunk 1 is all zero in the image).
+  auto tma_tap = [&](int tap) {
+    const int slot = tap & 1, nch = tap == 5 ? 2 : KC;
+    uint8_t* w_hi = w_ring + slot * 2 * W_PART;
+    mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(2 * nch * SLU_NFILT * 16));
+    for (int part = 0; part < 2; ++part)
+      for (int kc = 0; kc < nch; ++kc) {
+        const size_t e = ((((size_t)part * 6 + tap) * WKC + kc) * SLU_NFILT) * 8;
+        tma_load_1d(w_hi + part * W_PART + kc * LBO_W, wimg + e, SLU_NFILT * 16, &full_bar[slot]);
+      }
+  };
+  if (warp == 1 && elect_one()) { tma_tap(0); tma_tap(1); }
+  __syncwarp();
 
-  const size_t lo_off = (size_t)6 * SLU_NFILT * WKP;              // image = [hi | lo][tap][n][WKP]
-  for (int tap = 0; tap < 6; ++tap) {
-    const int slot = tap & 1;
-    if (tap >= 2) mbar_wait(&empty_bar[slot], (uint32_t)(((tap >> 1) - 1) & 1));
-    uint8_t* w_hi = w_ring + slot * 2 * W_PART; uint8_t* w_lo = w_hi + W_PART;
-    for (int task = tid; task < SLU_NFILT * KC; task += THREADS) {     // plain 16-byte copies of the pre-split bank
-      const int n = task / KC, kc = task - n * KC;
-      const size_t e = ((size_t)tap * SLU_NFILT + n) * WKP + kc * 8;
-      const uint32_t off = (uint32_t)kc * LBO_W + (uint32_t)n * 16;
-      *reinterpret_cast<uint4*>(w_hi + off) = __ldg(reinterpret_cast<const uint4*>(wimg + e));
-      *reinterpret_cast<uint4*>(w_lo + off) = __ldg(reinterpret_cast<const uint4*>(wimg + lo_off + e));
+  stage_wave_image(x_hi, x_lo, x + (size_t)b * T, t0, T, tid);
+  fence_async_smem();
+  __syncthreads();
+
+  if (warp == 1) {
+    for (int tap = 2; tap < 6; ++tap) {
+      mbar_wait(&empty_bar[tap & 1], (uint32_t)(((tap >> 1) - 1) & 1));      // the MMAs of tap - 2 have read the slot
+      if (elect_one()) tma_tap(tap);
+      __syncwarp();
     }
-    fence_async_smem();
-    __syncthreads();
-    if (warp == 0) {
+  } else if (warp == 0) {
+    for (int tap = 0; tap < 6; ++tap) {
+      const int slot = tap & 1;
+      mbar_wait(&full_bar[slot], (uint32_t)((tap >> 1) & 1));
+      fence_after_sync();
       if (elect_one()) {
-        fence_after_sync();
+        uint8_t* w_hi = w_ring + slot * 2 * W_PART; uint8_t* w_lo = w_hi + W_PART;
         // rows tap .. tap+127 of the staged image: start address + 16 B per row
         const uint64_t ah0 = smem_desc(smem_u32(x_hi) + tap * 16, LBO_X, 128), al0 = smem_desc(smem_u32(x_lo) + tap * 16, LBO_X, 128);
         const uint64_t bh0 = smem_desc(smem_u32(w_hi), LBO_W, 128), bl0 = smem_desc(smem_u32(w_lo), LBO_W, 128);
-#pragma unroll
-        for (int kk = 0; kk < SLU_STRIDE / 16; ++kk) {
+        const int nk = tap == 5 ? 1 : SLU_STRIDE / 16;
+#pragma unroll 1
+        for (int kk = 0; kk < nk; ++kk) {
           const uint64_t ah = desc_advance(ah0, kk * 2 * LBO_X), al = desc_advance(al0, kk * 2 * LBO_X);
           const uint64_t bh = desc_advance(bh0, kk * 2 * LBO_W), bl = desc_advance(bl0, kk * 2 * LBO_W);
           mma_bf16(tmem, ah, bh, idesc, (tap | kk) ? 1u : 0u);
@@ -304,14 +325,14 @@ sincconv_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ gy
 
 }  // namespace
 
-int slu_presplit_rows(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream);
+int slu_presplit_rows_cm(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream);
 
 // Forward: out[B][L1][80] = maxpool2(|conv1d(x, W, stride 80, pad 200)|), route bits for the backward pass.
 // `img` = scratch for the pre-split bank: 2*6*80*96 bf16 values.
 extern "C" int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T, float* out, uint8_t* route, void* img, void* stream) {
   if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
   const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
-  int e = slu_presplit_rows(W, SLU_NTAPS, 1, SLU_STRIDE, 6, SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // bank[c][80a + k], 0 beyond tap 400
+  int e = slu_presplit_rows_cm(W, SLU_NTAPS, 1, SLU_STRIDE, 6, SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // bank[c][80a + k], 0 beyond tap 400
   if (e) return e;
   static int attr = slu_set_smem((const void*)sincconv_fwd_tc_kernel, FWD_SMEM);
   if (attr) return attr;

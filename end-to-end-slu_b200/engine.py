@@ -77,19 +77,53 @@ def downsample_factor(down):
     raise NotImplementedError("slu_b200 CUDA path: Downsample(%s, %d) is not supported" % (down.method, down.factor))
 
 
-def _drop_mask(shape, p, training, device):
+def _drop_mask(shape, p, training, device, stream=None):
     if not training or p <= 0.0:
         return None
     mask = torch.empty(shape, device=device, dtype=torch.float32)
     seed = int(torch.randint(0, 2 ** 62, (1,)).item())        # host draw from torch's CPU generator: follows torch.manual_seed
-    _lib.call("slu_dropout_mask", _lib.ptr(mask), mask.numel(), float(p), seed, _lib.stream())
+    _lib.call("slu_dropout_mask", _lib.ptr(mask), mask.numel(), float(p), seed, _lib.stream() if stream is None else stream)
     return mask
 
 
-def _run_rnns(out, rnns, training):
-    for gru, p, ds in rnns:
+_default_drop_mask = _drop_mask
+
+
+def _premask(stacks, B, T, training, device):
+    """Keep-masks of several GRU stacks ahead of time: the tensors are allocated on the current stream, the generator kernels
+    run on a library side stream (they overlap the conv blocks) and `join()` orders them before the first GRU.
+    Returns ([masks per stack], join).  Same draw order as layer-by-layer generation."""
+    shapes = []
+    for rnns in stacks:
+        for _, p, ds in rnns:
+            shapes.append((B, T, 256))
+            T = (T + ds - 1) // ds
+    flat = [(gru, p, ds) for rnns in stacks for (gru, p, ds) in rnns]
+    if not training or _drop_mask is not _default_drop_mask:      # nothing to do / a test supplies the masks
+        masks = [_drop_mask(shp, p, training, device) for shp, (_, p, _) in zip(shapes, flat)]
+        join = None
+    else:
+        bufs = [torch.empty(shp, device=device, dtype=torch.float32) if p > 0.0 else None for shp, (_, p, _) in zip(shapes, flat)]
+        seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0.0 else 0 for (_, p, _) in flat]
+        main, side = _lib.fork(1)
+        for buf, seed, (_, p, _) in zip(bufs, seeds, flat):
+            if buf is not None:
+                _lib.call("slu_dropout_mask", _lib.ptr(buf), buf.numel(), float(p), seed, side[0])
+        masks, join = bufs, (lambda: _lib.join(main, 1))
+    out, i = [], 0
+    for rnns in stacks:
+        out.append(masks[i:i + len(rnns)])
+        i += len(rnns)
+    return out, join
+
+
+def _run_rnns(out, rnns, training, masks=None):
+    for i, (gru, p, ds) in enumerate(rnns):
         B, T, _ = out.shape
-        out = ops.bigru(out, gru, _drop_mask((B, T, 256), p, training, out.device), ds)
+        mask = masks[i] if masks is not None else _drop_mask((B, T, 256), p, training, out.device)
+        if mask is not None and tuple(mask.shape) != (B, T, 256):
+            raise RuntimeError("slu_b200: pre-generated dropout mask does not match the layer input")
+        out = ops.bigru(out, gru, mask, ds)
     return out
 
 
@@ -98,13 +132,21 @@ def phoneme_features(pm, x):
     plan = pm._plan
     _require(plan.sinc is not None, "use_sincnet must be True")
     out = ops.SincFrontend.apply(x, plan.sinc.filt_b1, plan.sinc.filt_band)      # [B, L1, 80] (LeakyReLU is identity on >=0)
+    # masks of the phoneme AND word stacks are generated now, next to the conv blocks
+    (m_phone, m_word), join = _premask([plan.phone, plan.word], out.shape[0], out.shape[1], pm.training, out.device)
     for conv, slope in plan.convs:
         out = ops.conv_block(out, conv.weight, conv.bias, slope)
-    return _run_rnns(out, plan.phone, pm.training)
+    if join is not None:
+        join()
+    out = _run_rnns(out, plan.phone, pm.training, m_phone)
+    pm._word_masks = (m_word, out.shape[0], out.shape[1]) if pm.training else None
+    return out
 
 
 def word_features(pm, ph):
-    return _run_rnns(ph, pm._plan.word, pm.training)
+    pending, pm._word_masks = getattr(pm, "_word_masks", None), None
+    masks = pending[0] if pending is not None and pm.training and pending[1:] == (ph.shape[0], ph.shape[1]) else None
+    return _run_rnns(ph, pm._plan.word, pm.training, masks)
 
 
 def compute_features(pm, x):

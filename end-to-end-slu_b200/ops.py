@@ -126,18 +126,27 @@ class ConvBlock(torch.autograd.Function):
         x, w, out = ctx.saved_tensors
         B, T, Cin = x.shape
         Cout, _, k = w.shape
-        dpre = torch.where(out > 0, gy, gy * ctx.slope).contiguous()
-        dx = dw = db = fork = None
+        gy = _f32(gy)
+        if Cout % 4 == 0:           # LeakyReLU backward + bias gradient in one pass
+            dpre = torch.empty_like(out)
+            zb = torch.zeros(Cout + Cout * Cin * k, device=x.device, dtype=torch.float32)     # db | dW, one fill
+            db = zb[:Cout]
+            _lib.call("slu_leaky_bwd_bias", _lib.ptr(out), _lib.ptr(gy), float(ctx.slope), _lib.ptr(dpre), _lib.ptr(db), B * T, Cout,
+                      _lib.stream())
+        else:
+            dpre = torch.where(out > 0, gy, gy * ctx.slope).contiguous()
+            db = dpre.sum((0, 1))
+        dx = dw = fork = None
         if ctx.needs_input_grad[1]:      # all k taps in one launch, written straight into the [Cout][Cin][k] weight layout
-            dw = torch.zeros(Cout, Cin, k, device=x.device, dtype=torch.float32)
+            dw = zb[Cout:].view(Cout, Cin, k) if Cout % 4 == 0 else torch.zeros(Cout, Cin, k, device=x.device, dtype=torch.float32)
             fork = _Fork(1)
             wgrad_tc(dpre, 0, Cout, Cout, x, 0, Cin, Cin, B, T, dw, 0, Cin * k, k, 1, taps=k, shift0=-(k // 2), stream=fork.stream(0))
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, Cin, device=x.device, dtype=torch.float32)
             # dX[b,t,ci] = sum_d sum_co dpre[b,t-(d-k//2),co] W[co,ci,d]; tap' = k-1-d walks the kernel backwards
             gemm_tc(dpre, Cout, presplit(w, k - 1, k, Cin * k, -1, k, Cin, Cout), B * T, Cin, Cout, dx, taps=k, tap_pad=k // 2, T=T)
-        if ctx.needs_input_grad[2]:
-            db = dpre.sum((0, 1))
+        if not ctx.needs_input_grad[2]:
+            db = None
         if fork is not None:
             fork.join()
         return dx, dw, db, None

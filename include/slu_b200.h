@@ -99,6 +99,10 @@ int slu_stream_join(void* main_stream, int n);
  * Philox4x32-10 keyed by `seed` (counter = i/4).  `mask` must be 16-byte aligned.  The GRU kernels multiply by it. */
 int slu_dropout_mask(float* mask, long n, float p, unsigned long long seed, void* stream);
 
+/* Backward of the conv blocks' LeakyReLU plus the Conv1d bias gradient in one pass (autograd of models.py:200/211):
+ *   dpre[r][c] = y[r][c] > 0 ? gy[r][c] : slope*gy[r][c];  db[c] += sum_r dpre[r][c]     (R rows of C floats, C % 4 == 0) */
+int slu_leaky_bwd_bias(const float* y, const float* gy, float slope, float* dpre, float* db, long R, int C, void* stream);
+
 /* Dense "tap-GEMM" on tcgen05 (fp32 in/out, 3-pass bf16 split, fp32 accumulate in TMEM) -- replaces the cuBLAS / cuDNN
  * calls behind nn.GRU's input projection (models.py:232/262/686), nn.Conv1d (models.py:200) and their input gradients:
  *   C[m][n] = sum_tap sum_k A[(m + tap - tap_pad)*lda + k] * W(n, tap, k) (+ bias[n]) (LeakyReLU(slope) if act == 1)
