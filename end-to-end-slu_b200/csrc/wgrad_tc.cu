@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       uint8_t* a_lo = a_hi + C::A_PART;
       uint8_t* b_hi = a_hi + 2 * C::A_PART;
       uint8_t* b_lo = b_hi + C::B_PART;
-#pragma unroll 2
+#pragma unroll 4
       for (int i = tid; i < GT; i += CONV_THREADS) {
         const int c = i / TF, f = i - c * TF;
         const float4 x0 = *reinterpret_cast<const float4*>(src + f * C::PITCH_G + c * 32);
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
         *reinterpret_cast<uint4*>(a_lo + off) = l;
       }
       const uint8_t* srcx = src + C::STG_G;
-#pragma unroll 2
+#pragma unroll 4
       for (int i = tid; i < XT; i += CONV_THREADS) {
         const int c = i / XR, f = i - c * XR;
         const float4 x0 = *reinterpret_cast<const float4*>(srcx + f * C::PITCH_X + c * 32);
@@ -286,7 +286,7 @@ int launch(const WgradParams& p, cudaStream_t st) {
   const int m_groups = (p.m_valid + C::MC - 1) / C::MC, n_groups = (p.n_valid + C::N - 1) / C::N;
   const long n_tiles = (long)p.B * p.tiles_per_utt;
   int gx = sm_count_w() / (m_groups * n_groups);        // CTAs per output block: fill the SMs ...
-  if (gx > n_tiles / 24) gx = (int)(n_tiles / 24);      // ... but give every CTA >= 24 frame tiles per atomic flush
+  if (gx > n_tiles / 8) gx = (int)(n_tiles / 8);        // ... but give every CTA >= 8 frame tiles per (vector-atomic) flush
   if (gx < 1) gx = 1;
   wgrad_tc_kernel<MT, NCH, NTAPS><<<dim3(gx, m_groups, n_groups), THREADS, C::TOTAL, st>>>(p);
   return (int)cudaGetLastError();

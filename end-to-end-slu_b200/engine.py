@@ -104,7 +104,7 @@ def _premask(stacks, B, T, training, device):
         join = None
     else:
         bufs = [torch.empty(shp, device=device, dtype=torch.float32) if p > 0.0 else None for shp, (_, p, _) in zip(shapes, flat)]
-        seeds = [int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0.0 else 0 for (_, p, _) in flat]
+        seeds = torch.randint(0, 2 ** 62, (len(flat),)).tolist()      # one host draw for all layers (torch's CPU generator)
         main, side = _lib.fork(1)
         for buf, seed, (_, p, _) in zip(bufs, seeds, flat):
             if buf is not None:
