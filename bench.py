@@ -266,6 +266,7 @@ def main():
         flops = sum(2 * 2 * t * 384 * 128 * B for t in GRU_T)
         sec = kern[name]["ms_per_step"] * 1e-3
         ach = flops / sec / 1e12
+        nr_rows = 16 if B >= 1184 else (8 if B >= 592 else 4)         # batch rows per CTA (csrc/gru_tc.cu pick_rows)
         traffic = None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture (layer 0, B=256)
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
@@ -275,10 +276,12 @@ def main():
         roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s",
                     "frac": ach / tf_sust, "traffic": traffic, "peak_source": how + " bf16 sustained (kernel timed inside a step)",
                     "traffic_note": "bytes of the layer-0 launch (T=400, the largest of the 5); its algorithmic bytes are 996 MB",
-                    "executed_tflops": 3 * ach if pkg.ops.GRU_IMPL == "tc" else ach,
+                    "executed_tflops": (32 // nr_rows if nr_rows < 16 else 3) * ach if pkg.ops.GRU_IMPL == "tc" else ach,
                     "note": "persistent-GRU forward, 5 launches/step summed; algorithmic flops = 2 dirs * T_l * 2*384*128 * B over the "
-                            "5 layers (h.W_hh only; the bf16 hi/lo 3-pass split executes 3x that on the tensor core). The recurrence is "
-                            "latency-bound (128 CTAs of 4 batch rows at B=256): see DESIGN.md section 4"}
+                            "5 layers (h.W_hh only).  The N=16 MMA tile carries %d batch rows, hi and lo stacked along N, times the W_hi / "
+                            "W_lo passes: the tensor core executes %dx the algorithmic flops.  The recurrence is a dependency chain "
+                            "(%d CTAs of %d batch rows): see DESIGN.md section 4" % (nr_rows, 32 // nr_rows if nr_rows < 16 else 3,
+                                                                                    2 * ((B + nr_rows - 1) // nr_rows), nr_rows)}
     sinc_names = [k for k in prof if k.startswith("slu_sincconv_fwd")]
     if sinc_names:
         name = sinc_names[0]
