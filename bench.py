@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=8)
+    ap.add_argument("--background-prefetch", action="store_true", help="stage batch i+1 in a helper thread instead of the consumer's")
     ap.add_argument("--launch-detail", action="store_true", help="print every launch of one step with its sizes and device time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-gpu", action="store_true", help="also time the reference-structured port on this GPU (cuDNN)")
@@ -207,7 +208,7 @@ def main():
         ev0.record()
         if host == "prefetch":                                        # the Trainer loop over a DevicePrefetcher-wrapped loader
             batches = ((xs_host[i % NB], ys_host[i % NB]) for i in range(k))
-            for x, y in pkg.loader.DevicePrefetcher(batches):         # H2D of batch i+1 on a copy stream under step i
+            for x, y in pkg.loader.DevicePrefetcher(batches, background=args.background_prefetch):   # H2D of batch i+1 under step i
                 loss, _ = step(x, y)
                 loss.item()                                           # D2H read of the step's result, every step
         for i in range(k if host != "prefetch" else 0):

@@ -117,13 +117,15 @@ def _premask(stacks, B, T, training, device):
     return out, join
 
 
-def _run_rnns(out, rnns, training, masks=None):
+def _run_rnns(out, rnns, training, masks=None, join=None):
     for i, (gru, p, ds) in enumerate(rnns):
         B, T, _ = out.shape
         mask = masks[i] if masks is not None else _drop_mask((B, T, 256), p, training, out.device)
         if mask is not None and tuple(mask.shape) != (B, T, 256):
             raise RuntimeError("slu_b200: pre-generated dropout mask does not match the layer input")
-        out = ops.bigru(out, gru, mask, ds)
+        out = ops.bigru(out, gru, mask, ds, join if i == 0 else None)     # masks are joined right before the first recurrence
+    if join is not None and not rnns:
+        join()
     return out
 
 
@@ -132,13 +134,12 @@ def phoneme_features(pm, x):
     plan = pm._plan
     _require(plan.sinc is not None, "use_sincnet must be True")
     out = ops.SincFrontend.apply(x, plan.sinc.filt_b1, plan.sinc.filt_band)      # [B, L1, 80] (LeakyReLU is identity on >=0)
-    # masks of the phoneme AND word stacks are generated now, next to the conv blocks
-    (m_phone, m_word), join = _premask([plan.phone, plan.word], out.shape[0], out.shape[1], pm.training, out.device)
     for conv, slope in plan.convs:
         out = ops.conv_block(out, conv.weight, conv.bias, slope)
-    if join is not None:
-        join()
-    out = _run_rnns(out, plan.phone, pm.training, m_phone)
+    # Masks of the phoneme AND word stacks: queued on a side stream once the front end is in flight (the host prepares them
+    # while the GPU is busy), they run next to the first x-projection GEMM and are joined right before the first recurrence.
+    (m_phone, m_word), join = _premask([plan.phone, plan.word], out.shape[0], out.shape[1], pm.training, out.device)
+    out = _run_rnns(out, plan.phone, pm.training, m_phone, join)
     pm._word_masks = (m_word, out.shape[0], out.shape[1]) if pm.training else None
     return out
 

@@ -231,7 +231,7 @@ class BiGRU(torch.autograd.Function):
     x [B,T,I] -> [B, ceil(T/ds), 256]."""
 
     @staticmethod
-    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, mask, ds, packed=None):
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, mask, ds, packed=None, before_recurrence=None):
         x = _f32(x)
         B, T, I = x.shape
         dev = x.device
@@ -248,6 +248,8 @@ class BiGRU(torch.autograd.Function):
         y_out = torch.empty(B, T2, 256, device=dev, dtype=torch.float32) if (ds != 1 or mask is not None) else y_full
         need = any(ctx.needs_input_grad[:9])
         stash = torch.empty(B, T, 1024, device=dev, dtype=torch.float32) if need else None
+        if before_recurrence is not None:       # e.g. join the side stream that wrote the dropout masks (the x-projection is queued)
+            before_recurrence()
         _lib.call("slu_gru_fwd_" + GRU_IMPL, _lib.ptr(gx), _lib.ptr(w_hh_cat), _lib.ptr(b_hh_cat), _lib.ptr(mask), B, T, ds,
                   _lib.ptr(y_full), _lib.ptr(y_out), _lib.ptr(stash), _lib.stream())
         if need:
@@ -290,7 +292,7 @@ class BiGRU(torch.autograd.Function):
                 grads[4 * d + 2] = db6[d, :3].reshape(384)                     # b_ih
                 grads[4 * d + 3] = db6[d, 3:].reshape(384)                     # b_hh
             fork.join()
-        return (dx, *grads, None, None, None)
+        return (dx, *grads, None, None, None, None)
 
 
 _PACK_ORDER = ("weight_ih_l0", "weight_ih_l0_reverse", "weight_hh_l0", "weight_hh_l0_reverse",
@@ -330,11 +332,11 @@ def packed_params(gru):
     return gru._slu_views
 
 
-def bigru(x, gru, mask=None, ds=1):
+def bigru(x, gru, mask=None, ds=1, before_recurrence=None):
     """Run BiGRU on the parameters of an nn.GRU holder module."""
     return BiGRU.apply(x, gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0,
                        gru.weight_ih_l0_reverse, gru.weight_hh_l0_reverse, gru.bias_ih_l0_reverse,
-                       gru.bias_hh_l0_reverse, mask, ds, packed_params(gru))
+                       gru.bias_hh_l0_reverse, mask, ds, packed_params(gru), before_recurrence)
 
 
 _tickets = {}

@@ -230,10 +230,11 @@ def test_seq2seq_model_on_gpu_matches_its_cpu_execution():
     assert isinstance(out, list) and isinstance(out[0], str)
 
 
-def test_device_prefetcher_feeds_the_step_in_order():
+@pytest.mark.parametrize("background", [True, False])
+def test_device_prefetcher_feeds_the_step_in_order(background):
     pkg = importlib.import_module("end-to-end-slu_b200")
     host = [(torch.full((4, 1000), float(i)), torch.full((4, 3), i, dtype=torch.int64)) for i in range(5)]
-    pf = pkg.loader.DevicePrefetcher(host)
+    pf = pkg.loader.DevicePrefetcher(host, background=background)
     seen = []
     for x, y in pf:
         assert x.is_cuda and y.is_cuda
@@ -242,5 +243,5 @@ def test_device_prefetcher_feeds_the_step_in_order():
     assert pf.h2d_bytes == 5 * (4 * 1000 * 4 + 4 * 3 * 8)
     m = gpu_model(R.synthetic_params(seed=6))
     xb, yb = R.synthetic_batch(2, 8000, seed=7)
-    (xd, yd), = list(pkg.loader.DevicePrefetcher([(xb, yb)]))
+    (xd, yd), = list(pkg.loader.DevicePrefetcher([(xb, yb)], background=background))
     assert abs(m(xd, yd)[0].item() - m(xb, yb)[0].item()) < 1e-6
