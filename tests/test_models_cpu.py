@@ -242,3 +242,22 @@ def test_packed_gru_parameters_keep_identity_values_and_checkpoints():
     g.double(); g.float()                                              # Module._apply re-homes the parameters
     v2 = ops.packed_params(g)
     assert v2 is not v and torch.equal(v2[0][:384], sd["weight_ih_l0"]) and torch.equal(g(x)[0], y0)
+
+
+def test_premask_shapes_and_draw_order(monkeypatch):
+    """engine._premask generates the keep-masks of several GRU stacks ahead of time; shapes follow the downsampling chain and the
+    draw order is the layer order (host logic; a supplied `_drop_mask` -- as the golden dropout test uses -- is called in line)."""
+    import importlib
+    eng = importlib.import_module("end-to-end-slu_b200").engine
+    calls = []
+
+    def fake(shape, p, training, device):
+        calls.append((tuple(shape), p, training))
+        return torch.zeros(shape)
+    monkeypatch.setattr(eng, "_drop_mask", fake)
+    stacks = [[(None, 0.5, 2), (None, 0.5, 2)], [(None, 0.25, 2), (None, 0.5, 1)]]
+    (m0, m1), join = eng._premask(stacks, 3, 401, True, torch.device("cpu"))
+    assert join is None
+    assert [c[0] for c in calls] == [(3, 401, 256), (3, 201, 256), (3, 101, 256), (3, 51, 256)]
+    assert [c[1] for c in calls] == [0.5, 0.5, 0.25, 0.5]
+    assert [tuple(m.shape) for m in m0] == [(3, 401, 256), (3, 201, 256)] and [tuple(m.shape) for m in m1] == [(3, 101, 256), (3, 51, 256)]
