@@ -10,15 +10,15 @@
 // (weight gradients live in wgrad_tc.cu, the SincNet front end in sinc_tc.cu).
 //
 // Persistent, warp-specialised kernel: one CTA per SM walks [128 x BN] output tiles (n fastest, so the activation rows of
-// a tile row are re-read from L2).  Roles (14 warps):
-//   warps 9-12 activation loaders: every k-block's [128 rows x 128 B] fp32 tile is fetched with 16-byte cp.async copies
+// a tile row are re-read from L2).  Roles (18 warps):
+//   warps 13-16 activation loaders: every k-block's [128 rows x 128 B] fp32 tile is fetched with 16-byte cp.async copies
 //              (coalesced full lines, zero-fill for rows shifted out of their utterance / the K tail) into a ring of
 //              staging slots -- several k-blocks in flight, no registers held; completion arrives on an mbarrier;
-//   warps 4-7  converters: staging slot -> bf16 hi + lo, stored K-major (no swizzle, padded leading-byte-offset) into the
-//              operand ring;
-//   warp 8     weight loader: the weights are PRE-SPLIT once per call (slu_presplit_bf16) into a k-chunk-major image, so
+//   warps 4-11 converters (2 groups of 4 taking alternate k-blocks): staging slot -> bf16 hi + lo, stored K-major (no swizzle,
+//              padded leading-byte-offset) into the operand ring;
+//   warp 12    weight loader: the weights are PRE-SPLIT once per call (slu_presplit_bf16) into a k-chunk-major image, so
 //              a stage's weight tile is 8 TMA bulk copies, no thread work;
-//   warp 13    MMA issuer: hi*hi + hi*lo + lo*hi tcgen05.mma per K=16 step into one of TWO [128 x BN] fp32 accumulators
+//   warp 17    MMA issuer: hi*hi + hi*lo + lo*hi tcgen05.mma per K=16 step into one of TWO [128 x BN] fp32 accumulators
 //              in TMEM; tcgen05.commit frees the operand stage / publishes the accumulator;
 //   warps 0-3  epilogue: tcgen05.ld, bias / LeakyReLU, transpose through shared memory, coalesced 16-byte row stores;
 //              the accumulator is released right after its last tcgen05.ld, so tile i+1's MMAs overlap tile i's stores.
@@ -46,11 +46,14 @@ constexpr int BM = 128, BK = 32;
 
 __host__ __device__ constexpr uint32_t tmem_cols(int bn) { return bn <= 32 ? 32 : (bn <= 64 ? 64 : (bn <= 128 ? 128 : 256)); }
 
-constexpr int EPI_WARPS = 4, CONV_WARPS = 4;                          // warps 0-3 epilogue (TMEM lane quarters), 4-7 converters
+// warps 0-3 epilogue (TMEM lane quarters); then CONV_GROUPS groups of 4 converter warps (group g takes k-blocks g, g + groups, ..:
+// converting one k-block is a chain of latencies -- barrier wait, LDS, split, STS, proxy fence, arrive -- so two groups in flight
+// double the rate of the activation path); weight loader; 4 activation loader warps; MMA issuer
+constexpr int EPI_WARPS = 4, CONV_GROUPS = 2, CONV_WARPS = 4 * CONV_GROUPS;
 constexpr int ALOAD_WARPS = 4;
 constexpr int WLOAD_WARP = EPI_WARPS + CONV_WARPS, ALOAD_WARP = WLOAD_WARP + 1, MMA_WARP = ALOAD_WARP + ALOAD_WARPS;
-constexpr int THREADS = (MMA_WARP + 1) * 32;                          // 448
-constexpr int CONV_THREADS = CONV_WARPS * 32, EPI_THREADS = EPI_WARPS * 32, ALOAD_THREADS = ALOAD_WARPS * 32;
+constexpr int THREADS = (MMA_WARP + 1) * 32;                          // 576
+constexpr int CONV_THREADS = 128, EPI_THREADS = EPI_WARPS * 32, ALOAD_THREADS = ALOAD_WARPS * 32;   // CONV_THREADS: per group
 constexpr uint32_t STG_ROW = BK * 4 + 16;                             // staged fp32 row segment + pad: conflict-free 16-byte reads
 constexpr uint32_t STG_SLOT = BM * STG_ROW;
 
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     }
   } else if (warp >= EPI_WARPS && warp < WLOAD_WARP) {
     // ================= converters: fp32 staging slot -> bf16 hi/lo K-major operand stage =================
-    const int ptid = tid - EPI_THREADS;
+    const int ptid = (tid - EPI_THREADS) & (CONV_THREADS - 1), grp = (tid - EPI_THREADS) / CONV_THREADS;
     constexpr int A_CH = BM * (BK / 8) / CONV_THREADS;              // 4 chunks of 8 consecutive k per thread and k-block
     int a_r[A_CH], a_kc[A_CH];
 #pragma unroll
@@ -153,9 +156,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       const int c = ptid + u * CONV_THREADS;
       a_kc[u] = c & 3; a_r[u] = c >> 2;
     }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
+    int my_tiles = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
+    const int total = my_tiles * nkb;                                 // k-blocks of this CTA, in pipeline order
+    {
+      for (int it = grp; it < total; it += CONV_GROUPS) {
         const int s = it % STAGES, slot = it % NSTG;
         mbar_wait(&stg_full[slot], (uint32_t)((it / NSTG) & 1));                       // this k-block's rows have landed
         const uint8_t* src = stg_base + slot * STG_SLOT;
@@ -398,16 +403,16 @@ extern "C" int slu_gemm_tc(const float* A, long lda, const void* w_img, const fl
   if ((reinterpret_cast<uintptr_t>(w_img) & 15) != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0 || (lda & 3) != 0 || (K & 3) != 0)
     return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
-  // Column-tile width: the widest tile unless a narrower one needs clearly fewer waves of the persistent grid (short
-  // sequences / small batches).  Cost model per wave: max(BN, 128) -- below 128 columns the producers bound a k-block.
+  // Column-tile width from a measured cost model: a k-block costs ~1100 cycles on the activation path (independent of BN) plus
+  // ~1.7 cycles per output column; pick the BN with the fewest (waves of the persistent grid) x (per-k-block cost).
   const int mt = (M + BM - 1) / BM, sms = sm_count();
   int best_bn = 0;
   long best_cost = 0;
   for (int bn = 256; bn >= 64; bn >>= 1) {
     if (bn > 64 && N <= bn / 2) continue;                     // tile would be mostly padding
     const long tiles = (long)mt * ((N + bn - 1) / bn);
-    const long cost = ((tiles + sms - 1) / sms) * (bn > 128 ? bn : 128);
-    if (best_bn == 0 || cost * 10 < best_cost * 9) { best_bn = bn; best_cost = cost; }
+    const long cost = ((tiles + sms - 1) / sms) * (1100 + (17 * bn) / 10);
+    if (best_bn == 0 || cost < best_cost) { best_bn = bn; best_cost = cost; }
   }
   if (best_bn == 64) return launch<64>(p, st);
   if (best_bn == 128) return launch<128>(p, st);

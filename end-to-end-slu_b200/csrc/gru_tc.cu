@@ -6,7 +6,10 @@
 //     384 of the 512 TMEM columns).  Nothing is re-read from shared memory or HBM during the T steps.
 //   * h_{t-1} is the B operand: a tiny K-major bf16 hi/lo tile [NB x 128] in shared memory, rewritten by the
 //     epilogue threads every step (h itself stays fp32 in registers; only the MMA operand copy is rounded).
-//   * every product is hi*hi + hi*lo + lo*hi (fp32 accumulate in TMEM): 72 MMAs (M=128, N=NB, K=16) per step.
+//   * every product is a bf16 hi/lo split with fp32 accumulation in TMEM.  On the 4- and 8-row tiles the hi and lo rows
+//     of the h tile are STACKED along the MMA's N dimension, so W_hi.[hi;lo] + W_lo.[hi;lo] = 48 MMAs (M=128, N=16, K=16)
+//     per step carry all four partial products; the 16-row tile issues hi*hi + hi*lo + lo*hi (72 MMAs).  At N=16 an MMA
+//     costs 8 cycles, i.e. the MMA phase is issue/pipe-bound -- which is why the count matters.
 //   * epilogue: tcgen05.ld the three [128 x NB] accumulators -> gate sigmoid/tanh -> h_t, fused with the
 //     Dropout-mask multiply and Downsample(avg, 2) of reference models.py:246-253, and the training stash.
 // The x-projection gx = x.W_ih^T + b_ih is a dense GEMM done beforehand for both directions (see gemm_tc.cu).

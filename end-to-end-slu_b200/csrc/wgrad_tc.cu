@@ -6,12 +6,12 @@
 // operand form of tcgen05: a [8-wide column chunk][frame] image with 16 bytes per frame and chunk columns SBO apart.
 // A persistent, warp-specialised CTA owns one [MT*128 x N] block of dW and walks 16-frame tiles of its share of the
 // (utterance, tile) list:
-//   warps 4-7  loaders: the tile's G rows and X rows arrive as 16-byte cp.async copies (coalesced full lines, zero-fill
+//   warps 8-11 loaders: the tile's G rows and X rows arrive as 16-byte cp.async copies (coalesced full lines, zero-fill
 //              for frames outside the utterance and for the column tails) in a 3-slot fp32 staging ring; completion is
 //              an asynchronous mbarrier arrival, no registers are held across the memory latency;
-//   warps 0-3  converters: staging slot -> bf16 hi + lo MN-major images (lanes walk frames: conflict-free 16-byte
+//   warps 0-7  converters (two groups of 4 warps taking alternate tiles): staging slot -> bf16 hi + lo MN-major images (lanes walk frames: conflict-free 16-byte
 //              shared-memory reads and stores), 2-stage operand ring;
-//   warp 8     MMA issuer: per tile hi*hi + hi*lo + lo*hi for every 128-row block of G and every tap (a tap is a frame
+//   warp 12    MMA issuer: per tile hi*hi + hi*lo + lo*hi for every 128-row block of G and every tap (a tap is a frame
 //              shift = +16 bytes on the B descriptor, so X is staged once for all taps); the MT * NTAPS accumulators
 //              [128 x N] stay in tensor memory across ALL tiles of the CTA.
 // One flush with fp32 atomics at the end.  G may come from two tensors (rows [0, m_split) from G0, the rest from G1):
@@ -27,9 +27,10 @@ using namespace tc05;
 
 constexpr int TF = 16;                         // frames per tile (= one K step of the MMA)
 constexpr int NSTG = 3, NOPS = 2;              // fp32 staging slots, bf16 operand stages
-constexpr int CONV_WARPS = 4, LOAD_WARPS = 4, MMA_WARP = CONV_WARPS + LOAD_WARPS;
-constexpr int THREADS = (MMA_WARP + 1) * 32;   // 288
-constexpr int CONV_THREADS = CONV_WARPS * 32, LOAD_THREADS = LOAD_WARPS * 32;
+constexpr int CONV_GROUPS = 2;                 // converter groups of 4 warps taking alternate tiles (a tile's conversion is a latency chain)
+constexpr int CONV_WARPS = 4 * CONV_GROUPS, LOAD_WARPS = 4, MMA_WARP = CONV_WARPS + LOAD_WARPS;
+constexpr int THREADS = (MMA_WARP + 1) * 32;   // 416
+constexpr int CONV_THREADS = 128, LOAD_THREADS = LOAD_WARPS * 32;      // CONV_THREADS: per group
 
 struct WgradParams {
   const float* G0; long ldg0;      // G rows [0, m_split):   G0[(b*T + t) * ldg0 + m]
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     // ================= loaders: one tile = TF rows of G (MC columns) + XR rows of X (N columns), 16 bytes per copy =================
     // A warp walks whole frame rows (frames lw, lw+4, ..), lanes walk 16-byte column pieces: one cp.async instruction
     // moves 512 contiguous bytes.  Column state (source tensor, validity) is fixed per thread and hoisted out of the loops.
-    const int lw = warp - CONV_WARPS;
+    const int lw = warp - CONV_WARPS;                         // loader warp 0..3
     constexpr int GJ = MC / 128, XJ = (N / 4 + 31) / 32;     // pieces per lane and row: G (= MT), X
     constexpr int GF = TF / LOAD_WARPS, XF = (XR + LOAD_WARPS - 1) / LOAD_WARPS;
     const float* gcol[GJ]; long gld[GJ]; bool gok[GJ];
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   } else if (warp < CONV_WARPS) {
     // ================= converters: fp32 staging -> bf16 hi/lo MN-major images (lanes walk frames) =================
     constexpr int GT = (MC / 8) * TF, XT = NCH * XR;        // (chunk, frame) tasks
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int grp = warp >> 2, ctid = tid & (CONV_THREADS - 1);
+    for (int it = grp; it < my_tiles; it += CONV_GROUPS) {
       const int slot = it % NSTG, s = it % NOPS;
       mbar_wait(&stg_full[slot], (uint32_t)((it / NSTG) & 1));
       if (it >= NOPS) mbar_wait(&op_empty[s], (uint32_t)(((it / NOPS) - 1) & 1));
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       uint8_t* b_hi = a_hi + 2 * C::A_PART;
       uint8_t* b_lo = b_hi + C::B_PART;
 #pragma unroll 4
-      for (int i = tid; i < GT; i += CONV_THREADS) {
+      for (int i = ctid; i < GT; i += CONV_THREADS) {
         const int c = i / TF, f = i - c * TF;
         const float4 x0 = *reinterpret_cast<const float4*>(src + f * C::PITCH_G + c * 32);
         const float4 x1 = *reinterpret_cast<const float4*>(src + f * C::PITCH_G + c * 32 + 16);
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       }
       const uint8_t* srcx = src + C::STG_G;
 #pragma unroll 4
-      for (int i = tid; i < XT; i += CONV_THREADS) {
+      for (int i = ctid; i < XT; i += CONV_THREADS) {
         const int c = i / XR, f = i - c * XR;
         const float4 x0 = *reinterpret_cast<const float4*>(srcx + f * C::PITCH_X + c * 32);
         const float4 x1 = *reinterpret_cast<const float4*>(srcx + f * C::PITCH_X + c * 32 + 16);
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   }
 
   // ================= flush: TMEM -> transposed through shared memory -> fp32 atomics (coalesced when s_n == 1) =================
-  if (my_tiles > 0 && warp < MMA_WARP) {
+  if (my_tiles > 0 && warp < 8) {
     mbar_wait(&acc_bar, 0);
     fence_after_sync();
     const int q = warp & 3, half = warp >> 2;          // two warps per TMEM lane quarter alternate 16-column groups
