@@ -29,6 +29,8 @@ SIGNATURES = {
     "slu_debug_gru_phase_clocks": [_P],
     "slu_intent_head_fwd": [_P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "slu_intent_head_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P],
+    "slu_h2d_async": [_P, _P, ctypes.c_size_t, _P, _I],
+    "slu_h2d_ready": [_P],
     "slu_stream_fork": [_P, _I, _P],
     "slu_stream_join": [_P, _I],
     "slu_dropout_mask": [_P, _L, _F, ctypes.c_ulonglong, _P],
@@ -74,7 +76,7 @@ stats = {"calls": 0}        # number of C-ABI kernel launches issued by this pro
 _prof = None                # name -> [(start_event, end_event)] while profiling
 _prof_detail = None         # [(name, small-int args, start, end)] per launch, when asked for
 _fn = {}
-_HOST_ONLY = ("slu_stream_fork", "slu_stream_join", "slu_set_gru_precision", "slu_debug_gru_phase_clocks")
+_HOST_ONLY = ("slu_h2d_async", "slu_h2d_ready", "slu_stream_fork", "slu_stream_join", "slu_set_gru_precision", "slu_debug_gru_phase_clocks")
 
 
 def call(name, *args):

@@ -17,6 +17,8 @@ struct Pool {
   cudaStream_t side[kMaxSide];
   cudaEvent_t forked;
   cudaEvent_t done[kMaxSide];
+  cudaStream_t copy;               // host -> device staging of the next batch
+  cudaEvent_t copy_after, copy_done;
 };
 
 Pool g_pool[kMaxDev];
@@ -34,6 +36,9 @@ int get_pool(Pool** out) {
       if ((e = cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
     }
     if ((e = cudaEventCreateWithFlags(&p.forked, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+    if ((e = cudaStreamCreateWithFlags(&p.copy, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+    if ((e = cudaEventCreateWithFlags(&p.copy_after, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+    if ((e = cudaEventCreateWithFlags(&p.copy_done, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
     p.ready = true;
   }
   *out = &p;
@@ -67,4 +72,29 @@ extern "C" int slu_stream_join(void* main_stream, int n) {
     if ((e = cudaStreamWaitEvent((cudaStream_t)main_stream, p->done[i], 0)) != cudaSuccess) return (int)e;
   }
   return 0;
+}
+
+// Host -> device staging on the library's copy stream.  `after_stream` (may be NULL = no ordering): the copy starts only after
+// everything queued there so far -- pass the consumer stream when `dst` is a recycled buffer whose previous contents may still be
+// in use.  `src` should be pinned (otherwise the runtime stages it synchronously).
+extern "C" int slu_h2d_async(void* dst, const void* src, size_t bytes, void* after_stream, int order_after) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  Pool* p = nullptr;
+  if (int err = get_pool(&p)) return err;
+  cudaError_t e;
+  if (order_after) {
+    if ((e = cudaEventRecord(p->copy_after, (cudaStream_t)after_stream)) != cudaSuccess) return (int)e;
+    if ((e = cudaStreamWaitEvent(p->copy, p->copy_after, 0)) != cudaSuccess) return (int)e;
+  }
+  return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, p->copy);
+}
+
+// Work queued on `consumer_stream` from now on waits for every copy queued with slu_h2d_async so far.
+extern "C" int slu_h2d_ready(void* consumer_stream) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  Pool* p = nullptr;
+  if (int err = get_pool(&p)) return err;
+  cudaError_t e = cudaEventRecord(p->copy_done, p->copy);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaStreamWaitEvent((cudaStream_t)consumer_stream, p->copy_done, 0);
 }

@@ -3,7 +3,9 @@
 The reference moves each batch inside `forward` (`models.py:300-303`, `351-352`: `x = x.cuda()`), a synchronous pageable
 copy in front of every step.  `DevicePrefetcher` wraps any iterable of batches (the `DataLoader` `training.py:57/92`
 iterates): it pins each host tensor and copies batch i+1 on a copy stream while batch i computes, handing the step
-device tensors (`forward` accepts those unchanged, as in the README snippet).  With `background=True` a helper thread pulls
+device tensors (`forward` accepts those unchanged, as in the README snippet).  Already-pinned batches of recurring shapes
+take a lean path (library copy stream, recycled device buffers: a yielded tensor stays valid until two more batches have
+been drawn -- long enough for a training step, not for hoarding batches).  With `background=True` a helper thread pulls
 the next batch from the loader and queues its copy (useful when the loader itself is slow; with in-memory batches the
 in-line variant measured 2 % faster: the staging costs less than the GIL hand-offs).  Host logic only -- no kernels.
 """
@@ -11,6 +13,8 @@ import queue
 import threading
 
 import torch
+
+from . import _lib
 
 _copy_streams = {}
 _END = object()
@@ -30,11 +34,44 @@ class DevicePrefetcher:
         self.depth = max(1, depth)
         self.background = background
         self.h2d_bytes = 0
+        self._pool = {}                 # (shape, dtype) -> rotating device buffers of the lean path
+
+    # ---- lean path: pinned tensors of recurring shapes go through the library's copy stream into recycled device buffers
+    # (two C calls per tensor; the generic path below costs ~0.15 ms of host time per batch, spent while the GPU idles
+    # between the result read of one step and the first launch of the next) -------------------------------------------------
+    def _buffer(self, t):
+        key = (tuple(t.shape), t.dtype)
+        ring = self._pool.get(key)
+        if ring is None:
+            ring = self._pool[key] = [[torch.empty(t.shape, dtype=t.dtype, device=self.device) for _ in range(self.depth + 2)], 0]
+        buf = ring[0][ring[1] % len(ring[0])]
+        ring[1] += 1
+        return buf
+
+    def _stage_lean(self, batch):
+        if not all((not torch.is_tensor(t)) or t.is_cuda or (t.is_pinned() and t.is_contiguous()) for t in batch):
+            return None
+        main = _lib.stream()
+        out = []
+        for t in batch:
+            if torch.is_tensor(t) and not t.is_cuda:
+                buf = self._buffer(t)
+                nbytes = t.numel() * t.element_size()
+                # recycled buffer: its previous consumer was queued on the compute stream at least `depth + 1` batches ago
+                _lib.call("slu_h2d_async", buf.data_ptr(), t.data_ptr(), nbytes, main, 1)
+                self.h2d_bytes += nbytes
+                t = buf
+            out.append(t)
+        return tuple(out), None
 
     def __len__(self):
         return len(self.loader)
 
     def _stage(self, batch, stream):
+        if not self.background and len(self._pool) < 16:          # lean path (consumer's thread only; bounded shape variety)
+            lean = self._stage_lean(batch)
+            if lean is not None:
+                return lean
         with torch.cuda.stream(stream):
             out = []
             for t in batch:
@@ -48,6 +85,9 @@ class DevicePrefetcher:
 
     def _hand_over(self, staged):
         batch, ready = staged
+        if ready is None:                          # lean path: one C call orders the compute stream after the copies
+            _lib.call("slu_h2d_ready", _lib.stream())
+            return batch
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ready)
         for t in batch:
@@ -67,14 +107,18 @@ class DevicePrefetcher:
                 staged.append(self._stage(next(it), stream))
         except StopIteration:
             it = None
-        while staged:
-            batch = self._hand_over(staged.pop(0))
-            if it is not None:
-                try:
-                    staged.append(self._stage(next(it), stream))
-                except StopIteration:
-                    it = None
-            yield batch
+        try:
+            while staged:
+                batch = self._hand_over(staged.pop(0))
+                if it is not None:
+                    try:
+                        staged.append(self._stage(next(it), stream))
+                    except StopIteration:
+                        it = None
+                yield batch
+        finally:
+            if self._pool:                     # abandoned mid-way: order the compute stream after copies still in flight
+                _lib.call("slu_h2d_ready", _lib.stream())
 
     def _iter_background(self):
         stream = _copy_stream(self.device)

@@ -95,6 +95,12 @@ int slu_intent_head_bwd(const float* gloss, const float* feats, const float* W, 
 int slu_stream_fork(void* main_stream, int n, void** side_streams);
 int slu_stream_join(void* main_stream, int n);
 
+/* Batch staging (replaces the synchronous `x = x.cuda()` inside forward, models.py:300-303): slu_h2d_async queues a host -> device
+ * copy on the library's copy stream (order_after != 0: only after everything queued on after_stream so far -- for recycled
+ * destination buffers); slu_h2d_ready makes consumer_stream wait for all copies queued so far.  src should be pinned. */
+int slu_h2d_async(void* dst, const void* src, size_t bytes, void* after_stream, int order_after);
+int slu_h2d_ready(void* consumer_stream);
+
 /* Dropout keep-mask (nn.Dropout, models.py:246/276/700, training mode): mask[i] = Bernoulli(1-p) / (1-p), i < n, from
  * Philox4x32-10 keyed by `seed` (counter = i/4).  `mask` must be 16-byte aligned.  The GRU kernels multiply by it. */
 int slu_dropout_mask(float* mask, long n, float p, unsigned long long seed, void* stream);

@@ -230,17 +230,21 @@ def test_seq2seq_model_on_gpu_matches_its_cpu_execution():
     assert isinstance(out, list) and isinstance(out[0], str)
 
 
-@pytest.mark.parametrize("background", [True, False])
-def test_device_prefetcher_feeds_the_step_in_order(background):
+@pytest.mark.parametrize("background,pin", [(True, False), (False, False), (False, True)])
+def test_device_prefetcher_feeds_the_step_in_order(background, pin):
+    """generic path (helper thread / in line) and the lean path (pinned batches -> library copy stream, recycled buffers)"""
     pkg = importlib.import_module("end-to-end-slu_b200")
-    host = [(torch.full((4, 1000), float(i)), torch.full((4, 3), i, dtype=torch.int64)) for i in range(5)]
+    host = [(torch.full((4, 1000), float(i)), torch.full((4, 3), i, dtype=torch.int64)) for i in range(7)]
+    if pin:
+        host = [(a.pin_memory(), b.pin_memory()) for a, b in host]
     pf = pkg.loader.DevicePrefetcher(host, background=background)
     seen = []
     for x, y in pf:
         assert x.is_cuda and y.is_cuda
         seen.append((x.mean().item(), int(y[0, 0].item())))
-    assert [(round(a, 4), b) for a, b in seen] == [(float(i), i) for i in range(5)]
-    assert pf.h2d_bytes == 5 * (4 * 1000 * 4 + 4 * 3 * 8)
+    assert [(round(a, 4), b) for a, b in seen] == [(float(i), i) for i in range(7)]
+    assert pf.h2d_bytes == 7 * (4 * 1000 * 4 + 4 * 3 * 8)
+    assert (len(pf._pool) > 0) == pin                                  # the lean path ran iff the batches were pinned
     m = gpu_model(R.synthetic_params(seed=6))
     xb, yb = R.synthetic_batch(2, 8000, seed=7)
     (xd, yd), = list(pkg.loader.DevicePrefetcher([(xb, yb)], background=background))

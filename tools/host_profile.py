@@ -98,3 +98,31 @@ sync()
 s = io.StringIO()
 pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(28)
 print(s.getvalue())
+
+# ---- where does the end-to-end step lose time against the device-timed one? --------------------------------------------------
+if dev == "cuda":
+    pkg.ops.OVERLAP = True
+    xs = [(0.1 * torch.randn(B, T)).pin_memory() for _ in range(4)]
+    ys = [torch.stack([torch.randint(0, v, (B,)) for v in (6, 14, 4)], 1).pin_memory() for _ in range(4)]
+
+    def run(n, host, read):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        e0.record()
+        if host:
+            for xb, yb in pkg.loader.DevicePrefetcher(((xs[i % 4], ys[i % 4]) for i in range(n))):
+                loss, _ = m(xb, yb); opt.zero_grad(); loss.backward(); opt.step()
+                if read:
+                    loss.item()
+        else:
+            for i in range(n):
+                loss, _ = m(x, y); opt.zero_grad(); loss.backward(); opt.step()
+                if read:
+                    loss.item()
+        e1.record()
+        sync()
+        return e0.elapsed_time(e1) / n
+
+    for host, read in ((False, False), (False, True), (True, False), (True, True)):
+        run(3, host, read)
+        print("inputs %-6s loss.item() per step %-5s : %.3f ms/step" % ("host" if host else "device", read, run(20, host, read)))
