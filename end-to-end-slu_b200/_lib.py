@@ -37,6 +37,7 @@ SIGNATURES = {
     "slu_leaky_bwd_bias": [_P, _P, _F, _P, _P, _L, _I, _P],
     "slu_gemm_tc": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "slu_presplit_bf16": [_P, _L, _L, _L, _I, _I, _I, _P, _P],
+    "slu_presplit_multi": [_P, _I, _P],
     "slu_wgrad2_tc": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P],
     "slu_wgrad_tc": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P],
     "slu_tc_selftest": [_P, _P, _P, _I, _I, _P],

@@ -367,6 +367,27 @@ __global__ void presplit_kernel(const float* __restrict__ W, long sn, long sk, l
   }
 }
 
+// Up to 16 pre-split jobs in ONE launch (blockIdx.y = job): every weight image a forward/backward pass needs, made at once.
+struct PresplitJob { const float* W; long sn, sk, stap; int taps, N, K, pad_; __nv_bfloat16* img; };
+struct PresplitTable { PresplitJob job[16]; };
+
+__global__ void presplit_multi_kernel(const __grid_constant__ PresplitTable tab) {
+  const PresplitJob& j = tab.job[blockIdx.y];
+  const int Kp = (j.K + 31) / 32 * 32, KC = Kp / 8;
+  const size_t total = (size_t)j.taps * j.N * Kp;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i & 7);
+    const size_t r = i >> 3;
+    const int n = (int)(r % j.N);
+    const size_t c = r / j.N;
+    const int k = (int)(c % KC) * 8 + e, tap = (int)(c / KC);
+    const float v = k < j.K ? j.W[(long)n * j.sn + (long)k * j.sk + (long)tap * j.stap] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    j.img[i] = h;
+    j.img[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 }  // namespace
 
 // like slu_presplit_bf16, with elements whose in-row offset k*sk + tap*stap reaches row_len read as 0 (sinc_tc.cu's TMA-fed filter bank)
@@ -389,6 +410,26 @@ extern "C" int slu_presplit_bf16(const float* W, long sn, long sk, long stap, in
   int grid = (int)((total + 255) / 256);
   if (grid > 1184) grid = 1184;
   presplit_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(W, sn, sk, stap, taps, N, K, Kp, 0, (__nv_bfloat16*)img);
+  return (int)cudaGetLastError();
+}
+
+// n <= 16 jobs of slu_presplit_bf16 in one launch.  `jobs` is a HOST array of {W, sn, sk, stap, taps, N, K, (pad), img}.
+extern "C" int slu_presplit_multi(const void* jobs, int n, void* stream) {
+  if (n <= 0) return 0;
+  if (n > 16 || !jobs) return (int)cudaErrorInvalidValue;
+  PresplitTable tab;
+  const PresplitJob* src = (const PresplitJob*)jobs;
+  size_t most = 0;
+  for (int i = 0; i < n; ++i) {
+    tab.job[i] = src[i];
+    if (src[i].taps <= 0 || src[i].N <= 0 || src[i].K <= 0 || !src[i].W || !src[i].img) return (int)cudaErrorInvalidValue;
+    const size_t total = (size_t)src[i].taps * src[i].N * ((src[i].K + 31) / 32 * 32);
+    most = total > most ? total : most;
+  }
+  for (int i = n; i < 16; ++i) tab.job[i] = tab.job[0];
+  int gx = (int)((most + 255) / 256);
+  if (gx > 296) gx = 296;
+  presplit_multi_kernel<<<dim3(gx, n), 256, 0, (cudaStream_t)stream>>>(tab);
   return (int)cudaGetLastError();
 }
 

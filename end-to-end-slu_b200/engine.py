@@ -5,9 +5,15 @@ freeze/unfreeze, Adam, .cpu()/.cuda() behave exactly like the reference's); this
 runs when those parameters live on a CUDA device.  Unsupported architectures raise -- there is
 no silent fallback to library kernels or to the CPU.
 """
+import os
+
 import torch
 
 from . import _lib, ops
+
+
+# One weight-image launch per forward (slu_presplit_multi) instead of one per GEMM; SLU_MULTI_PRESPLIT=0 restores the latter (A/B).
+MULTI_PRESPLIT = os.environ.get("SLU_MULTI_PRESPLIT", "1") != "0"
 
 
 class Plan:
@@ -117,13 +123,43 @@ def _premask(stacks, B, T, training, device):
     return out, join
 
 
-def _run_rnns(out, rnns, training, masks=None, join=None):
+def _weight_images(convs, rnns):
+    """Operand images (bf16 hi/lo, k-chunk-major) of every GEMM weight of the given layers, made by ONE launch
+    (slu_presplit_multi): x-projection / conv forward forms and, when gradients are on, the input-gradient forms that the
+    backward pass will use.  Returns ([per conv (fwd, dx)], [per GRU (nt, nn)]); None entries = let the op make its own."""
+    if not MULTI_PRESPLIT:
+        return [None] * len(convs), [None] * len(rnns)
+    need_dx = torch.is_grad_enabled()
+    items, owners = [], []
+    for li, (conv, _) in enumerate(convs):
+        it = ops.conv_weight_items(conv, need_dx)
+        if it is not None:
+            owners += [("c", li, k) for k in range(len(it))]
+            items += it
+    for li, (gru, _, _) in enumerate(rnns):
+        it = ops.gru_weight_items(gru, need_dx)
+        if it is not None:
+            owners += [("g", li, k) for k in range(len(it))]
+            items += it
+    imgs = ops.presplit_many(items) if items else []
+    conv_imgs, gru_imgs = [None] * len(convs), [None] * len(rnns)
+    for (kind, li, k), img in zip(owners, imgs):
+        dst = conv_imgs if kind == "c" else gru_imgs
+        pair = list(dst[li]) if dst[li] is not None else [None, None]
+        pair[k] = img
+        dst[li] = tuple(pair)
+    return conv_imgs, gru_imgs
+
+
+def _run_rnns(out, rnns, training, masks=None, join=None, imgs=None):
+    if imgs is None and rnns:
+        imgs = _weight_images([], rnns)[1]
     for i, (gru, p, ds) in enumerate(rnns):
         B, T, _ = out.shape
         mask = masks[i] if masks is not None else _drop_mask((B, T, 256), p, training, out.device)
         if mask is not None and tuple(mask.shape) != (B, T, 256):
             raise RuntimeError("slu_b200: pre-generated dropout mask does not match the layer input")
-        out = ops.bigru(out, gru, mask, ds, join if i == 0 else None)     # masks are joined right before the first recurrence
+        out = ops.bigru(out, gru, mask, ds, join if i == 0 else None, imgs[i])   # masks are joined right before the first recurrence
     if join is not None and not rnns:
         join()
     return out
@@ -136,18 +172,24 @@ def phoneme_features(pm, x):
     out = ops.SincFrontend.apply(x, plan.sinc.filt_b1, plan.sinc.filt_band)      # [B, L1, 80] (LeakyReLU is identity on >=0)
     for conv, slope in plan.convs:
         out = ops.conv_block(out, conv.weight, conv.bias, slope)
+    # W_ih operand images of both GRU stacks in one launch, queued while the GPU is busy with the front end (an A/B on the same
+    # box showed that making them -- and the conv images -- BEFORE the front end costs more host time in the idle gap at the
+    # start of a step than the saved launches are worth)
+    _, gru_imgs = _weight_images([], plan.phone + plan.word)
     # Masks of the phoneme AND word stacks: queued on a side stream once the front end is in flight (the host prepares them
     # while the GPU is busy), they run next to the first x-projection GEMM and are joined right before the first recurrence.
     (m_phone, m_word), join = _premask([plan.phone, plan.word], out.shape[0], out.shape[1], pm.training, out.device)
-    out = _run_rnns(out, plan.phone, pm.training, m_phone, join)
+    out = _run_rnns(out, plan.phone, pm.training, m_phone, join, gru_imgs[:len(plan.phone)])
     pm._word_masks = (m_word, out.shape[0], out.shape[1]) if pm.training else None
+    pm._word_imgs = gru_imgs[len(plan.phone):]
     return out
 
 
 def word_features(pm, ph):
     pending, pm._word_masks = getattr(pm, "_word_masks", None), None
     masks = pending[0] if pending is not None and pm.training and pending[1:] == (ph.shape[0], ph.shape[1]) else None
-    return _run_rnns(ph, pm._plan.word, pm.training, masks)
+    imgs, pm._word_imgs = getattr(pm, "_word_imgs", None), None      # made together with the phoneme stack's (same forward pass)
+    return _run_rnns(ph, pm._plan.word, pm.training, masks, None, imgs if imgs and len(imgs) == len(pm._plan.word) else None)
 
 
 def compute_features(pm, x):

@@ -67,6 +67,47 @@ def presplit(W, w_off, sn, sk, stap, taps, N, K):
     return img
 
 
+class _Job(ctypes.Structure):
+    _fields_ = [("W", ctypes.c_void_p), ("sn", ctypes.c_long), ("sk", ctypes.c_long), ("stap", ctypes.c_long),
+                ("taps", ctypes.c_int), ("N", ctypes.c_int), ("K", ctypes.c_int), ("pad", ctypes.c_int), ("img", ctypes.c_void_p)]
+
+
+# weight-operand forms (arguments of slu_presplit_bf16) of the layers' GEMMs
+def _form_nt(w):                     # linear_nt: w [N, K] row-major
+    N, K = w.shape
+    return (0, K, 1, 0, 1, N, K)
+
+
+def _form_nn(w):                     # matmul_nn: w [K, N] row-major, read transposed
+    K, N = w.shape
+    return (0, 1, N, 0, 1, N, K)
+
+
+def _form_conv_fwd(w):               # Conv1d weight [Cout, Cin, k] as k taps of [Cout, Cin]
+    Cout, Cin, k = w.shape
+    return (0, Cin * k, k, 1, k, Cout, Cin)
+
+
+def _form_conv_dx(w):                # input gradient: taps walked backwards, [Cin, Cout] per tap
+    Cout, Cin, k = w.shape
+    return (k - 1, k, Cin * k, -1, k, Cin, Cout)
+
+
+def presplit_many(items):
+    """items: [(weight tensor, form tuple)] -> list of operand images, made by ONE launch per 16 items (slu_presplit_multi)."""
+    imgs = []
+    for base in range(0, len(items), 16):
+        chunk = items[base:base + 16]
+        jobs = (_Job * len(chunk))()
+        for i, (w, (w_off, sn, sk, stap, taps, N, K)) in enumerate(chunk):
+            Kp = (K + 31) // 32 * 32
+            img = torch.empty(2 * taps * N * Kp, device=w.device, dtype=torch.bfloat16)
+            jobs[i] = _Job(_eptr(w, w_off), sn, sk, stap, taps, N, K, 0, img.data_ptr())
+            imgs.append(img)
+        _lib.call("slu_presplit_multi", jobs, len(chunk), _lib.stream())
+    return imgs
+
+
 def wgrad_tc(G, g_off, ldg, M, X, x_off, ldx, N, B, T, out, o_off, s_m, s_n=1, s_tap=0, taps=1, shift0=0, stream=None):
     """out[...] += G^T . X over frames (slu_wgrad_tc); `out` must be pre-zeroed for a plain gradient."""
     _lib.call("slu_wgrad_tc", _eptr(G, g_off), ldg, M, _eptr(X, x_off), ldx, N, B, T, taps, shift0, _eptr(out, o_off), s_m, s_n,
@@ -81,20 +122,20 @@ def wgrad2_tc(G0, g0_off, ldg0, m_split, G1, g1_off, ldg1, M, X, x_off, ldx, N, 
     return out
 
 
-def linear_nt(x2, w, bias=None):
-    """x2 [M,K] @ w[N,K]^T + bias -> [M,N]."""
+def linear_nt(x2, w, bias=None, img=None):
+    """x2 [M,K] @ w[N,K]^T + bias -> [M,N]  (img: w's operand image if the caller already made it)."""
     M, K = x2.shape
     N = w.shape[0]
     out = torch.empty(M, N, device=x2.device, dtype=torch.float32)
-    return gemm_tc(x2, K, presplit(w, 0, K, 1, 0, 1, N, K), M, N, K, out, bias=bias)
+    return gemm_tc(x2, K, presplit(w, *_form_nt(w)) if img is None else img, M, N, K, out, bias=bias)
 
 
-def matmul_nn(a2, w):
+def matmul_nn(a2, w, img=None):
     """a2 [M,K] @ w[K,N] -> [M,N]  (w row-major, i.e. the 'transposed weight' operand of an input gradient)."""
     M, K = a2.shape
     N = w.shape[1]
     out = torch.empty(M, N, device=a2.device, dtype=torch.float32)
-    return gemm_tc(a2, K, presplit(w, 0, 1, N, 0, 1, N, K), M, N, K, out)
+    return gemm_tc(a2, K, presplit(w, *_form_nn(w)) if img is None else img, M, N, K, out)
 
 
 def matmul_tn(g2, x2):
@@ -109,16 +150,17 @@ class ConvBlock(torch.autograd.Function):
     """Conv1d(k odd, pad k//2) + bias + LeakyReLU on NLC activations as an accumulating tap-GEMM (models.py:200-220)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, slope):
+    def forward(ctx, x, weight, bias, slope, imgs=None):
         x = _f32(x)
         B, T, Cin = x.shape
         Cout, _, k = weight.shape
         w = weight.detach().contiguous()
         out = torch.empty(B, T, Cout, device=x.device, dtype=torch.float32)
-        gemm_tc(x, Cin, presplit(w, 0, Cin * k, k, 1, k, Cout, Cin), B * T, Cout, Cin, out, bias=bias.detach(), taps=k,
-                tap_pad=k // 2, T=T, act=1, slope=slope)
+        img_fwd, img_dx = imgs if imgs is not None else (presplit(w, *_form_conv_fwd(w)), None)
+        gemm_tc(x, Cin, img_fwd, B * T, Cout, Cin, out, bias=bias.detach(), taps=k, tap_pad=k // 2, T=T, act=1, slope=slope)
         ctx.save_for_backward(x, w, out)
         ctx.slope = slope
+        ctx.img_dx = img_dx
         return out
 
     @staticmethod
@@ -144,16 +186,17 @@ class ConvBlock(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, Cin, device=x.device, dtype=torch.float32)
             # dX[b,t,ci] = sum_d sum_co dpre[b,t-(d-k//2),co] W[co,ci,d]; tap' = k-1-d walks the kernel backwards
-            gemm_tc(dpre, Cout, presplit(w, k - 1, k, Cin * k, -1, k, Cin, Cout), B * T, Cin, Cout, dx, taps=k, tap_pad=k // 2, T=T)
+            img_dx = ctx.img_dx if ctx.img_dx is not None else presplit(w, *_form_conv_dx(w))
+            gemm_tc(dpre, Cout, img_dx, B * T, Cin, Cout, dx, taps=k, tap_pad=k // 2, T=T)
         if not ctx.needs_input_grad[2]:
             db = None
         if fork is not None:
             fork.join()
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def conv_block(x, weight, bias, slope):
-    return ConvBlock.apply(x, weight, bias, slope)
+def conv_block(x, weight, bias, slope, imgs=None):
+    return ConvBlock.apply(x, weight, bias, slope, imgs)
 
 
 def set_gru_precision(mode):
@@ -231,7 +274,7 @@ class BiGRU(torch.autograd.Function):
     x [B,T,I] -> [B, ceil(T/ds), 256]."""
 
     @staticmethod
-    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, mask, ds, packed=None, before_recurrence=None):
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, mask, ds, packed=None, before_recurrence=None, imgs=None):
         x = _f32(x)
         B, T, I = x.shape
         dev = x.device
@@ -242,7 +285,8 @@ class BiGRU(torch.autograd.Function):
             b_ih_cat = torch.cat([b_ih, b_ih_r], 0).detach()
             w_hh_cat = torch.stack([w_hh, w_hh_r], 0).detach().contiguous()   # [2,384,128]
             b_hh_cat = torch.stack([b_hh, b_hh_r], 0).detach().contiguous()
-        gx = linear_nt(x.view(B * T, I), w_ih_cat, b_ih_cat)                    # x-projection, both directions
+        img_nt, img_nn = imgs if imgs is not None else (None, None)
+        gx = linear_nt(x.view(B * T, I), w_ih_cat, b_ih_cat, img_nt)            # x-projection, both directions
         T2 = (T + ds - 1) // ds
         y_full = torch.empty(B, T, 256, device=dev, dtype=torch.float32)
         y_out = torch.empty(B, T2, 256, device=dev, dtype=torch.float32) if (ds != 1 or mask is not None) else y_full
@@ -255,6 +299,7 @@ class BiGRU(torch.autograd.Function):
         if need:
             ctx.save_for_backward(x, w_ih_cat, w_hh_cat, y_full, stash, mask)
             ctx.ds = ds
+            ctx.img_nn = img_nn
         return y_out
 
     @staticmethod
@@ -283,7 +328,7 @@ class BiGRU(torch.autograd.Function):
             for d in range(2):          # dW_hh[d] = [dr,dz | dhn]^T . h_{t-1}  (h_{t+1} for the reverse direction), one launch
                 wgrad2_tc(dgx, d * 384, 768, 256, dhn, d * H, 256, 384, y_full, d * H, 256, H, B, T, dw_hh, d * 384 * H, H,
                           shift0=1 if d else -1, stream=fork.stream(1 + d))
-        dx = matmul_nn(dgx.view(B * T, 768), w_ih_cat).view(B, T, I) if ni[0] else None
+        dx = matmul_nn(dgx.view(B * T, 768), w_ih_cat, ctx.img_nn).view(B, T, I) if ni[0] else None
         if wg:
             db6 = dbias.index_select(1, _bias_gather(dev))                     # (dr, dz, dn | dr, dz, dhn) per direction
             for d in range(2):
@@ -292,7 +337,7 @@ class BiGRU(torch.autograd.Function):
                 grads[4 * d + 2] = db6[d, :3].reshape(384)                     # b_ih
                 grads[4 * d + 3] = db6[d, 3:].reshape(384)                     # b_hh
             fork.join()
-        return (dx, *grads, None, None, None, None)
+        return (dx, *grads, None, None, None, None, None)
 
 
 _PACK_ORDER = ("weight_ih_l0", "weight_ih_l0_reverse", "weight_hh_l0", "weight_hh_l0_reverse",
@@ -332,11 +377,27 @@ def packed_params(gru):
     return gru._slu_views
 
 
-def bigru(x, gru, mask=None, ds=1, before_recurrence=None):
-    """Run BiGRU on the parameters of an nn.GRU holder module."""
+def bigru(x, gru, mask=None, ds=1, before_recurrence=None, imgs=None):
+    """Run BiGRU on the parameters of an nn.GRU holder module (imgs: operand images of its W_ih from gru_weight_items)."""
     return BiGRU.apply(x, gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0,
                        gru.weight_ih_l0_reverse, gru.weight_hh_l0_reverse, gru.bias_ih_l0_reverse,
-                       gru.bias_hh_l0_reverse, mask, ds, packed_params(gru), before_recurrence)
+                       gru.bias_hh_l0_reverse, mask, ds, packed_params(gru), before_recurrence, imgs)
+
+
+def gru_weight_items(gru, need_dx):
+    """presplit_many items of one GRU: W_ih of both directions as the x-projection operand (+ the input-gradient operand)."""
+    packed = packed_params(gru)
+    if packed is None:
+        return None
+    w = packed[0]
+    return [(w, _form_nt(w))] + ([(w, _form_nn(w))] if need_dx else [])
+
+
+def conv_weight_items(conv, need_dx):
+    w = conv.weight.detach()
+    if not w.is_contiguous():
+        return None
+    return [(w, _form_conv_fwd(w))] + ([(w, _form_conv_dx(w))] if need_dx else [])
 
 
 _tickets = {}

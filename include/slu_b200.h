@@ -119,6 +119,8 @@ int slu_gemm_tc(const float* A, long lda, const void* w_img, const float* bias, 
 /* Weights W(n, tap, k) = W[n*sn + k*sk + tap*stap] (any strides, so transposed / reversed-tap views cost nothing) -> bf16 hi/lo
  * image [2][taps][N][Kp], Kp = K rounded up to 32 (img: 2*taps*N*Kp bf16 values). */
 int slu_presplit_bf16(const float* W, long sn, long sk, long stap, int taps, int N, int K, void* img, void* stream);
+/* n <= 16 such jobs in ONE launch; `jobs` = host array of struct { const float* W; long sn, sk, stap; int taps, N, K, pad; void* img; }. */
+int slu_presplit_multi(const void* jobs, int n, void* stream);
 
 /* Weight-gradient GEMM (reduction over frames) with MN-major tcgen05 operands and TMEM-resident accumulators:
  *   out[m*s_m + n*s_n + tap*s_tap] += sum_{b<B, t<T} G[(b*T+t)][m] * X[(b*T + t + shift0 + tap)*ldx + n]

@@ -249,3 +249,21 @@ def test_device_prefetcher_feeds_the_step_in_order(background, pin):
     xb, yb = R.synthetic_batch(2, 8000, seed=7)
     (xd, yd), = list(pkg.loader.DevicePrefetcher([(xb, yb)], background=background))
     assert abs(m(xd, yd)[0].item() - m(xb, yb)[0].item()) < 1e-6
+
+
+def test_weights_changed_in_place_are_seen_by_the_next_forward():
+    """Weight operand images / packed parameter buffers are derived state: after in-place updates (optimizer-style and via
+    .data) the next forward must use the new values."""
+    p = R.synthetic_params(seed=9)
+    m = gpu_model(p)
+    x, _ = R.synthetic_batch(3, 16000, seed=10)
+    with torch.no_grad():
+        l0, _ = m.predict_intents(x)
+        assert rel_err(l0.cpu(), R.intent_logits(x, p)) < LOGIT_TOL / 10
+        for i, (k, q) in enumerate(m.named_parameters()):
+            if q.dtype == torch.float32:
+                (q if i % 2 else q.data).mul_(1.02)
+        p2 = {k: (v * 1.02 if v.dtype == torch.float32 else v) for k, v in p.items()}
+        l1, _ = m.predict_intents(x)
+        assert rel_err(l1.cpu(), R.intent_logits(x, p2)) < LOGIT_TOL / 10
+        assert rel_err(l1.cpu(), l0.cpu()) > 1e-3
