@@ -18,49 +18,67 @@ _installed = False
 stats = {"allreduce_calls": 0, "bucket_bytes": 0}
 
 
-def _flatten(grads):
-    parts = []
-    for g in grads:
-        if g.dtype == torch.float64:
-            hi = g.float()
-            parts.append(hi.reshape(-1))
-            parts.append((g - hi.double()).float().reshape(-1))
-        else:
-            parts.append(g.reshape(-1))
-    return torch.cat(parts)
+class _Bucket:
+    """Flat fp32 bucket + per-gradient views, built once per set of gradient shapes (the host cost of slicing / concatenating
+    ~50 tensors every step is what makes a multi-GPU step host-bound, not the collective)."""
+
+    def __init__(self, grads):
+        self.key = _key(grads)
+        n = sum(g.numel() * (2 if g.dtype == torch.float64 else 1) for g in grads)
+        self.flat = torch.empty(n, device=grads[0].device, dtype=torch.float32)
+        self.views32, self.idx32, self.views64, self.idx64 = [], [], [], []
+        off = 0
+        for i, g in enumerate(grads):
+            k = g.numel()
+            if g.dtype == torch.float64:                      # carried as an fp32 (hi, lo) pair inside the single bucket
+                self.views64.append((self.flat[off:off + k].view_as(g), self.flat[off + k:off + 2 * k].view_as(g)))
+                self.idx64.append(i)
+                off += 2 * k
+            else:
+                self.views32.append(self.flat[off:off + k].view_as(g))
+                self.idx32.append(i)
+                off += k
+
+    def pack(self, grads):
+        if self.idx32:
+            torch._foreach_copy_(self.views32, [grads[i] for i in self.idx32])
+        for (hi, lo), i in zip(self.views64, self.idx64):
+            g = grads[i]
+            hi.copy_(g)
+            lo.copy_(g - hi.double())
+
+    def unpack(self, grads):
+        if self.idx32:
+            torch._foreach_copy_([grads[i] for i in self.idx32], self.views32)
+        for (hi, lo), i in zip(self.views64, self.idx64):
+            grads[i].copy_(hi.double() + lo.double())
 
 
-def _unflatten(flat, grads):
-    """Write the (already averaged) bucket back: one multi-tensor copy for the fp32 gradients."""
-    off = 0
-    dst, src = [], []
-    for g in grads:
-        n = g.numel()
-        if g.dtype == torch.float64:
-            g.copy_((flat[off:off + n].double() + flat[off + n:off + 2 * n].double()).view_as(g))
-            off += 2 * n
-        else:
-            dst.append(g)
-            src.append(flat[off:off + n].view_as(g))
-            off += n
-    if dst:
-        torch._foreach_copy_(dst, src)
+def _key(grads):
+    return tuple((g.shape, g.dtype, g.device) for g in grads)
+
+
+_bucket = None
 
 
 def allreduce_grads(params, group=None):
     """Average `.grad` of `params` across ranks with a single collective.  Returns bytes exchanged."""
+    global _bucket
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return 0
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return 0
-    flat = _flatten(grads)
+    if _bucket is None or _bucket.key != _key(grads):
+        _bucket = _Bucket(grads)
+    _bucket.pack(grads)
+    flat = _bucket.flat
     if flat.is_cuda:                                   # NCCL averages inside the collective
         dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
     else:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         flat.mul_(1.0 / dist.get_world_size(group))
-    _unflatten(flat, grads)
+    _bucket.unpack(grads)
     stats["allreduce_calls"] += 1
     stats["bucket_bytes"] = flat.numel() * 4
     return stats["bucket_bytes"]
