@@ -25,6 +25,7 @@ SIGNATURES = {
     "slu_gru_bwd_simt": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_gru_fwd_tc": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "slu_bigru_bwd_tc": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
     "slu_set_gru_precision": [_I],
     "slu_debug_gru_phase_clocks": [_P],
     "slu_intent_head_fwd": [_P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P],

@@ -21,6 +21,10 @@ SINC_IMPL = os.environ.get("SLU_SINC_IMPL", "tc")
 # Weight-gradient launches of one layer are independent of each other and of the input-gradient GEMM: they go to side
 # streams (forked after the producer kernel, joined before the autograd node returns), so the small grids share the GPU.
 OVERLAP = os.environ.get("SLU_OVERLAP", "1") != "0"
+# SLU_FUSED_BWD=1: one C-ABI call per GRU layer backward (slu_bigru_bwd_tc) instead of driving its launches one by one from
+# Python -- ~0.3 ms less host time per step.  Off by default: on a single GPU the step is GPU-bound and the A/B on one box
+# measured 2.98 ms (one call) vs 2.94 ms (launch by launch); it is meant for host-bound set-ups.
+FUSED_BWD = os.environ.get("SLU_FUSED_BWD", "0") != "0"
 
 
 class _Fork:
@@ -317,18 +321,32 @@ class BiGRU(torch.autograd.Function):
         n_ih, n_hh = 768 * I, 2 * 384 * H
         zbuf = torch.zeros((n_ih + n_hh if wg else 0) + 2 * 4 * H, device=dev, dtype=torch.float32)
         dbias = zbuf[-2 * 4 * H:].view(2, 4, H)
-        _lib.call("slu_gru_bwd_" + GRU_IMPL, _lib.ptr(gy), _lib.ptr(mask), _lib.ptr(y_full), _lib.ptr(stash), _lib.ptr(w_hh_cat),
-                  B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), _lib.ptr(dbias), _lib.stream())
         grads = [None] * 8
         fork = None
         if wg:
             dw_ih, dw_hh = zbuf[:n_ih].view(768, I), zbuf[n_ih:n_ih + n_hh].view(2, 384, H)
-            fork = _Fork(3)
-            wgrad_tc(dgx, 0, 768, 768, x, 0, I, I, B, T, dw_ih, 0, I, stream=fork.stream(0))
-            for d in range(2):          # dW_hh[d] = [dr,dz | dhn]^T . h_{t-1}  (h_{t+1} for the reverse direction), one launch
-                wgrad2_tc(dgx, d * 384, 768, 256, dhn, d * H, 256, 384, y_full, d * H, 256, H, B, T, dw_hh, d * 384 * H, H,
-                          shift0=1 if d else -1, stream=fork.stream(1 + d))
-        dx = matmul_nn(dgx.view(B * T, 768), w_ih_cat, ctx.img_nn).view(B, T, I) if ni[0] else None
+        if GRU_IMPL == "tc" and FUSED_BWD and _lib._prof is None:
+            # the whole launch sequence of the layer in one C-ABI call (csrc/bigru.cu); the per-launch path below is what the
+            # profiling pass uses, and the only one for the CUDA-core GRU variant
+            dx = torch.empty(B, T, I, device=dev, dtype=torch.float32) if ni[0] else None
+            img = None
+            if ni[0]:
+                img = ctx.img_nn if ctx.img_nn is not None else presplit(w_ih_cat, *_form_nn(w_ih_cat))
+            _lib.call("slu_bigru_bwd_tc", _lib.ptr(gy), _lib.ptr(mask), _lib.ptr(y_full), _lib.ptr(stash), _lib.ptr(w_hh_cat), _lib.ptr(x),
+                      I, None if img is None else img.data_ptr(), B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), _lib.ptr(dbias),
+                      dw_ih.data_ptr() if wg else None, dw_hh.data_ptr() if wg else None, _lib.ptr(dx), 1 if OVERLAP else 0,
+                      _lib.stream())
+            _lib.stats["calls"] += (3 if wg else 0) + (1 if ni[0] else 0)          # kernels launched beyond the first
+        else:
+            _lib.call("slu_gru_bwd_" + GRU_IMPL, _lib.ptr(gy), _lib.ptr(mask), _lib.ptr(y_full), _lib.ptr(stash), _lib.ptr(w_hh_cat),
+                      B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), _lib.ptr(dbias), _lib.stream())
+            if wg:
+                fork = _Fork(3)
+                wgrad_tc(dgx, 0, 768, 768, x, 0, I, I, B, T, dw_ih, 0, I, stream=fork.stream(0))
+                for d in range(2):      # dW_hh[d] = [dr,dz | dhn]^T . h_{t-1}  (h_{t+1} for the reverse direction), one launch
+                    wgrad2_tc(dgx, d * 384, 768, 256, dhn, d * H, 256, 384, y_full, d * H, 256, H, B, T, dw_hh, d * 384 * H, H,
+                              shift0=1 if d else -1, stream=fork.stream(1 + d))
+            dx = matmul_nn(dgx.view(B * T, 768), w_ih_cat, ctx.img_nn).view(B, T, I) if ni[0] else None
         if wg:
             db6 = dbias.index_select(1, _bias_gather(dev))                     # (dr, dz, dn | dr, dz, dhn) per direction
             for d in range(2):
@@ -336,7 +354,8 @@ class BiGRU(torch.autograd.Function):
                 grads[4 * d + 1] = dw_hh[d]
                 grads[4 * d + 2] = db6[d, :3].reshape(384)                     # b_ih
                 grads[4 * d + 3] = db6[d, 3:].reshape(384)                     # b_hh
-            fork.join()
+            if fork is not None:
+                fork.join()
         return (dx, *grads, None, None, None, None, None)
 
 

@@ -88,6 +88,15 @@ int slu_intent_head_bwd(const float* gloss, const float* feats, const float* W, 
                         const int* tstar, int B, int T, int C, const int* values_per_slot, int n_slots, float* dfeats, float* dW,
                         float* dbias, void* stream);
 
+/* Backward of one bidirectional GRU layer in one host call (the launch sequence of slu_gru_bwd_tc, slu_wgrad_tc (dW_ih),
+ * 2 x slu_wgrad2_tc (dW_hh per direction), slu_gemm_tc (dX) with the weight-gradient launches forked to side streams when
+ * overlap != 0).  x [B][T][I] = the layer input; w_ih_nn_img = slu_presplit_bf16 image of W_ih [768][I] read as the [K=768][N=I]
+ * operand (NULL with dx == NULL: no input gradient); dw_ih [768][I] and dw_hh [2][384][128] accumulate (NULL, NULL: no weight
+ * gradients); dgx [B][T][768] and dhn [B][T][256] are caller-provided scratch that holds the pre-activation gradients. */
+int slu_bigru_bwd_tc(const float* gy, const float* drop_mask, const float* y_full, const float* stash, const float* w_hh, const float* x,
+                     int I, const void* w_ih_nn_img, int B, int T, int ds, float* dgx, float* dhn, float* dbias, float* dw_ih,
+                     float* dw_hh, float* dx, int overlap, void* stream);
+
 /* Fork / join of independent launches (host-side stream plumbing, no kernels): after slu_stream_fork the n (<= 8)
  * streams returned in side_streams[] wait for everything queued on main_stream so far; after slu_stream_join work queued
  * on main_stream waits for everything queued on those n side streams.  Used to run one layer's weight-gradient GEMMs

@@ -201,12 +201,14 @@ def test_conv_block_tc_fwd_bwd(pkg, monkeypatch, B, T, Cin, Cout):
     assert rel_err(wc.grad.cpu(), w.grad) < GRAD_TOL and rel_err(bc.grad.cpu(), b.grad) < GRAD_TOL
 
 
-@pytest.mark.parametrize("mode,ftol,gtol", [("fp16", 2e-3, 1e-2), ("bf16x3-separate", FWD_TOL, GRAD_TOL)])
+@pytest.mark.parametrize("mode,ftol,gtol,fused", [("fp16", 2e-3, 1e-2, True), ("bf16x3-separate", FWD_TOL, GRAD_TOL, True),
+                                                  ("bf16x3", FWD_TOL, GRAD_TOL, False)])
 @pytest.mark.parametrize("B,T,I,ds", [(16, 40, 256, 2), (5, 23, 60, 1)])
-def test_bigru_alternative_operand_formats(pkg, monkeypatch, B, T, I, ds, mode, ftol, gtol):
+def test_bigru_alternative_operand_formats(pkg, monkeypatch, B, T, I, ds, mode, ftol, gtol, fused):
     """Other operand formats of the recurrence: one fp16 pass (looser per-layer tolerance) and the un-stacked three-pass
-    bf16 split (same tolerance as the default stacked form)."""
+    bf16 split (same tolerance as the default stacked form); and the launch-by-launch backward (the default is one C call)."""
     monkeypatch.setattr(pkg.ops, "GRU_IMPL", "tc")
+    monkeypatch.setattr(pkg.ops, "FUSED_BWD", fused)
     pkg.ops.set_gru_precision(mode)
     try:
         rs = np.random.RandomState(B + T)
