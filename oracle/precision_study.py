@@ -25,6 +25,11 @@ def mm(a, b, mode):
     if mode == "bf16x3":
         ah, bh = q_bf16(a), q_bf16(b); al, bl = q_bf16(a - ah), q_bf16(b - bh)
         return ah @ bh + (ah @ bl + al @ bh)
+    if mode == "bf16x4":   # all four partial products: what the GRU's N-stacked hi/lo operand tile computes (W_hi, W_lo) x [h_hi; h_lo]
+        ah, bh = q_bf16(a), q_bf16(b); al, bl = q_bf16(a - ah), q_bf16(b - bh)
+        return (ah @ bh + al @ bh) + (ah @ bl + al @ bl)
+    if mode == "fp16":     # single fp16 pass (the optional recurrence mode)
+        return a.half().float() @ b.half().float()
     if mode == "bf16x2":   # activation hi/lo, weights bf16 only
         ah = q_bf16(a); al = q_bf16(a - ah); bh = q_bf16(b)
         return ah @ bh + al @ bh
@@ -76,6 +81,7 @@ if __name__ == "__main__":
     print("ref max|logit| %.3f" % ref.abs().max())
     for modes in [("bf16",) * 3, ("tf32t",) * 3, ("tf32r",) * 3, ("bf16x2",) * 3, ("bf16x3",) * 3,
                   ("bf16x3", "bf16x3", "bf16"), ("bf16x3", "bf16x3", "tf32r"), ("bf16x3", "tf32r", "tf32r"),
-                  ("bf16x3", "bf16", "bf16x3"), ("bf16", "bf16x3", "bf16x3"), ("tf32r", "bf16x3", "bf16x3")]:
+                  ("bf16x3", "bf16", "bf16x3"), ("bf16", "bf16x3", "bf16x3"), ("tf32r", "bf16x3", "bf16x3"),
+                  ("bf16x3", "bf16x3", "bf16x4"), ("bf16x3", "bf16x3", "fp16")]:
         out = forward(x, p, *modes)
         print("conv=%-7s xw=%-7s hu=%-7s  rel err %.2e" % (*modes, ((out - ref).abs().max() / ref.abs().max()).item()))
