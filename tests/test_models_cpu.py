@@ -261,3 +261,31 @@ def test_premask_shapes_and_draw_order(monkeypatch):
     assert [c[0] for c in calls] == [(3, 401, 256), (3, 201, 256), (3, 101, 256), (3, 51, 256)]
     assert [c[1] for c in calls] == [0.5, 0.5, 0.25, 0.5]
     assert [tuple(m.shape) for m in m0] == [(3, 401, 256), (3, 201, 256)] and [tuple(m.shape) for m in m1] == [(3, 101, 256), (3, 51, 256)]
+
+
+def test_prefetcher_iteration_protocol_without_a_device(monkeypatch):
+    """loader.DevicePrefetcher's iteration logic (order, early close, loader exceptions surfacing in the consumer) for the in-line
+    and the helper-thread variant, with the device staging stubbed out (host logic only)."""
+    import importlib
+    ld = importlib.import_module("end-to-end-slu_b200").loader
+    monkeypatch.setattr(ld, "_copy_stream", lambda device: None)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(ld.DevicePrefetcher, "_stage", lambda self, batch, stream: (batch, "ready"))
+    monkeypatch.setattr(ld.DevicePrefetcher, "_hand_over", lambda self, staged: staged[0])
+    for background in (False, True):
+        mk = lambda it: ld.DevicePrefetcher(it, device="cuda:0", background=background)
+        assert list(mk([(i, i * i) for i in range(5)])) == [(i, i * i) for i in range(5)]
+        assert list(mk([])) == []
+
+        def bad():
+            yield (1, 1)
+            raise ValueError("boom")
+        try:
+            list(mk(bad()))
+            raised = False
+        except ValueError:
+            raised = True
+        assert raised
+        it = iter(mk([(i,) for i in range(100)]))
+        assert next(it) == (0,) and next(it) == (1,)
+        it.close()                                         # abandoning the epoch must not hang (helper thread joins)
