@@ -97,7 +97,7 @@ _default_drop_mask = _drop_mask
 
 def _premask(stacks, B, T, training, device):
     """Keep-masks of several GRU stacks ahead of time: the tensors are allocated on the current stream, the generator kernels
-    run on a library side stream (they overlap the conv blocks) and `join()` orders them before the first GRU.
+    run on a library side stream (next to the first x-projection GEMM) and `join()` orders them before the first recurrence.
     Returns ([masks per stack], join).  Same draw order as layer-by-layer generation."""
     shapes = []
     for rnns in stacks:
