@@ -289,3 +289,63 @@ def test_prefetcher_iteration_protocol_without_a_device(monkeypatch):
         it = iter(mk([(i,) for i in range(100)]))
         assert next(it) == (0,) and next(it) == (1,)
         it.close()                                         # abandoning the epoch must not hang (helper thread joins)
+
+
+def test_reference_trainer_drives_this_model_unchanged(reference, tmp_path, capsys):
+    """the UNMODIFIED reference `training.Trainer` (imported from the reference tree, resolving `from models
+    import ...` to this repo's models.py) trains this Model for an epoch of synthetic batches on the CPU; the same Trainer code
+    over the reference's own Model from the same seed must land on the same losses and the same updated parameters."""
+    import importlib.util
+    saved_data = sys.modules.get("data")
+    sys.path.insert(0, REF)
+    try:
+        sys.modules.pop("data", None)
+        sys.modules.pop("training", None)
+        for m in ("soundfile", "textgrid"):
+            sys.modules.setdefault(m, types.ModuleType(m))
+        training = importlib.import_module("training")            # reference/training.py: `from models import ...` -> OUR models
+    finally:
+        sys.path.remove(REF)
+    assert training.__file__.startswith(REF) and training.Model is models.Model
+    # the same Trainer source bound to the reference's own classes (isinstance(model, PretrainedModel) picks lr / folder)
+    spec = importlib.util.spec_from_file_location("training_ref", os.path.join(REF, "training.py"))
+    training_ref = importlib.util.module_from_spec(spec)
+    sys.modules["models"] = reference
+    try:
+        spec.loader.exec_module(training_ref)
+    finally:
+        sys.modules["models"] = models
+    assert training_ref.Model is reference.Model
+
+    class Loader(list):
+        pass
+
+    class FakeSLU:                      # Trainer.train only needs `.loader`; it is not an ASRDataset -> SLU branch
+        def __init__(self, batches):
+            self.loader = Loader(batches)
+    g = torch.Generator().manual_seed(5)
+    batches = [(0.1 * torch.randn(3, 8000, generator=g), torch.stack([torch.randint(0, v, (3,), generator=g) for v in (6, 14, 4)], 1))
+               for _ in range(3)]
+    out = {}
+    for name, mod, trainer_mod in (("new", models, training), ("ref", reference, training_ref)):
+        cfg = make_config("unfreeze_all_layers")
+        cfg.folder = str(tmp_path / name)
+        os.makedirs(os.path.join(cfg.folder, "training"))
+        torch.manual_seed(77)
+        m = mod.Model(cfg)
+        m.cpu(); m.is_cuda = False
+        for layer in list(m.pretrained_model.phoneme_layers) + list(m.pretrained_model.word_layers):
+            for q in layer.parameters():
+                q.requires_grad = True            # fully unfrozen, dropout active: one generator seed drives both runs
+        trainer = trainer_mod.Trainer(model=m, config=cfg)
+        torch.manual_seed(99)
+        acc, loss = trainer.train(FakeSLU(batches), print_interval=10 ** 9)
+        out[name] = (acc, loss, {k: v.detach().clone() for k, v in m.state_dict().items()})
+        assert os.path.isfile(os.path.join(cfg.folder, "training", "log.csv"))
+    capsys.readouterr()
+    (a_n, l_n, sd_n), (a_r, l_r, sd_r) = out["new"], out["ref"]
+    assert abs(l_n - l_r) < 1e-4 * abs(l_r) and a_n == a_r
+    for k in sd_r:
+        assert rel_err(sd_n[k], sd_r[k]) < 1e-4, k
+    if saved_data is not None:
+        sys.modules["data"] = saved_data
