@@ -27,6 +27,7 @@ SIGNATURES = {
     "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_bigru_bwd_tc": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
     "slu_set_gru_precision": [_I],
+    "slu_gru_rows_per_cta": [_I],
     "slu_debug_gru_phase_clocks": [_P],
     "slu_intent_head_fwd": [_P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "slu_intent_head_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P],
@@ -78,7 +79,7 @@ stats = {"calls": 0}        # number of C-ABI kernel launches issued by this pro
 _prof = None                # name -> [(start_event, end_event)] while profiling
 _prof_detail = None         # [(name, small-int args, start, end)] per launch, when asked for
 _fn = {}
-_HOST_ONLY = ("slu_h2d_async", "slu_h2d_ready", "slu_stream_fork", "slu_stream_join", "slu_set_gru_precision", "slu_debug_gru_phase_clocks")
+_HOST_ONLY = ("slu_gru_rows_per_cta", "slu_h2d_async", "slu_h2d_ready", "slu_stream_fork", "slu_stream_join", "slu_set_gru_precision", "slu_debug_gru_phase_clocks")
 
 
 def call(name, *args):

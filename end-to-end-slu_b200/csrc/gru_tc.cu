@@ -544,6 +544,7 @@ extern "C" int slu_set_gru_precision(int mode) {
 // Tile shape: the MMA is always N = 16 wide; NR of those columns carry real batch rows.  Small batches use fewer rows
 // per CTA so that more SMs share the latency-bound recurrence (B=256: NR=4 -> 128 CTAs), large batches fill all 16.
 static int pick_rows(int B) { return B >= 1184 ? 16 : (B >= 592 ? 8 : 4); }
+extern "C" int slu_gru_rows_per_cta(int B) { return pick_rows(B); }
 
 template <int NR, bool STASH, bool FULL>
 static void launch_fwd(dim3 grid, cudaStream_t st, const float* gx, const float* w_hh, const float* b_hh, const float* mask,

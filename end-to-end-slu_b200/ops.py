@@ -483,3 +483,14 @@ class IntentHead(torch.autograd.Function):
         _lib.call("slu_intent_head_bwd", _lib.ptr(g), _lib.ptr(feats), _lib.ptr(w), _lib.ptr(y), _lib.ptr(logits), _lib.ptr(tstar),
                   B, T, C, sl, len(slots), _lib.ptr(dfeats), zb.data_ptr(), zb[C * 2 * H:].data_ptr(), _lib.stream())
         return dfeats, zb[:C * 2 * H].view(C, 2 * H), zb[C * 2 * H:], None, None
+
+
+def gru_rows_per_cta(B):
+    """Batch rows one CTA of the tcgen05 recurrence carries (csrc/gru_tc.cu pick_rows, exported as slu_gru_rows_per_cta)."""
+    return int(_lib.load().slu_gru_rows_per_cta(int(B)))
+
+
+def gru_executed_flop_factor(B):
+    """Executed / algorithmic tensor-core flops of the recurrence: the N=16 tile carries NR rows, hi/lo stacked, x (W_hi, W_lo)."""
+    nr = gru_rows_per_cta(B)
+    return 32 // nr if nr < 16 else 3

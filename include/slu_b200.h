@@ -71,6 +71,8 @@ int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_f
  *   1 = one fp16 pass (11-bit operands; intent logits stay within the 1e-3 parity tolerance);
  *   2 = three separate bf16 passes on every tile (un-stacked form, for A/B checks). */
 int slu_set_gru_precision(int mode);
+/* Batch rows one CTA of slu_gru_{fwd,bwd}_tc carries for a batch of B utterances (4, 8 or 16; host-side query, no launch). */
+int slu_gru_rows_per_cta(int B);
 
 /* Developer tool: accumulate clock64() per step phase of slu_gru_fwd_tc (CTA 0, threads 0 and 128) into buf[2][8]. */
 int slu_debug_gru_phase_clocks(long long* buf);

@@ -37,7 +37,16 @@ cfg.values_per_slot = [6, 14, 4]
 cfg.num_phonemes = 42
 
 
+ONLY = set(filter(None, os.environ.get("GOLDEN_ONLY", "").split(",")))     # e.g. GOLDEN_ONLY=seq2seq regenerates one fixture
+
+
+def want(tag):
+    return not ONLY or tag in ONLY
+
+
 def save(name, **arrs):
+    if not want(name.split(".")[0].replace("golden_", "").replace("synth_", "").split("_")[0]) and not want(name):
+        return
     out = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()}
     np.savez_compressed(os.path.join(HERE, name), **out)
     print(name, {k: v.shape for k, v in out.items() if v.size > 1 and len(out) < 20})
@@ -163,4 +172,35 @@ named = dict(pm.named_parameters())
 save("golden_asr.npz", phoneme_loss=pl, word_loss=wl, phoneme_acc=pa, word_acc=wa, y_phoneme=yp, y_word=yw,
      phoneme_logits=ph_post, word_logits_sub=w_post[..., ::50], B=B, T=T,
      **{"gl2/" + k: v.grad.double().norm() for k, v in named.items() if v.grad is not None})
+
+# ---- 6. seq2seq intent module (Model.forward / Seq2SeqDecoder.forward + infer, models.py:381-651) -------------
+#      Weights: torch.manual_seed(21) default init of the reference Model itself -- the same seed reproduces them in
+#      models.Model on any box with this torch build (tests/test_models_cpu.py checks the init order is identical), so
+#      only outputs and a parameter checksum are stored.
+if want("seq2seq"):
+    import importlib
+    cfgmod = importlib.import_module("end-to-end-slu_b200.config")
+    scfg = cfgmod.read_config(os.path.join(ROOT, "configs", "seq2seq.cfg"))
+    scfg.pretraining_type = 0
+    scfg.num_phonemes = 42
+    scfg.Sy_intent = ["<sos>"] + list("abcdefghij {}:'\",") + ["<eos>"]
+    torch.manual_seed(21)
+    sm = ref_models.Model(scfg); sm.cpu(); sm.is_cuda = False
+    sm.eval()
+    S, U, Bs, Ts = len(scfg.Sy_intent), 7, 3, 8000
+    xb, _ = R.synthetic_batch(Bs, Ts, seed=31)
+    rs = np.random.RandomState(32)
+    idx = rs.randint(1, S - 1, size=(Bs, U)); idx[:, 0] = 0; idx[:, -1] = S - 1
+    yb = torch.nn.functional.one_hot(torch.from_numpy(idx.astype(np.int64)), S).float()
+    for q in sm.parameters():
+        q.requires_grad = True
+    loss, _ = sm(xb, yb)
+    loss.backward()
+    enc = sm.encoder(sm.pretrained_model.compute_features(xb))
+    log_p = sm.decoder(enc, yb)
+    scores, beam = sm.decoder.infer(enc, scfg.Sy_intent, B=4, y_lengths=[6])
+    named = dict(sm.named_parameters())
+    save("golden_seq2seq.npz", loss=loss, log_p=log_p, enc=enc, beam_scores=scores, beam_ids=beam.argmax(-1), idx=idx, B=Bs, T=Ts, U=U,
+         seed=21, bseed=31, param_abs_sum=sum(v.detach().double().abs().sum() for v in sm.state_dict().values()),
+         **{"gl2/" + k: v.grad.double().norm() for k, v in named.items() if v.grad is not None})
 print("done")

@@ -267,3 +267,113 @@ def test_weights_changed_in_place_are_seen_by_the_next_forward():
         l1, _ = m.predict_intents(x)
         assert rel_err(l1.cpu(), R.intent_logits(x, p2)) < LOGIT_TOL / 10
         assert rel_err(l1.cpu(), l0.cpu()) > 1e-3
+
+
+# ---- parity at the BENCHMARKED size (bench.py config 3: 256 x 64 000 samples per GPU) -------------------------------------
+def _grads(m):
+    return {k: q.grad.detach().double().clone() for k, q in m.named_parameters() if q.grad is not None}
+
+
+def test_benchmark_size_train_step_is_tied_to_the_oracle():
+    """The bench's shape (B=256 x 4 s: 128-CTA recurrence, multi-tile GEMMs, side-stream forks) has no CPU oracle that finishes in
+    seconds, so it is tied to the oracle in two links, dropout off, all 48 gradients:
+      (1) size-independent property: loss/gradients of the 256-utterance batch == mean over its eight 32-utterance
+          sub-batches (different CTA counts / tile shapes / tail tiles on every kernel);
+      (2) anchor at full utterance length: a 4-utterance sub-batch (rows 0..3 of the SAME input) against oracle autograd."""
+    p = R.synthetic_params(seed=4)
+    m = gpu_model(p)
+    for q in m.parameters():
+        q.requires_grad = True
+    x, y = R.synthetic_batch(256, 64000, seed=5)
+    xd, yd = x.cuda(), y.cuda()
+    m.zero_grad()
+    loss, _ = m(xd, yd)
+    loss.backward()
+    torch.cuda.synchronize()
+    full = _grads(m)
+    assert len(full) == 48
+    acc = {k: torch.zeros_like(v) for k, v in full.items()}
+    lsum = 0.0
+    for s in range(8):
+        m.zero_grad()
+        l, _ = m(xd[32 * s:32 * s + 32], yd[32 * s:32 * s + 32])
+        l.backward()
+        lsum += l.item() / 8
+        for k, v in _grads(m).items():
+            acc[k] += v / 8
+    assert abs(loss.item() - lsum) < 2e-5 * abs(lsum)
+    for k in full:
+        assert rel_err(full[k], acc[k]) < 1e-3, (k, rel_err(full[k], acc[k]))
+    # (2) oracle anchor at T = 64 000
+    m.zero_grad()
+    l4, _ = m(xd[:4], yd[:4])
+    l4.backward()
+    g4 = _grads(m)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    l_ref, _, lg_ref = R.slu_forward(x[:4], y[:4], pr)
+    l_ref.backward()
+    assert abs(l4.item() - l_ref.item()) < 1e-4 * abs(l_ref.item())
+    with torch.no_grad():
+        lg, _ = m.predict_intents(xd[:4])
+    assert rel_err(lg.cpu(), lg_ref.detach()) < LOGIT_TOL / 10
+    for k in g4:
+        assert rel_err(g4[k].cpu(), pr[k].grad) < GRAD_TOL, (k, rel_err(g4[k].cpu(), pr[k].grad))
+
+
+def test_frozen_encoder_gradients_match_the_oracle():
+    """BASELINE config 2 (freeze_all_layers): intent-module gradient VALUES against oracle autograd, nothing else gets a grad."""
+    p = R.synthetic_params(seed=2)
+    m = gpu_model(p)
+    m.freeze_all_layers()
+    x, y = R.synthetic_batch(5, 16000, seed=3)
+    loss, _ = m(x, y)
+    loss.backward()
+    pr = {k: v.clone().requires_grad_(k.startswith("intent_layers")) for k, v in p.items()}
+    l_ref, _, _ = R.slu_forward(x, y, pr)
+    l_ref.backward()
+    assert abs(loss.item() - l_ref.item()) < 1e-4 * abs(l_ref.item())
+    n = 0
+    for k, q in m.named_parameters():
+        if k.startswith("intent_layers"):
+            assert rel_err(q.grad.cpu(), pr[k].grad) < GRAD_TOL, k
+            n += 1
+        else:
+            assert q.grad is None, k
+    assert n == 10
+
+
+def test_seq2seq_model_on_gpu_matches_the_reference_golden():
+    """BASELINE config 5 against the REAL reference (tests/golden/make_golden.py section 6): same seed -> same default init,
+    teacher-forced loss, per-example log-likelihoods, encoder states, all gradients (L2 norms), best beam-search hypothesis."""
+    g = golden("golden_seq2seq.npz")
+    cfg = make_config("seq2seq")
+    cfg.Sy_intent = ["<sos>"] + list("abcdefghij {}:'\",") + ["<eos>"]
+    torch.manual_seed(int(g["seed"]))
+    m = models.Model(cfg).eval()
+    assert m.seq2seq and next(m.parameters()).is_cuda
+    psum = sum(v.detach().double().abs().sum().item() for v in m.state_dict().values())
+    assert abs(psum - float(g["param_abs_sum"])) < 1e-6 * psum            # identical initial weights
+    for q in m.parameters():
+        q.requires_grad = True
+    S = len(cfg.Sy_intent)
+    x, _ = R.synthetic_batch(int(g["B"]), int(g["T"]), seed=int(g["bseed"]))
+    y = torch.nn.functional.one_hot(torch.from_numpy(g["idx"].astype(np.int64)), S).float()
+    loss, _ = m(x, y)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-4 * float(g["loss"])
+    named = dict(m.named_parameters())
+    n = 0
+    for k in g.files:
+        if k.startswith("gl2/"):
+            ref = float(g[k])
+            assert abs(named[k[4:]].grad.double().norm().item() - ref) < GRAD_TOL * ref + 1e-9, k
+            n += 1
+    assert n >= 60
+    with torch.no_grad():
+        enc = m.encoder(m.pretrained_model.compute_features(x))
+        assert rel_err(enc.cpu(), g["enc"]) < LOGIT_TOL / 10
+        log_p = m.decoder(enc, y.cuda())
+        assert rel_err(log_p.cpu(), g["log_p"]) < 1e-4
+        scores, beam = m.decoder.infer(enc, cfg.Sy_intent, B=4, y_lengths=[6])
+    assert rel_err(scores.cpu(), g["beam_scores"]) < 1e-4
+    assert np.array_equal(beam.argmax(-1)[0].cpu().numpy(), g["beam_ids"][0])

@@ -349,3 +349,25 @@ def test_reference_trainer_drives_this_model_unchanged(reference, tmp_path, caps
         assert rel_err(sd_n[k], sd_r[k]) < 1e-4, k
     if saved_data is not None:
         sys.modules["data"] = saved_data
+
+
+def test_seq2seq_cpu_path_matches_the_reference_golden():
+    """config 5 without the reference tree (GPU box): same seed -> same default init (checksum), then the teacher-forced loss,
+    log-likelihoods and the best beam hypothesis of the reference's Model (tests/golden/make_golden.py section 6)."""
+    g = golden("golden_seq2seq.npz")
+    cfg = make_config("seq2seq")
+    cfg.Sy_intent = ["<sos>"] + list("abcdefghij {}:'\",") + ["<eos>"]
+    torch.manual_seed(int(g["seed"]))
+    m = cpu_model(cfg).eval()
+    psum = sum(v.detach().double().abs().sum().item() for v in m.state_dict().values())
+    assert abs(psum - float(g["param_abs_sum"])) < 1e-9 * psum
+    from oracle import torch_ref as R
+    x, _ = R.synthetic_batch(int(g["B"]), int(g["T"]), seed=int(g["bseed"]))
+    y = torch.nn.functional.one_hot(torch.from_numpy(g["idx"].astype(np.int64)), len(cfg.Sy_intent)).float()
+    with torch.no_grad():
+        loss, _ = m(x, y)
+        enc = m.encoder(m.pretrained_model.compute_features(x))
+        scores, beam = m.decoder.infer(enc, cfg.Sy_intent, B=4, y_lengths=[6])
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * float(g["loss"])
+    assert rel_err(enc, g["enc"]) < 2e-5 and rel_err(scores, g["beam_scores"]) < 1e-5
+    assert np.array_equal(beam.argmax(-1).numpy(), g["beam_ids"])
