@@ -22,10 +22,10 @@ SIGNATURES = {
     "slu_sincconv_fwd_tc": [_P, _P, _I, _I, _P, _P, _P, _P],
     "slu_sincconv_bwd_tc": [_P, _P, _P, _I, _I, _P, _P],
     "slu_gru_fwd_simt": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
-    "slu_gru_bwd_simt": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "slu_gru_bwd_simt": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "slu_gru_fwd_tc": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
-    "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
-    "slu_bigru_bwd_tc": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
+    "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "slu_bigru_bwd_tc": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "slu_set_gru_precision": [_I],
     "slu_gru_rows_per_cta": [_I],
     "slu_debug_gru_phase_clocks": [_P],
@@ -33,6 +33,8 @@ SIGNATURES = {
     "slu_intent_head_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P],
     "slu_h2d_async": [_P, _P, ctypes.c_size_t, _P, _I],
     "slu_h2d_ready": [_P],
+    "slu_h2d_pending": [_P],
+    "slu_h2d_wait": [],
     "slu_stream_fork": [_P, _I, _P],
     "slu_stream_join": [_P, _I],
     "slu_dropout_mask": [_P, _L, _F, ctypes.c_ulonglong, _P],
@@ -42,6 +44,9 @@ SIGNATURES = {
     "slu_presplit_multi": [_P, _I, _P],
     "slu_wgrad2_tc": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P],
     "slu_wgrad_tc": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P],
+    "slu_adam_multi": [_P, _I, _F, _F, _F, _F, _P],
+    "slu_f64_hilo_split": [_P, _P, _P, _I, _P],
+    "slu_f64_hilo_merge": [_P, _P, _P, _I, _P],
     "slu_tc_selftest": [_P, _P, _P, _I, _I, _P],
     "slu_tc_selftest_ts": [_P, _P, _P, _I, _I, _P],
 }
@@ -75,11 +80,12 @@ def stream():
     return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
+ERR_TOO_LARGE = 100001      # SLU_ERR_TOO_LARGE in include/slu_b200.h
 stats = {"calls": 0}        # number of C-ABI kernel launches issued by this process
 _prof = None                # name -> [(start_event, end_event)] while profiling
 _prof_detail = None         # [(name, small-int args, start, end)] per launch, when asked for
 _fn = {}
-_HOST_ONLY = ("slu_gru_rows_per_cta", "slu_h2d_async", "slu_h2d_ready", "slu_stream_fork", "slu_stream_join", "slu_set_gru_precision", "slu_debug_gru_phase_clocks")
+_HOST_ONLY = ("slu_gru_rows_per_cta", "slu_h2d_async", "slu_h2d_ready", "slu_h2d_pending", "slu_h2d_wait", "slu_stream_fork", "slu_stream_join", "slu_set_gru_precision", "slu_debug_gru_phase_clocks")
 
 
 def call(name, *args):
@@ -100,6 +106,9 @@ def call(name, *args):
     else:
         err = fn(*args)
     if err != 0:
+        if err == ERR_TOO_LARGE:
+            raise RuntimeError("slu_b200: %s: a size exceeds the kernel's 32-bit index range (the GRU kernels take B*T < 2^21 "
+                               "frames per launch) -- split the batch" % name)
         raise RuntimeError("slu_b200: %s failed with cudaError %d" % (name, err))
 
 

@@ -2,7 +2,7 @@
 // Python (autograd of nn.GRU at reference models.py:232/262/686).  Nothing new runs on the device -- it is the same kernels in
 // the same order -- but the host pays one C-ABI call per layer instead of eight, which matters because a train step is only a
 // few hundred microseconds away from being host-bound (multi-GPU runs, per-step result reads).
-//   1. slu_gru_bwd_tc            recurrence backward -> dgx [B][T][768], dhn [B][T][256], dbias
+//   1. slu_gru_bwd_tc            recurrence backward -> dgx [B][T][768], dhn [B][T][256], db_ih / db_hh
 //   2. fork: slu_wgrad_tc        dW_ih = dgx^T . x                      (side stream 0)
 //            slu_wgrad2_tc x2    dW_hh[d] = [dr,dz | dhn]^T . h_{t-+1}  (side streams 1, 2)
 //   3. slu_gemm_tc               dX = dgx . W_ih (pre-split operand image), on the caller's stream
@@ -12,11 +12,11 @@
 
 extern "C" int slu_bigru_bwd_tc(const float* gy, const float* drop_mask, const float* y_full, const float* stash, const float* w_hh,
                                 const float* x, int I, const void* w_ih_nn_img, int B, int T, int ds, float* dgx, float* dhn,
-                                float* dbias, float* dw_ih, float* dw_hh, float* dx, int overlap, void* stream) {
+                                float* db_ih, float* db_hh, float* dw_ih, float* dw_hh, float* dx, int overlap, void* stream) {
   if (B <= 0 || T <= 0 || I <= 0 || !dgx || !dhn) return (int)cudaErrorInvalidValue;
   if (dx && !w_ih_nn_img) return (int)cudaErrorInvalidValue;
   if ((dw_ih == nullptr) != (dw_hh == nullptr)) return (int)cudaErrorInvalidValue;
-  int e = slu_gru_bwd_tc(gy, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, dbias, stream);
+  int e = slu_gru_bwd_tc(gy, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh, stream);
   if (e) return e;
   void* side[3] = {stream, stream, stream};
   const int ns = (dw_ih && overlap) ? 3 : 0;

@@ -330,8 +330,7 @@ int sm_count() {
 template <int BN>
 int launch(const GemmParams& p, cudaStream_t stream) {
   const size_t smem = Smem<BN>::TOTAL;
-  static int attr = slu_set_smem((const void*)gemm_tc_kernel<BN>, smem);
-  if (attr) return attr;
+  SLU_SMEM_ONCE(gemm_tc_kernel<BN>, smem);
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<BN><<<grid, THREADS, smem, stream>>>(p);

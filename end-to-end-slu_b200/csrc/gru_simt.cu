@@ -125,7 +125,7 @@ gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, con
 __global__ void __launch_bounds__(512, 1)
 gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, const float* __restrict__ y_full,
                const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds,
-               float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ dbias) {
+               float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ db_ih, float* __restrict__ db_hh) {
   extern __shared__ float4 smem4[];
   float4* Wt = smem4;                                          // [c*128 + k] = W[4c..4c+3][k], c < 96
   float* gs = reinterpret_cast<float*>(smem4 + 96 * 128);      // [2][BT][384]
@@ -200,9 +200,11 @@ gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask,
     cur_in = nxt_in;
     cur ^= 1;
   }
-  if (dbias) {
-    float* pb = dbias + d * 512 + j;
-    atomicAdd(pb, sb_r); atomicAdd(pb + 128, sb_z); atomicAdd(pb + 256, sb_n); atomicAdd(pb + 384, sb_hn);
+  if (db_ih) {                   // parameter layout [2][384]: b_ih <- (dr, dz, dn), b_hh <- (dr, dz, dhn)
+    float* pa = db_ih + d * SLU_G3 + j;
+    float* pb = db_hh + d * SLU_G3 + j;
+    atomicAdd(pa, sb_r); atomicAdd(pa + 128, sb_z); atomicAdd(pa + 256, sb_n);
+    atomicAdd(pb, sb_r); atomicAdd(pb + 128, sb_z); atomicAdd(pb + 256, sb_hn);
   }
 }
 
@@ -212,9 +214,8 @@ extern "C" int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float*
                                 int ds, float* y_full, float* y_out, float* stash, void* stream) {
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2)) return (int)cudaErrorInvalidValue;
   const size_t smem = W_SMEM + 2 * BT * SLU_H * sizeof(float);
-  static int a1 = slu_set_smem((const void*)gru_fwd_kernel<true>, smem);
-  static int a2 = slu_set_smem((const void*)gru_fwd_kernel<false>, smem);
-  if (a1 || a2) return a1 ? a1 : a2;
+  SLU_SMEM_ONCE(gru_fwd_kernel<true>, smem);
+  SLU_SMEM_ONCE(gru_fwd_kernel<false>, smem);
   dim3 grid((B + BT - 1) / BT, 2);
   if (stash) gru_fwd_kernel<true><<<grid, 512, smem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, stash);
   else gru_fwd_kernel<false><<<grid, 512, smem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, nullptr);
@@ -223,13 +224,12 @@ extern "C" int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float*
 }
 
 extern "C" int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                                const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* dbias, void* stream) {
-  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2)) return (int)cudaErrorInvalidValue;
+                                const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh, void* stream) {
+  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (db_ih == nullptr) != (db_hh == nullptr)) return (int)cudaErrorInvalidValue;
   const size_t smem = W_SMEM + 2 * BT * SLU_G3 * sizeof(float);
-  static int a1 = slu_set_smem((const void*)gru_bwd_kernel, smem);
-  if (a1) return a1;
+  SLU_SMEM_ONCE(gru_bwd_kernel, smem);
   dim3 grid((B + BT - 1) / BT, 2);
-  gru_bwd_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, dbias);
+  gru_bwd_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh);
   SLU_CHECK_LAUNCH();
   return 0;
 }

@@ -334,7 +334,7 @@ template <int NB, int NR, bool FULL, int PASSES>
 __global__ void __launch_bounds__(block_threads(NR), 1)
 gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, const float* __restrict__ y_full,
                   const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds, int tile0,
-                  float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ dbias) {
+                  float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ db_ih, float* __restrict__ db_hh) {
   constexpr int NC = NR * 128 / TC_THREADS;
   constexpr uint32_t LBO = NB * 16 + 16;
   __shared__ __align__(128) uint8_t g_tile[2 * 48 * LBO];   // [hi | lo] x 48 k-chunks (384 gate rows)
@@ -515,9 +515,11 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
       off[c] += dt * 256;
     }
   }
-  if (dbias && is_compute) {     // dbias[d][4][128]: sums of dr, dz, dn (-> b_ih and b_hh r/z rows), dhn (-> b_hh n rows)
-    float* pb = dbias + d * 512 + j;
-    atomicAdd(pb, sb_r); atomicAdd(pb + 128, sb_z); atomicAdd(pb + 256, sb_n); atomicAdd(pb + 384, sb_hn);
+  if (db_ih && is_compute) {     // bias gradients in the parameters' own layout [2][384]: b_ih <- (dr, dz, dn), b_hh <- (dr, dz, dhn)
+    float* pa = db_ih + d * SLU_G3 + j;
+    float* pb = db_hh + d * SLU_G3 + j;
+    atomicAdd(pa, sb_r); atomicAdd(pa + 128, sb_z); atomicAdd(pa + 256, sb_n);
+    atomicAdd(pb, sb_r); atomicAdd(pb + 128, sb_z); atomicAdd(pb + 256, sb_hn);
   }
   fence_before_sync();
   __syncthreads();
@@ -576,7 +578,8 @@ static void run_fwd(cudaStream_t st, const float* gx, const float* w_hh, const f
 
 extern "C" int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T,
                               int ds, float* y_full, float* y_out, float* stash, void* stream) {
-  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (long)B * T * 1024 >= (1L << 31)) return (int)cudaErrorInvalidValue;
+  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2)) return (int)cudaErrorInvalidValue;
+  if ((long)B * T * 1024 >= (1L << 31)) return SLU_ERR_TOO_LARGE;
   cudaStream_t st = (cudaStream_t)stream;
   switch (pick_rows(B)) {
     case 16: run_fwd<16>(st, gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, stash); break;
@@ -589,34 +592,35 @@ extern "C" int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b
 
 template <int NR, bool FULL>
 static void launch_bwd(dim3 grid, cudaStream_t st, const float* dy_out, const float* mask, const float* y_full, const float* stash,
-                       const float* w_hh, int B, int T, int ds, int tile0, float* dgx, float* dhn, float* dbias) {
+                       const float* w_hh, int B, int T, int ds, int tile0, float* dgx, float* dhn, float* db_ih, float* db_hh) {
   constexpr size_t smem = (size_t)BWD_RING * NR * 896 * sizeof(float);
   constexpr int P = 2 * NR <= 16 ? 2 : 3;
   static int a3 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, 3>, smem);
   static int a2 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, P>, smem);
   static int a1 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, 1>, smem);
   (void)a3; (void)a2; (void)a1;
-  if (g_gru_mode == 0) gru_bwd_tc_kernel<16, NR, FULL, P><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
-  else if (g_gru_mode == 2) gru_bwd_tc_kernel<16, NR, FULL, 3><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
-  else gru_bwd_tc_kernel<16, NR, FULL, 1><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, dbias);
+  if (g_gru_mode == 0) gru_bwd_tc_kernel<16, NR, FULL, P><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
+  else if (g_gru_mode == 2) gru_bwd_tc_kernel<16, NR, FULL, 3><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
+  else gru_bwd_tc_kernel<16, NR, FULL, 1><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
 }
 
 template <int NR>
 static void run_bwd(cudaStream_t st, const float* dy_out, const float* mask, const float* y_full, const float* stash, const float* w_hh,
-                    int B, int T, int ds, float* dgx, float* dhn, float* dbias) {
+                    int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh) {
   const int full = B / NR, rem = B % NR;
-  if (full) launch_bwd<NR, true>(dim3(full, 2), st, dy_out, mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn, dbias);
-  if (rem) launch_bwd<NR, false>(dim3(1, 2), st, dy_out, mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn, dbias);
+  if (full) launch_bwd<NR, true>(dim3(full, 2), st, dy_out, mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn, db_ih, db_hh);
+  if (rem) launch_bwd<NR, false>(dim3(1, 2), st, dy_out, mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn, db_ih, db_hh);
 }
 
 extern "C" int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                              const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* dbias, void* stream) {
-  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (long)B * T * 1024 >= (1L << 31)) return (int)cudaErrorInvalidValue;
+                              const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh, void* stream) {
+  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (db_ih == nullptr) != (db_hh == nullptr)) return (int)cudaErrorInvalidValue;
+  if ((long)B * T * 1024 >= (1L << 31)) return SLU_ERR_TOO_LARGE;
   cudaStream_t st = (cudaStream_t)stream;
   switch (pick_rows(B)) {
-    case 16: run_bwd<16>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, dbias); break;
-    case 8: run_bwd<8>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, dbias); break;
-    default: run_bwd<4>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, dbias); break;
+    case 16: run_bwd<16>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh); break;
+    case 8: run_bwd<8>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh); break;
+    default: run_bwd<4>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh); break;
   }
   SLU_CHECK_LAUNCH();
   return 0;

@@ -81,9 +81,11 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
       if (lg[c] > m) { m = lg[c]; am = c; }
     float se = 0.f;
     for (int c = s0; c < s1; ++c) se += expf(lg[c] - m);
-    const int target = s0 + (int)y[(long)b * slots.n_slots + tid];
-    slot_loss[tid] = (m + logf(se)) - lg[target];
-    slot_ok[tid] = am == target;
+    const long long yv = y[(long)b * slots.n_slots + tid];
+    const bool in_range = yv >= 0 && yv < (long long)(s1 - s0);      // F.cross_entropy would device-assert; here the loss turns NaN
+    const int target = s0 + (in_range ? (int)yv : 0);
+    slot_loss[tid] = in_range ? (m + logf(se)) - lg[target] : __int_as_float(0x7fc00000);
+    slot_ok[tid] = in_range && am == target;
   }
   __syncthreads();
   if (tid == 0) {
@@ -127,10 +129,12 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   const int tid = threadIdx.x;
   for (int i = tid; i < C * HEAD_F; i += 256) dw_s[i] = 0.f;
   float db = 0.f;
-  const float g = gloss[0] / (float)B;
+  const float g = y ? gloss[0] / (float)B : 0.f;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
-    if (tid < slots.n_slots) {
+    if (y == nullptr) {                      // logits-only head (predict path): `gloss` is dL/dlogits [B][C]
+      if (tid < C) dl[tid] = gloss[(long)b * C + tid];
+    } else if (tid < slots.n_slots) {
       const int s0 = slots.start[tid], s1 = slots.start[tid + 1];
       const float* lg = logits + (long)b * C;
       float m = lg[s0];
@@ -138,8 +142,10 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       float se = 0.f;
       for (int c = s0; c < s1; ++c) se += expf(lg[c] - m);
       const float inv = 1.f / se;
-      const int target = s0 + (int)y[(long)b * slots.n_slots + tid];
-      for (int c = s0; c < s1; ++c) dl[c] = g * (expf(lg[c] - m) * inv - (c == target ? 1.f : 0.f));
+      const long long yv = y[(long)b * slots.n_slots + tid];
+      const float poison = (yv >= 0 && yv < (long long)(s1 - s0)) ? 0.f : __int_as_float(0x7fc00000);   // out-of-range label -> NaN grads
+      const int target = s0 + (int)yv;
+      for (int c = s0; c < s1; ++c) dl[c] = g * (expf(lg[c] - m) * inv - (c == target ? 1.f : 0.f)) + poison;
     }
     if (tid < C) ts[tid] = tstar[(long)b * C + tid];
     __syncthreads();
@@ -178,7 +184,8 @@ extern "C" int slu_intent_head_fwd(const float* feats, const float* W, const flo
   SlotTable st;
   if (int e = make_slots(values_per_slot, n_slots, C, &st)) return e;
   const size_t smem = sizeof(float) * ((size_t)((C * 257 + 3) & ~3) + HEAD_TT * HEAD_F + (size_t)HEAD_TT * C + HEAD_MAXC);
-  if (int e = slu_set_smem((const void*)head_fwd_kernel, smem)) return e;
+  if (smem > 48 * 1024)
+    if (int e = slu_set_smem((const void*)head_fwd_kernel, smem)) return e;
   head_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(feats, W, bias, y, B, T, C, st, logits, tstar, row_loss, row_ok, loss_acc,
                                                           ticket);
   SLU_CHECK_LAUNCH();
@@ -192,7 +199,8 @@ extern "C" int slu_intent_head_bwd(const float* gloss, const float* feats, const
   SlotTable st;
   if (int e = make_slots(values_per_slot, n_slots, C, &st)) return e;
   const size_t smem = sizeof(float) * ((size_t)C * HEAD_F + HEAD_MAXC) + sizeof(int) * HEAD_MAXC;
-  if (int e = slu_set_smem((const void*)head_bwd_kernel, smem)) return e;
+  if (smem > 48 * 1024)
+    if (int e = slu_set_smem((const void*)head_bwd_kernel, smem)) return e;
   const int grid = B < 148 ? B : 148;
   head_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(gloss, feats, W, y, logits, tstar, B, T, C, st, dfeats, dW, dbias);
   SLU_CHECK_LAUNCH();

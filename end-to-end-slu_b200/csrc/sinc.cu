@@ -237,8 +237,7 @@ extern "C" int slu_sincconv_fwd_simt(const float* x, const float* W, int B, int 
   if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
   const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
   const size_t smem = (5504 + SC_HALF * SLU_NFILT) * sizeof(float);
-  static int attr_done = slu_set_smem((const void*)sincconv_fwd_kernel, smem);
-  if (attr_done) return attr_done;
+  SLU_SMEM_ONCE(sincconv_fwd_kernel, smem);
   dim3 grid((L1 + SC_TP - 1) / SC_TP, B);
   sincconv_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, W, B, T, L0, L1, out, route);
   SLU_CHECK_LAUNCH();

@@ -334,8 +334,7 @@ extern "C" int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T,
   const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
   int e = slu_presplit_rows_cm(W, SLU_NTAPS, 1, SLU_STRIDE, 6, SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // bank[c][80a + k], 0 beyond tap 400
   if (e) return e;
-  static int attr = slu_set_smem((const void*)sincconv_fwd_tc_kernel, FWD_SMEM);
-  if (attr) return attr;
+  SLU_SMEM_ONCE(sincconv_fwd_tc_kernel, FWD_SMEM);
   dim3 grid((L0 + TF - 1) / TF, B);
   sincconv_fwd_tc_kernel<<<grid, THREADS, FWD_SMEM, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)img, T, L0, L1, out, route);
   SLU_CHECK_LAUNCH();
@@ -347,8 +346,7 @@ extern "C" int slu_sincconv_bwd_tc(const float* x, const float* gy, const uint8_
   if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
   const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
   const int tiles_per_utt = (L0 + TF - 1) / TF;
-  static int attr = slu_set_smem((const void*)sincconv_bwd_tc_kernel, BWD_SMEM);
-  if (attr) return attr;
+  SLU_SMEM_ONCE(sincconv_bwd_tc_kernel, BWD_SMEM);
   const long n_tiles = (long)B * tiles_per_utt;
   const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
   sincconv_bwd_tc_kernel<<<grid, THREADS, BWD_SMEM, (cudaStream_t)stream>>>(x, gy, route, B, T, L0, L1, tiles_per_utt, dW);

@@ -98,3 +98,31 @@ extern "C" int slu_h2d_ready(void* consumer_stream) {
   if (e != cudaSuccess) return (int)e;
   return (int)cudaStreamWaitEvent((cudaStream_t)consumer_stream, p->copy_done, 0);
 }
+
+// *pending = 1 while copies queued with slu_h2d_async are still in flight on the copy stream (their pinned sources must stay
+// alive until then), 0 once all have completed.  Never blocks.
+extern "C" int slu_h2d_pending(int* pending) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  Pool* p = nullptr;
+  if (int err = get_pool(&p)) return err;
+  const cudaError_t e = cudaStreamQuery(p->copy);
+  if (e == cudaErrorNotReady) {
+    (void)cudaGetLastError();
+    *pending = 1;
+    return 0;
+  }
+  *pending = 0;
+  return (int)e;
+}
+
+// Block the calling host thread until every copy queued with slu_h2d_async has completed (end of an epoch / teardown).
+extern "C" int slu_h2d_wait(void) {
+  cudaStream_t s;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    Pool* p = nullptr;
+    if (int err = get_pool(&p)) return err;
+    s = p->copy;
+  }
+  return (int)cudaStreamSynchronize(s);
+}

@@ -282,8 +282,7 @@ int sm_count_w() {
 template <int MT, int NCH, int NTAPS>
 int launch(const WgradParams& p, cudaStream_t st) {
   using C = Cfg<MT, NCH, NTAPS>;
-  static int attr = slu_set_smem((const void*)wgrad_tc_kernel<MT, NCH, NTAPS>, C::TOTAL);
-  if (attr) return attr;
+  SLU_SMEM_ONCE((wgrad_tc_kernel<MT, NCH, NTAPS>), C::TOTAL);
   const int m_groups = (p.m_valid + C::MC - 1) / C::MC, n_groups = (p.n_valid + C::N - 1) / C::N;
   const long n_tiles = (long)p.B * p.tiles_per_utt;
   int gx = sm_count_w() / (m_groups * n_groups);        // CTAs per output block: fill the SMs ...

@@ -6,13 +6,17 @@ its shard's mean loss, and the mean over ranks is the global-batch gradient (equ
 
 `install()` registers a global optimizer pre-step hook (torch.optim.optimizer.register_optimizer_step_pre_hook),
 so the reference's Trainer (`loss.backward(); optimizer.step()`, training.py:65-66/97-98) needs no change:
-the hook packs every existing `.grad` (fp64 sinc grads are carried as fp32 pairs hi/lo to stay inside the
-single fp32 bucket), issues one NCCL all-reduce on the current stream, and unpacks scaled by 1/world.
+on the CUDA path every `.grad` is a view of ONE flat arena (grads.py) that the weight-gradient kernels wrote into, so the hook
+all-reduces that buffer in place (NCCL AVG) -- no pack / unpack; the fp64 sinc grads cross the fp32 collective as (hi, lo) float
+pairs.  Gradients that are not arena views (CPU / gloo runs, modules executed by torch ops such as the seq2seq decoder) take the
+generic path: pack into a cached flat bucket, one all-reduce, unpack.
 Parameters whose `.grad` is None (frozen layers, the unused ASR heads) are skipped; the set is re-derived
 each step, which follows `unfreeze_one_layer()` for free.  All ranks must agree on that set.
 """
 import torch
 import torch.distributed as dist
+
+from . import _lib, grads as grads_mod
 
 _installed = False
 stats = {"allreduce_calls": 0, "bucket_bytes": 0}
@@ -69,6 +73,22 @@ def allreduce_grads(params, group=None):
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return 0
+    arena = grads_mod.find(grads[0]) if grads[0].is_cuda else None
+    if arena is not None and all(arena.owns(g) for g in grads):
+        # Every gradient is a view of this backward pass's arena (grads.py): the buffer IS the bucket -- no pack, no unpack.
+        # The fp64 SincNet gradients sit at its front; they cross the fp32 collective as (hi, lo) float pairs staged behind
+        # them (2 tiny launches), and the merge overwrites whatever the collective made of the raw fp64 words.
+        flat = arena.flat
+        if arena.n64:
+            d, hi, lo = arena.f64_region()
+            _lib.call("slu_f64_hilo_split", d.data_ptr(), hi.data_ptr(), lo.data_ptr(), arena.n64, _lib.stream())
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+        if arena.n64:
+            _lib.call("slu_f64_hilo_merge", d.data_ptr(), hi.data_ptr(), lo.data_ptr(), arena.n64, _lib.stream())
+        stats["allreduce_calls"] += 1
+        stats["bucket_bytes"] = flat.numel() * 4
+        stats["arena"] = stats.get("arena", 0) + 1
+        return stats["bucket_bytes"]
     if _bucket is None or _bucket.key != _key(grads):
         _bucket = _Bucket(grads)
     _bucket.pack(grads)

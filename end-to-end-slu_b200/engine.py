@@ -9,7 +9,7 @@ import os
 
 import torch
 
-from . import _lib, ops
+from . import _lib, grads, ops
 
 
 # One weight-image launch per forward (slu_presplit_multi) instead of one per GEMM; SLU_MULTI_PRESPLIT=0 restores the latter (A/B).
@@ -48,6 +48,7 @@ class Plan:
                 _require(l.kernel_size[0] % 2 == 1 and l.stride[0] == 1 and l.padding[0] == l.kernel_size[0] // 2,
                          "conv layers must be odd-k, stride 1, same padding")
                 _require(_pool_len(layers[i + 1]) == 1, "cnn_max_pool_len[1:] must be 1")
+                _require(l.out_channels % 4 == 0 and l.in_channels % 4 == 0, "conv channel counts must be multiples of 4")
                 act = layers[i + 2]
                 slope = act.negative_slope if isinstance(act, torch.nn.LeakyReLU) else 0.0
                 _require(layers[i + 3].p == 0.0, "cnn_drop must be 0")
@@ -165,52 +166,54 @@ def _run_rnns(out, rnns, training, masks=None, join=None, imgs=None):
     return out
 
 
-def phoneme_features(pm, x):
-    """[B,T] waveform -> [B, ceil(T/640), 256] (output of the phoneme module)."""
+def phoneme_features(pm, x, with_word=True):
+    """[B,T] waveform -> ([B, ceil(T/640), 256] output of the phoneme module, carry).  `carry` = what was prepared in the same
+    pass for the word module that follows (its dropout masks and weight operand images), handed to word_features() explicitly;
+    with_word=False (phoneme-only pre-training, models.py:243) prepares nothing for it."""
     plan = pm._plan
     _require(plan.sinc is not None, "use_sincnet must be True")
+    grads.begin(x.device)            # a new forward pass: its weight gradients will share one flat arena (grads.py)
     out = ops.SincFrontend.apply(x, plan.sinc.filt_b1, plan.sinc.filt_band)      # [B, L1, 80] (LeakyReLU is identity on >=0)
     for conv, slope in plan.convs:
         out = ops.conv_block(out, conv.weight, conv.bias, slope)
     # W_ih operand images of both GRU stacks in one launch, queued while the GPU is busy with the front end (an A/B on the same
     # box showed that making them -- and the conv images -- BEFORE the front end costs more host time in the idle gap at the
     # start of a step than the saved launches are worth)
-    _, gru_imgs = _weight_images([], plan.phone + plan.word)
+    word = plan.word if with_word else []
+    _, gru_imgs = _weight_images([], plan.phone + word)
     # Masks of the phoneme AND word stacks: queued on a side stream once the front end is in flight (the host prepares them
     # while the GPU is busy), they run next to the first x-projection GEMM and are joined right before the first recurrence.
-    (m_phone, m_word), join = _premask([plan.phone, plan.word], out.shape[0], out.shape[1], pm.training, out.device)
+    (m_phone, m_word), join = _premask([plan.phone, word], out.shape[0], out.shape[1], pm.training, out.device)
     out = _run_rnns(out, plan.phone, pm.training, m_phone, join, gru_imgs[:len(plan.phone)])
-    pm._word_masks = (m_word, out.shape[0], out.shape[1]) if pm.training else None
-    pm._word_imgs = gru_imgs[len(plan.phone):]
-    return out
+    carry = (m_word if pm.training else None, gru_imgs[len(plan.phone):]) if with_word else None
+    return out, carry
 
 
-def word_features(pm, ph):
-    pending, pm._word_masks = getattr(pm, "_word_masks", None), None
-    masks = pending[0] if pending is not None and pm.training and pending[1:] == (ph.shape[0], ph.shape[1]) else None
-    imgs, pm._word_imgs = getattr(pm, "_word_imgs", None), None      # made together with the phoneme stack's (same forward pass)
-    return _run_rnns(ph, pm._plan.word, pm.training, masks, None, imgs if imgs and len(imgs) == len(pm._plan.word) else None)
+def word_features(pm, ph, carry=None):
+    """Word module on the phoneme module's output; `carry` comes from the phoneme_features() call that produced `ph`."""
+    masks, imgs = carry if carry is not None else (None, None)
+    return _run_rnns(ph, pm._plan.word, pm.training, masks, None, imgs)
 
 
 def compute_features(pm, x):
-    return word_features(pm, phoneme_features(pm, x))
+    ph, carry = phoneme_features(pm, x)
+    return word_features(pm, ph, carry)
 
 
 def intent_logits(model, feats):
     """intent GRU(s) -> Linear -> max over time (models.py:806-809)."""
     out = _run_rnns(feats, model._intent_rnns, model.training)
     lin = model._final_classifier
-    if ops.intent_head_supported(lin.weight, (lin.weight.shape[0],)):
-        return ops.intent_head_logits(out, lin.weight, lin.bias)
-    B, T, C = out.shape
-    logits = torch.addmm(lin.bias, out.reshape(B * T, C), lin.weight.t()).view(B, T, -1)
-    return logits.max(dim=1)[0]
+    _require(ops.intent_head_supported(lin.weight, (lin.weight.shape[0],)),
+             "the intent head kernel takes 256 features and at most 128 values in total")
+    return ops.intent_head_logits(out, lin.weight, lin.bias)
 
 
 def intent_loss_acc(model, x, y_intent):
     """Training tail of Model.forward (models.py:806-823) as one kernel per direction: intent GRU(s) -> Linear -> max over
-    time -> summed per-slot cross-entropy and all-slots-right accuracy.  Returns None when the head does not fit the kernel
-    (more than 128 values / 16 slots), and the caller composes it from library ops."""
+    time -> summed per-slot cross-entropy and all-slots-right accuracy.  Returns None when the labels do not fit the fused loss
+    (more than 16 slots, unusual label layout): the caller then takes intent_logits() -- the same head kernel, differentiable --
+    and composes the loss on the [B, C] logits."""
     lin = model._final_classifier
     slots = tuple(int(n) for n in model.values_per_slot)
     if not (ops.intent_head_supported(lin.weight, slots) and y_intent.dtype == torch.int64 and y_intent.dim() == 2):

@@ -9,6 +9,7 @@ been drawn -- long enough for a training step, not for hoarding batches).  With 
 the next batch from the loader and queues its copy (useful when the loader itself is slow; with in-memory batches the
 in-line variant measured 2 % faster: the staging costs less than the GIL hand-offs).  Host logic only -- no kernels.
 """
+import ctypes
 import queue
 import threading
 
@@ -35,6 +36,8 @@ class DevicePrefetcher:
         self.background = background
         self.h2d_bytes = 0
         self._pool = {}                 # (shape, dtype) -> rotating device buffers of the lean path
+        self._keep = []                 # pinned sources of lean-path copies that may still be in flight (see _stage_lean)
+        self._pending = ctypes.c_int(0)
 
     # ---- lean path: pinned tensors of recurring shapes go through the library's copy stream into recycled device buffers
     # (two C calls per tensor; the generic path below costs ~0.15 ms of host time per batch, spent while the GPU idles
@@ -52,6 +55,16 @@ class DevicePrefetcher:
         if not all((not torch.is_tensor(t)) or t.is_cuda or (t.is_pinned() and t.is_contiguous()) for t in batch):
             return None
         main = _lib.stream()
+        # The copies below are raw cudaMemcpyAsync calls on the library's stream: torch's pinned-memory allocator does not know
+        # about them, so a source that came from DataLoader(pin_memory=True) would return to the host pool (and be overwritten by
+        # the pin thread) as soon as the caller drops it.  Every source is therefore held here until the copy stream has drained.
+        if self._keep:
+            _lib.call("slu_h2d_pending", ctypes.byref(self._pending))
+            if not self._pending.value:
+                self._keep.clear()
+            elif len(self._keep) > 64:         # the host runs far ahead of the copy stream: bound what is held
+                _lib.call("slu_h2d_wait")
+                self._keep.clear()
         out = []
         for t in batch:
             if torch.is_tensor(t) and not t.is_cuda:
@@ -59,6 +72,7 @@ class DevicePrefetcher:
                 nbytes = t.numel() * t.element_size()
                 # recycled buffer: its previous consumer was queued on the compute stream at least `depth + 1` batches ago
                 _lib.call("slu_h2d_async", buf.data_ptr(), t.data_ptr(), nbytes, main, 1)
+                self._keep.append(t)
                 self.h2d_bytes += nbytes
                 t = buf
             out.append(t)
@@ -119,6 +133,9 @@ class DevicePrefetcher:
         finally:
             if self._pool:                     # abandoned mid-way: order the compute stream after copies still in flight
                 _lib.call("slu_h2d_ready", _lib.stream())
+            if self._keep:                     # and do not let go of pinned sources a DMA may still be reading
+                _lib.call("slu_h2d_wait")
+                self._keep.clear()
 
     def _iter_background(self):
         stream = _copy_stream(self.device)

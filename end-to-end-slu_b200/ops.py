@@ -8,7 +8,7 @@ import os
 
 import torch
 
-from . import _lib
+from . import _lib, grads
 
 H = 128
 # Which persistent-GRU kernel family runs the recurrence: "tc" = tcgen05 (weights stationary in TMEM),
@@ -49,6 +49,22 @@ class _Fork:
 
 def _f32(t):
     return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def _reserve(ctx, numel, f64=False):
+    """Forward side of the gradient arena (grads.py): remember the arena of this forward pass and a slot of `numel` values."""
+    arena = grads.current()
+    ctx.arena = arena
+    return arena.reserve(numel, f64) if arena is not None else None
+
+
+def _zeros(ctx, key, shape, f64=False):
+    """Backward side: the zero-filled slot as a tensor of `shape` (a private torch.zeros when there is no arena / slot)."""
+    v = ctx.arena.view(key, shape, f64) if getattr(ctx, "arena", None) is not None else None
+    if v is None:
+        v = torch.zeros(shape, device=ctx.arena.device if getattr(ctx, "arena", None) is not None else torch.device("cuda"),
+                        dtype=torch.float64 if f64 else torch.float32)
+    return v
 
 
 def _eptr(t, off=0):
@@ -165,6 +181,7 @@ class ConvBlock(torch.autograd.Function):
         ctx.save_for_backward(x, w, out)
         ctx.slope = slope
         ctx.img_dx = img_dx
+        ctx.slot = _reserve(ctx, Cout + Cout * Cin * k) if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) else None
         return out
 
     @staticmethod
@@ -173,18 +190,17 @@ class ConvBlock(torch.autograd.Function):
         B, T, Cin = x.shape
         Cout, _, k = w.shape
         gy = _f32(gy)
-        if Cout % 4 == 0:           # LeakyReLU backward + bias gradient in one pass
-            dpre = torch.empty_like(out)
-            zb = torch.zeros(Cout + Cout * Cin * k, device=x.device, dtype=torch.float32)     # db | dW, one fill
-            db = zb[:Cout]
-            _lib.call("slu_leaky_bwd_bias", _lib.ptr(out), _lib.ptr(gy), float(ctx.slope), _lib.ptr(dpre), _lib.ptr(db), B * T, Cout,
-                      _lib.stream())
-        else:
-            dpre = torch.where(out > 0, gy, gy * ctx.slope).contiguous()
-            db = dpre.sum((0, 1))
+        if Cout % 4 != 0:
+            raise NotImplementedError("slu_b200 CUDA path: conv blocks need a channel count that is a multiple of 4")
+        # LeakyReLU backward + bias gradient in one pass
+        dpre = torch.empty_like(out)
+        zb = _zeros(ctx, ctx.slot, (Cout + Cout * Cin * k,))                               # db | dW (arena slot)
+        db = zb[:Cout]
+        _lib.call("slu_leaky_bwd_bias", _lib.ptr(out), _lib.ptr(gy), float(ctx.slope), _lib.ptr(dpre), _lib.ptr(db), B * T, Cout,
+                  _lib.stream())
         dx = dw = fork = None
         if ctx.needs_input_grad[1]:      # all k taps in one launch, written straight into the [Cout][Cin][k] weight layout
-            dw = zb[Cout:].view(Cout, Cin, k) if Cout % 4 == 0 else torch.zeros(Cout, Cin, k, device=x.device, dtype=torch.float32)
+            dw = zb[Cout:].view(Cout, Cin, k)
             fork = _Fork(1)
             wgrad_tc(dpre, 0, Cout, Cout, x, 0, Cin, Cin, B, T, dw, 0, Cin * k, k, 1, taps=k, shift0=-(k // 2), stream=fork.stream(0))
         if ctx.needs_input_grad[0]:
@@ -234,6 +250,8 @@ class SincFrontend(torch.autograd.Function):
             _lib.call("slu_sincconv_fwd_simt", _lib.ptr(x), _lib.ptr(W), B, T, _lib.ptr(out), _lib.ptr(route), _lib.stream())
         if need:
             ctx.save_for_backward(x, b1, band, route)
+            ctx.slot_dw = _reserve(ctx, 80 * 401)                  # dW scratch shares the arena's single memset
+            ctx.slot_f64 = _reserve(ctx, 160, f64=True)            # d_b1 | d_band (fp64, like the parameters)
         return out
 
     @staticmethod
@@ -241,15 +259,14 @@ class SincFrontend(torch.autograd.Function):
         x, b1, band, route = ctx.saved_tensors
         B, T = x.shape
         gy = _f32(gy)
+        dW = _zeros(ctx, ctx.slot_dw, (80, 401))
         if SINC_IMPL == "tc":
-            dW = torch.zeros(80, 401, device=x.device, dtype=torch.float32)
             _lib.call("slu_sincconv_bwd_tc", _lib.ptr(x), _lib.ptr(gy), _lib.ptr(route), B, T, _lib.ptr(dW), _lib.stream())
         else:
-            dW = torch.empty(80, 401, device=x.device, dtype=torch.float32)
             _lib.call("slu_sincconv_bwd_simt", _lib.ptr(x), _lib.ptr(gy), _lib.ptr(route), B, T, _lib.ptr(dW), _lib.stream())
-        d_b1 = torch.empty(80, device=x.device, dtype=torch.float64)
-        d_band = torch.empty(80, device=x.device, dtype=torch.float64)
-        _lib.call("slu_sinc_filters_bwd", _lib.ptr(b1), _lib.ptr(band), _lib.ptr(dW), _lib.ptr(d_b1), _lib.ptr(d_band),
+        d = _zeros(ctx, ctx.slot_f64, (160,), f64=True)
+        d_b1, d_band = d[:80], d[80:]
+        _lib.call("slu_sinc_filters_bwd", _lib.ptr(b1), _lib.ptr(band), _lib.ptr(dW), d_b1.data_ptr(), d_band.data_ptr(),
                   _lib.stream())
         return None, d_b1, d_band
 
@@ -261,15 +278,6 @@ def sinc_filters(filt_b1, filt_band):
     W = torch.empty(80, 401, device=b1.device, dtype=torch.float32)
     _lib.call("slu_sinc_filters_fwd", _lib.ptr(b1), _lib.ptr(band), _lib.ptr(W), _lib.stream())
     return W
-
-
-_gather_idx = {}
-
-
-def _bias_gather(dev):
-    if dev.index not in _gather_idx:
-        _gather_idx[dev.index] = torch.tensor([0, 1, 2, 0, 1, 3], device=dev)
-    return _gather_idx[dev.index]
 
 
 class BiGRU(torch.autograd.Function):
@@ -304,12 +312,21 @@ class BiGRU(torch.autograd.Function):
             ctx.save_for_backward(x, w_ih_cat, w_hh_cat, y_full, stash, mask)
             ctx.ds = ds
             ctx.img_nn = img_nn
+            # the packed views alias the Parameters' storage without sharing their version counters: remember the versions so
+            # that an in-place update between this forward and its backward is detected (stock autograd would raise too)
+            ctx.param_versions = [(q, q._version) for q in (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)]
+            # gradients in the layout of the packed parameter buffer: dW_ih [768,I] | dW_hh [2,384,H] | db_ih [768] | db_hh [768]
+            ctx.slot = _reserve(ctx, 768 * I + 2 * 384 * H + 2 * 768) if any(ctx.needs_input_grad[1:9]) else None
         return y_out
 
     @staticmethod
     def backward(ctx, gy):
         x, w_ih_cat, w_hh_cat, y_full, stash, mask = ctx.saved_tensors
         ds = ctx.ds
+        for q, v in ctx.param_versions:
+            if q._version != v:
+                raise RuntimeError("slu_b200: a GRU parameter needed for gradient computation has been modified by an inplace "
+                                   "operation between forward and backward")
         B, T, I = x.shape
         dev = x.device
         gy = _f32(gy)
@@ -317,14 +334,15 @@ class BiGRU(torch.autograd.Function):
         dhn = torch.empty(B, T, 256, device=dev, dtype=torch.float32)
         ni = ctx.needs_input_grad
         wg = any(ni[1:9])
-        # one zero-filled buffer: dW_ih [768,I] | dW_hh [2,384,H] | column sums of dr, dz, dn, dhn per direction [2,4,H]
+        # one zero-filled slot in parameter order: dW_ih [768,I] | dW_hh [2,384,H] | db_ih [2,384] | db_hh [2,384]
         n_ih, n_hh = 768 * I, 2 * 384 * H
-        zbuf = torch.zeros((n_ih + n_hh if wg else 0) + 2 * 4 * H, device=dev, dtype=torch.float32)
-        dbias = zbuf[-2 * 4 * H:].view(2, 4, H)
         grads = [None] * 8
         fork = None
+        db_ih = db_hh = dw_ih = dw_hh = None
         if wg:
+            zbuf = _zeros(ctx, ctx.slot, (n_ih + n_hh + 2 * 768,))
             dw_ih, dw_hh = zbuf[:n_ih].view(768, I), zbuf[n_ih:n_ih + n_hh].view(2, 384, H)
+            db_ih, db_hh = zbuf[n_ih + n_hh:n_ih + n_hh + 768], zbuf[n_ih + n_hh + 768:]
         if GRU_IMPL == "tc" and FUSED_BWD and _lib._prof is None:
             # the whole launch sequence of the layer in one C-ABI call (csrc/bigru.cu); the per-launch path below is what the
             # profiling pass uses, and the only one for the CUDA-core GRU variant
@@ -333,13 +351,15 @@ class BiGRU(torch.autograd.Function):
             if ni[0]:
                 img = ctx.img_nn if ctx.img_nn is not None else presplit(w_ih_cat, *_form_nn(w_ih_cat))
             _lib.call("slu_bigru_bwd_tc", _lib.ptr(gy), _lib.ptr(mask), _lib.ptr(y_full), _lib.ptr(stash), _lib.ptr(w_hh_cat), _lib.ptr(x),
-                      I, None if img is None else img.data_ptr(), B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), _lib.ptr(dbias),
+                      I, None if img is None else img.data_ptr(), B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn),
+                      db_ih.data_ptr() if wg else None, db_hh.data_ptr() if wg else None,
                       dw_ih.data_ptr() if wg else None, dw_hh.data_ptr() if wg else None, _lib.ptr(dx), 1 if OVERLAP else 0,
                       _lib.stream())
             _lib.stats["calls"] += (3 if wg else 0) + (1 if ni[0] else 0)          # kernels launched beyond the first
         else:
             _lib.call("slu_gru_bwd_" + GRU_IMPL, _lib.ptr(gy), _lib.ptr(mask), _lib.ptr(y_full), _lib.ptr(stash), _lib.ptr(w_hh_cat),
-                      B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), _lib.ptr(dbias), _lib.stream())
+                      B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), db_ih.data_ptr() if wg else None, db_hh.data_ptr() if wg else None,
+                      _lib.stream())
             if wg:
                 fork = _Fork(3)
                 wgrad_tc(dgx, 0, 768, 768, x, 0, I, I, B, T, dw_ih, 0, I, stream=fork.stream(0))
@@ -348,12 +368,11 @@ class BiGRU(torch.autograd.Function):
                               shift0=1 if d else -1, stream=fork.stream(1 + d))
             dx = matmul_nn(dgx.view(B * T, 768), w_ih_cat, ctx.img_nn).view(B, T, I) if ni[0] else None
         if wg:
-            db6 = dbias.index_select(1, _bias_gather(dev))                     # (dr, dz, dn | dr, dz, dhn) per direction
             for d in range(2):
                 grads[4 * d + 0] = dw_ih[d * 384:(d + 1) * 384]
                 grads[4 * d + 1] = dw_hh[d]
-                grads[4 * d + 2] = db6[d, :3].reshape(384)                     # b_ih
-                grads[4 * d + 3] = db6[d, 3:].reshape(384)                     # b_hh
+                grads[4 * d + 2] = db_ih[d * 384:(d + 1) * 384]
+                grads[4 * d + 3] = db_hh[d * 384:(d + 1) * 384]
             if fork is not None:
                 fork.join()
         return (dx, *grads, None, None, None, None, None)
@@ -446,10 +465,38 @@ def _head_fwd(feats, w, b, y, slots):
     return fbuf, logits, tstar
 
 
+class IntentLogits(torch.autograd.Function):
+    """feats [B,T,256] -> logits [B,C] = max over time of Linear(256->C): models.py:806-809 (predict path), differentiable like
+    the reference's (the arg-max frame of each class receives the gradient)."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, bias):
+        feats = _f32(feats)
+        w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        C = w.shape[0]
+        _, logits, tstar = _head_fwd(feats, w, b, None, (C,))
+        ctx.save_for_backward(feats, w, tstar)
+        ctx.slot = _reserve(ctx, w.numel() + C) if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) else None
+        return logits
+
+    @staticmethod
+    def backward(ctx, g_logits):
+        feats, w, tstar = ctx.saved_tensors
+        B, T, _ = feats.shape
+        C = w.shape[0]
+        dev = feats.device
+        g = _f32(g_logits)
+        dfeats = torch.empty(B, T, 2 * H, device=dev, dtype=torch.float32)
+        zb = _zeros(ctx, ctx.slot, (C * 2 * H + C,))
+        sl = (ctypes.c_int * 1)(C)
+        _lib.call("slu_intent_head_bwd", _lib.ptr(g), _lib.ptr(feats), _lib.ptr(w), None, None, _lib.ptr(tstar),
+                  B, T, C, sl, 1, _lib.ptr(dfeats), zb.data_ptr(), zb[C * 2 * H:].data_ptr(), _lib.stream())
+        return dfeats, zb[:C * 2 * H].view(C, 2 * H), zb[C * 2 * H:]
+
+
 def intent_head_logits(feats, weight, bias):
-    """Linear + max over time -> logits [B,C] (no labels, no autograd): models.py:806-809 on the predict path."""
-    C = weight.shape[0]
-    return _head_fwd(_f32(feats.detach()), weight.detach().contiguous(), bias.detach().contiguous(), None, (C,))[1]
+    """Linear + max over time -> logits [B,C] (no labels): models.py:806-809 on the predict path."""
+    return IntentLogits.apply(feats, weight, bias)
 
 
 class IntentHead(torch.autograd.Function):
@@ -465,6 +512,7 @@ class IntentHead(torch.autograd.Function):
         fbuf, logits, tstar = _head_fwd(feats, w, b, y, slots)
         ctx.save_for_backward(feats, w, y, logits, tstar)
         ctx.slots = slots
+        ctx.slot = _reserve(ctx, w.numel() + w.shape[0]) if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) else None
         loss, acc = fbuf[-2], fbuf[-1]
         ctx.mark_non_differentiable(acc, logits)
         return loss, acc, logits
@@ -478,7 +526,7 @@ class IntentHead(torch.autograd.Function):
         dev = feats.device
         g = _f32(g_loss).reshape(1)
         dfeats = torch.empty(B, T, 2 * H, device=dev, dtype=torch.float32)
-        zb = torch.zeros(C * 2 * H + C, device=dev, dtype=torch.float32)
+        zb = _zeros(ctx, ctx.slot, (C * 2 * H + C,))
         sl = (ctypes.c_int * len(slots))(*slots)
         _lib.call("slu_intent_head_bwd", _lib.ptr(g), _lib.ptr(feats), _lib.ptr(w), _lib.ptr(y), _lib.ptr(logits), _lib.ptr(tstar),
                   B, T, C, sl, len(slots), _lib.ptr(dfeats), zb.data_ptr(), zb[C * 2 * H:].data_ptr(), _lib.stream())

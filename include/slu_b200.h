@@ -6,7 +6,7 @@
  * and reaches these through ctypes (end-to-end-slu_b200/_lib.py).  See INTEGRATION.md.
  *
  * Conventions: plain device pointers + sizes, no torch types; every function enqueues work on `stream`
- * (a cudaStream_t passed as void*), returns 0 or a cudaError_t, never synchronises, never allocates.
+ * (a cudaStream_t passed as void*), returns 0, a cudaError_t or SLU_ERR_TOO_LARGE, never synchronises, never allocates.
  * All tensors are contiguous row-major fp32 unless stated.  H = 128 hidden units, gate order (r, z, n).
  */
 #ifndef SLU_B200_H
@@ -15,6 +15,10 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+/* Returned (instead of a cudaError_t) when a size exceeds a kernel's 32-bit index range, e.g. B*T >= 2^21 frames in
+ * slu_gru_{fwd,bwd}_tc: split the batch. */
+#define SLU_ERR_TOO_LARGE 100001
 
 /* Filter-bank synthesis W[80][401] from the fp64 cut-offs -- replaces the 80-iteration python loop
  * models.py:82-106 (sinc() :17-24, flip() :7-14). */
@@ -52,17 +56,17 @@ int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float* b_hh, cons
                      float* y_full, float* y_out, float* stash, void* stream);
 /* Backward through time -- replaces _cudnn_rnn_backward.  Emits dgx[B][T][768] (gradient wrt gx) and
  * dhn[B][T][256] (gradient wrt the n-gate's recurrent pre-activation); the weight/input gradients are dense
- * GEMMs over these.  dbias[2][4][128] (caller-zeroed, may be NULL) accumulates the bias gradients: sums over (b,t) of
- * dr, dz, dn (b_ih; and b_hh for r, z) and dhn (b_hh, n rows). */
+ * GEMMs over these.  db_ih[2][384] and db_hh[2][384] (the bias parameters' own layout; both NULL or both caller-zeroed)
+ * ACCUMULATE the bias gradients: b_ih <- sums over (b,t) of (dr, dz, dn), b_hh <- (dr, dz, dhn). */
 int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                     const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* dbias, void* stream);
+                     const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh, void* stream);
 
 /* Same contracts as slu_gru_fwd_simt / slu_gru_bwd_simt, executed on tcgen05 tensor cores: W_hh (bf16 hi+lo) stationary
  * in tensor memory, h / dG as the shared-memory B operand, 3-pass bf16 split with fp32 accumulation in TMEM. */
 int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T, int ds,
                    float* y_full, float* y_out, float* stash, void* stream);
 int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                   const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* dbias, void* stream);
+                   const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh, void* stream);
 
 /* Operand format of the tcgen05 recurrence:
  *   0 = bf16 hi/lo split, fp32-class accuracy (default).  On the 4- and 8-row batch tiles the hi and lo rows of the activation
@@ -82,7 +86,9 @@ int slu_debug_gru_phase_clocks(long long* buf);
  * (NULL: logits only); values_per_slot = n_slots HOST ints summing to C (C <= 128, n_slots <= 16).
  * fwd writes logits [B][C], tstar [B][C] (arg-max frame), row_loss/row_ok [B] scratch and loss_acc[2] = {loss, accuracy};
  * `ticket` is one zero-initialised device word the kernel uses and resets.
- * bwd: gloss = dL/dloss (one device float); writes dfeats [B][T][256], ACCUMULATES into dW [C][256] and dbias [C]. */
+ * bwd: gloss = dL/dloss (one device float); writes dfeats [B][T][256], ACCUMULATES into dW [C][256] and dbias [C].
+ * With y == NULL (the logits-only head of predict_intents) gloss is dL/dlogits [B][C] instead.
+ * A label outside [0, values_per_slot[slot]) makes the loss and the gradients NaN (F.cross_entropy would device-assert). */
 int slu_intent_head_fwd(const float* feats, const float* W, const float* bias, const long long* y, int B, int T, int C,
                         const int* values_per_slot, int n_slots, float* logits, int* tstar, float* row_loss, float* row_ok,
                         float* loss_acc, unsigned int* ticket, void* stream);
@@ -96,8 +102,8 @@ int slu_intent_head_bwd(const float* gloss, const float* feats, const float* W, 
  * operand (NULL with dx == NULL: no input gradient); dw_ih [768][I] and dw_hh [2][384][128] accumulate (NULL, NULL: no weight
  * gradients); dgx [B][T][768] and dhn [B][T][256] are caller-provided scratch that holds the pre-activation gradients. */
 int slu_bigru_bwd_tc(const float* gy, const float* drop_mask, const float* y_full, const float* stash, const float* w_hh, const float* x,
-                     int I, const void* w_ih_nn_img, int B, int T, int ds, float* dgx, float* dhn, float* dbias, float* dw_ih,
-                     float* dw_hh, float* dx, int overlap, void* stream);
+                     int I, const void* w_ih_nn_img, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh,
+                     float* dw_ih, float* dw_hh, float* dx, int overlap, void* stream);
 
 /* Fork / join of independent launches (host-side stream plumbing, no kernels): after slu_stream_fork the n (<= 8)
  * streams returned in side_streams[] wait for everything queued on main_stream so far; after slu_stream_join work queued
@@ -111,6 +117,10 @@ int slu_stream_join(void* main_stream, int n);
  * destination buffers); slu_h2d_ready makes consumer_stream wait for all copies queued so far.  src should be pinned. */
 int slu_h2d_async(void* dst, const void* src, size_t bytes, void* after_stream, int order_after);
 int slu_h2d_ready(void* consumer_stream);
+/* Lifetime of the pinned sources: *pending = 1 while copies queued with slu_h2d_async are still in flight (non-blocking query);
+ * slu_h2d_wait blocks the host until all of them have completed. */
+int slu_h2d_pending(int* pending);
+int slu_h2d_wait(void);
 
 /* Dropout keep-mask (nn.Dropout, models.py:246/276/700, training mode): mask[i] = Bernoulli(1-p) / (1-p), i < n, from
  * Philox4x32-10 keyed by `seed` (counter = i/4).  `mask` must be 16-byte aligned.  The GRU kernels multiply by it. */
@@ -146,6 +156,24 @@ int slu_wgrad_tc(const float* G, long ldg, int M, const float* X, long ldx, int 
                  long s_m, long s_n, long s_tap, void* stream);
 
 /* tcgen05 self-test: C[128][N] = A[128][K] . B[N][K]^T (3-pass bf16 split, fp32 accumulate in TMEM). */
+/* ---- optimizer step / gradient bucket (reference training.py:19, 64-66, 96-98: torch.optim.Adam, zero_grad/backward/step) ----
+ * slu_adam_multi: one Adam step over `n` parameter tensors (fp32 or fp64, any sizes) in ceil(n/64) launches; torch.optim.Adam's
+ * single-tensor arithmetic with PER-TENSOR step counts (parameters un-frozen later keep their own bias corrections):
+ *   g += weight_decay*p;  m += (g - m)(1 - beta1);  v = v*beta2 + (1 - beta2) g^2;  p -= step_size * m / (sqrt(v)/bc2_sqrt + eps)
+ * `tensors` is a HOST array (it travels in the kernel parameters). */
+struct SluAdamTensor {
+  void* p; const void* g; void* m; void* v;   /* parameter, gradient, exp_avg, exp_avg_sq (device pointers, same dtype) */
+  long n;                                     /* elements */
+  float step_size;                            /* lr / (1 - beta1^t) */
+  float bc2_sqrt;                             /* sqrt(1 - beta2^t) */
+  int is_f64;                                 /* 0: float, 1: double */
+  int pad;
+};
+int slu_adam_multi(const void* tensors, int n, float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* fp64 gradients inside an fp32 all-reduce bucket: split into (hi, lo) floats before the collective, merge after it. */
+int slu_f64_hilo_split(const double* src, float* hi, float* lo, int n, void* stream);
+int slu_f64_hilo_merge(double* dst, const float* hi, const float* lo, int n, void* stream);
+
 int slu_tc_selftest(const float* A, const float* B, float* C, int N, int K, void* stream);
 /* Same, A operand resident in tensor memory (K <= 128), B tile with a padded leading-byte-offset. */
 int slu_tc_selftest_ts(const float* A, const float* B, float* C, int N, int K, void* stream);

@@ -35,6 +35,8 @@ def _engine():
         if here not in sys.path:
             sys.path.insert(0, here)
         _pkg = importlib.import_module("end-to-end-slu_b200")
+        if torch.cuda.is_available():
+            _pkg.optim.install()         # torch.optim.Adam -> the fused-step subclass the unchanged Trainer then constructs
     return _pkg.engine
 
 
@@ -207,6 +209,7 @@ class PretrainedModel(torch.nn.Module):
         self._plan_cache = None
         if self.is_cuda:
             self.cuda()
+            _engine()          # load the CUDA engine now: the Trainer builds its optimizer right after the model (training.py:19)
 
     # -- execution ------------------------------------------------------------------------------
     @property
@@ -219,14 +222,15 @@ class PretrainedModel(torch.nn.Module):
         self.is_cuda = next(self.parameters()).is_cuda
         return self.is_cuda
 
-    def _phoneme_features(self, x):
+    def _phoneme_features(self, x, with_word=True):
+        """-> (phoneme-module output, carry for _word_features: what the CUDA engine prepared for the word module in the same pass)"""
         if self._on_gpu():
-            return _engine().phoneme_features(self, x.cuda())
-        return _run(self.phoneme_layers, x.unsqueeze(1))
+            return _engine().phoneme_features(self, x.cuda(), with_word)
+        return _run(self.phoneme_layers, x.unsqueeze(1)), None
 
-    def _word_features(self, ph):
+    def _word_features(self, ph, carry=None):
         if self.is_cuda:
-            return _engine().word_features(self, ph)
+            return _engine().word_features(self, ph, carry)
         return _run(self.word_layers, ph)
 
     def forward(self, x, y_phoneme, y_word):
@@ -234,7 +238,7 @@ class PretrainedModel(torch.nn.Module):
         Returns (phoneme_loss, word_loss, phoneme_acc, word_acc) (models.py:291-331)."""
         if self._on_gpu():
             y_phoneme, y_word = y_phoneme.cuda(), y_word.cuda()
-        out = self._phoneme_features(x)
+        out, carry = self._phoneme_features(x, with_word=self.pretraining_type != 1)
         logits = self.phoneme_linear(out)
         logits = logits.reshape(-1, logits.shape[-1])
         y_phoneme = y_phoneme.reshape(-1)
@@ -242,7 +246,7 @@ class PretrainedModel(torch.nn.Module):
         phoneme_acc = _masked_acc(logits, y_phoneme)
         if self.pretraining_type == 1:          # phoneme-only pre-training: skip the word module
             return phoneme_loss, torch.tensor([0.]), phoneme_acc, torch.tensor([0.])
-        out = self._word_features(out)
+        out = self._word_features(out, carry)
         logits = self.word_linear(out)
         logits = logits.reshape(-1, logits.shape[-1])
         y_word = y_word.reshape(-1)
@@ -252,12 +256,13 @@ class PretrainedModel(torch.nn.Module):
 
     def compute_posteriors(self, x):
         """(phoneme_logits [B,T/640,P], word_logits [B,T/2560,V]) (models.py:333-347)."""
-        ph = self._phoneme_features(x)
-        return self.phoneme_linear(ph), self.word_linear(self._word_features(ph))
+        ph, carry = self._phoneme_features(x)
+        return self.phoneme_linear(ph), self.word_linear(self._word_features(ph, carry))
 
     def compute_features(self, x):
         """[B,T] -> [B, T/2560, 256] word-module features (models.py:349-361)."""
-        return self._word_features(self._phoneme_features(x))
+        ph, carry = self._phoneme_features(x)
+        return self._word_features(ph, carry)
 
 
 def freeze_layer(layer):

@@ -152,8 +152,9 @@ def train_steps(params, B, T, steps, warmup, device="cpu", loop80=True, seed=123
     """Adam train steps of the port on `device`; returns seconds per step.  CPU: wall clock.  GPU: CUDA events around the
     whole timed run (synchronised on both sides), which includes the reference's per-step host work and result read."""
     import time
+    from torch.optim.adam import Adam as StockAdam      # the library class itself, whatever `torch.optim.Adam` is bound to
     model = RefPort(params, loop80=loop80, kind=kind).to(device).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt = StockAdam(model.parameters(), lr=1e-3)
     x, _ = R.synthetic_batch(B, T, seed=seed)
     ys = synthetic_labels(kind, B, T, seed)
     x = x.to(device)
