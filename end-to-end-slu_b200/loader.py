@@ -179,3 +179,73 @@ class DevicePrefetcher:
         finally:
             stop.set()
             th.join(timeout=5)
+
+
+class ShardedBucketBatchSampler:
+    """`batch_sampler` for the reference's datasets when the minibatch is sharded over ranks.
+
+    The reference builds `DataLoader(dataset, batch_size, shuffle=True, collate_fn=CollateWavs*())` (data.py:261, 344-391,
+    511-545): every rank seeded alike (main.py:22) would draw the SAME batches, and the pad-to-longest collate wastes the kernels'
+    time on zeros (the GRU processes padding as real frames).  This sampler yields, for rank r of `world`,
+    lists of dataset indices such that
+      * the ranks' batches of one step are disjoint and together form one global batch of batch_size * world utterances
+        (every rank gets the same number of steps; the tail is dropped or padded by wrap-around, `drop_last`);
+      * utterances of similar length share a batch: the epoch's shuffled order is cut into buckets of `bucket_batches` global
+        batches, each bucket is sorted by length and cut into global batches, and the batches are shuffled again -- the
+        shuffle of the reference survives at bucket granularity while padding shrinks to the within-bucket spread;
+      * within a global batch, rank r takes every world-th utterance of the length-sorted order, so all ranks see the same
+        length profile (equal step times: the all-reduce waits for the slowest rank);
+      * the order depends only on (seed, epoch): all ranks compute the same permutation without communicating.
+    `lengths[i]` = samples (or any monotone proxy, e.g. file size) of item i; None = no bucketing, only sharding.
+    """
+
+    def __init__(self, lengths, batch_size, rank=0, world=1, seed=0, bucket_batches=50, drop_last=False, n_items=None):
+        if lengths is None and n_items is None:
+            raise ValueError("lengths or n_items is required")
+        self.lengths = None if lengths is None else [int(v) for v in lengths]
+        self.n = len(self.lengths) if self.lengths is not None else int(n_items)
+        if not (0 <= rank < world) or batch_size < 1:
+            raise ValueError("bad rank / world / batch_size")
+        self.batch_size, self.rank, self.world, self.seed = batch_size, rank, world, seed
+        self.bucket_batches, self.drop_last, self.epoch = max(1, bucket_batches), drop_last, 0
+
+    def set_epoch(self, epoch):
+        self.epoch = int(epoch)
+
+    def __len__(self):
+        g = self.batch_size * self.world
+        return self.n // g if self.drop_last else -(-self.n // g)
+
+    def global_batches(self):
+        """The epoch's global batches (lists of batch_size * world indices), identical on every rank."""
+        gen = torch.Generator().manual_seed(self.seed * 1000003 + self.epoch)
+        order = torch.randperm(self.n, generator=gen).tolist()
+        g = self.batch_size * self.world
+        if self.drop_last:
+            order = order[:self.n // g * g]
+        elif len(order) % g:
+            order = order + order[:g - len(order) % g]                  # wrap around: every rank gets a full last batch
+        batches = []
+        span = g * self.bucket_batches
+        for s in range(0, len(order), span):
+            bucket = order[s:s + span]
+            if self.lengths is not None:
+                bucket.sort(key=lambda i: self.lengths[i])
+            batches += [bucket[k:k + g] for k in range(0, len(bucket), g)]
+        perm = torch.randperm(len(batches), generator=gen).tolist()
+        return [batches[i] for i in perm]
+
+    def __iter__(self):
+        for gb in self.global_batches():
+            yield gb[self.rank::self.world]
+
+    def padding_fraction(self):
+        """Fraction of the padded [batch, max_len] samples that is padding, over this rank's epoch (0 without lengths)."""
+        if self.lengths is None:
+            return 0.0
+        real = padded = 0
+        for b in self:
+            ls = [self.lengths[i] for i in b]
+            real += sum(ls)
+            padded += max(ls) * len(ls)
+        return 1.0 - real / max(1, padded)

@@ -14,6 +14,7 @@ from util import ckpt_params, golden, load_test_wav, make_config, rel_err
 pytestmark = pytest.mark.gpu
 LOGIT_TOL = 1e-3      # north star; we assert 10x tighter where fp32 kernels are used
 GRAD_TOL = 5e-3
+SINC_GRAD_TOL = 5e-3  # the two SincNet cut-off vectors (their chain through the max-normalisation cancels: see csrc/sinc_tc.cu)
 
 
 def gpu_model(params=None, train=False):
@@ -317,7 +318,7 @@ def test_benchmark_size_train_step_is_tied_to_the_oracle():
         lg, _ = m.predict_intents(xd[:4])
     assert rel_err(lg.cpu(), lg_ref.detach()) < LOGIT_TOL / 10
     for k in g4:
-        assert rel_err(g4[k].cpu(), pr[k].grad) < GRAD_TOL, (k, rel_err(g4[k].cpu(), pr[k].grad))
+        assert rel_err(g4[k].cpu(), pr[k].grad) < (SINC_GRAD_TOL if "filt_" in k else GRAD_TOL), (k, rel_err(g4[k].cpu(), pr[k].grad))
 
 
 def test_frozen_encoder_gradients_match_the_oracle():

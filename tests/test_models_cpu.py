@@ -371,3 +371,47 @@ def test_seq2seq_cpu_path_matches_the_reference_golden():
     assert abs(loss.item() - float(g["loss"])) < 1e-5 * float(g["loss"])
     assert rel_err(enc, g["enc"]) < 2e-5 and rel_err(scores, g["beam_scores"]) < 1e-5
     assert np.array_equal(beam.argmax(-1).numpy(), g["beam_ids"])
+
+
+def test_sharded_bucket_batch_sampler_shards_and_buckets():
+    """per-rank disjoint shards of one global batch, full coverage, same permutation on every rank, less
+    padding than the reference's plain shuffle, usable as a DataLoader batch_sampler with the reference's pad-collate contract."""
+    loader = importlib.import_module("end-to-end-slu_b200.loader")
+    rs = np.random.RandomState(0)
+    lengths = (16000 * (1.0 + 3.0 * rs.beta(2, 5, size=1003))).astype(int).tolist()      # 1-4 s, skewed like FSC
+    world, bs = 4, 8
+    samplers = [loader.ShardedBucketBatchSampler(lengths, bs, rank=r, world=world, seed=7, bucket_batches=10) for r in range(world)]
+    per_rank = [list(s) for s in samplers]
+    assert len({len(b) for b in per_rank}) == 1 and len(per_rank[0]) == len(samplers[0]) == -(-1003 // (bs * world))
+    seen = []
+    for step in range(len(per_rank[0])):
+        shard = [per_rank[r][step] for r in range(world)]
+        assert all(len(b) == bs for b in shard)
+        flat = [i for b in shard for i in b]
+        assert len(set(flat)) == len(flat)                           # ranks are disjoint within a step
+        means = [np.mean([lengths[i] for i in b]) for b in shard]
+        assert max(means) - min(means) < 0.1 * np.mean(means)       # same length profile on every rank
+        seen += flat
+    assert set(seen) == set(range(1003))                            # every utterance once per epoch (+ wrap-around fill)
+    assert len(seen) - 1003 == (-1003) % (bs * world)
+    plain = list(loader.ShardedBucketBatchSampler(None, bs, rank=0, world=world, seed=7, n_items=1003))   # the reference's plain shuffle
+    plain_pad = 1.0 - sum(sum(lengths[i] for i in b) for b in plain) / sum(max(lengths[i] for i in b) * len(b) for b in plain)
+    assert samplers[0].padding_fraction() < 0.35 * plain_pad
+    e0 = list(samplers[1]); samplers[1].set_epoch(1); e1 = list(samplers[1]); samplers[1].set_epoch(0)
+    assert e0 == list(samplers[1]) and e0 != e1                      # deterministic per epoch, reshuffled across epochs
+    drop = loader.ShardedBucketBatchSampler(lengths, bs, rank=1, world=world, seed=7, drop_last=True)
+    assert len(list(drop)) == len(drop) == 1003 // (bs * world)
+
+    class Wavs(torch.utils.data.Dataset):                            # contract of data.py:373-376: (x [T_i], y [3])
+        def __len__(self):
+            return 1003
+
+        def __getitem__(self, i):
+            return torch.full((lengths[i] // 100,), float(i)), torch.tensor([i % 6, i % 14, i % 4])
+
+    def collate(batch):                                              # pad-and-stack like CollateWavsSLU (data.py:344-391)
+        T = max(len(x) for x, _ in batch)
+        return torch.stack([torch.nn.functional.pad(x, (0, T - len(x))) for x, _ in batch]), torch.stack([y for _, y in batch])
+    dl = torch.utils.data.DataLoader(Wavs(), batch_sampler=samplers[2], collate_fn=collate)
+    x, y = next(iter(dl))
+    assert x.shape[0] == bs and y.shape == (bs, 3)
