@@ -44,6 +44,11 @@ SIGNATURES = {
     "slu_presplit_multi": [_P, _I, _P],
     "slu_wgrad2_tc": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P],
     "slu_wgrad_tc": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P],
+    "slu_ce_count": [_P, _L, _P, _P],
+    "slu_ce_rows": [_P, _L, _I, _P, _L, _P, _I, _P, _P, _P],
+    "slu_ce_finish": [_P, _P, _L, _P, _P, _P],
+    "slu_colsum_acc": [_P, _L, _L, _I, _P, _P],
+    "slu_scale": [_P, _P, _L, _P, _P],
     "slu_adam_multi": [_P, _I, _F, _F, _F, _F, _P],
     "slu_f64_hilo_split": [_P, _P, _P, _I, _P],
     "slu_f64_hilo_merge": [_P, _P, _P, _I, _P],

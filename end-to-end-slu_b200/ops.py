@@ -542,3 +542,120 @@ def gru_executed_flop_factor(B):
     """Executed / algorithmic tensor-core flops of the recurrence: the N=16 tile carries NR rows, hi/lo stacked, x (W_hi, W_lo)."""
     nr = gru_rows_per_cta(B)
     return 32 // nr if nr < 16 else 3
+
+
+# ---- ASR heads (SURVEY.md 8(f) rank 1) ----------------------------------------------------------------------------------------
+CE_CHUNK = int(os.environ.get("SLU_CE_CHUNK", "4096"))      # frames per logits tile (x V floats: 164 MB at V = 10 000)
+
+
+def _pad4_rows(w, b, neg=-1e30):
+    """Weight [V,K] / bias [V] with V padded to a multiple of 4 (zero rows, bias -1e30: the padded classes get probability 0)."""
+    V, K = w.shape
+    Vp = (V + 3) // 4 * 4
+    if Vp == V:
+        return w, b, V
+    wp = torch.zeros(Vp, K, device=w.device, dtype=torch.float32)
+    wp[:V].copy_(w)
+    bp = torch.full((Vp,), neg, device=w.device, dtype=torch.float32)
+    bp[:V].copy_(b)
+    return wp, bp, Vp
+
+
+class LinearCE(torch.autograd.Function):
+    """feats [M,K] -> (loss, acc): Linear(K -> V) + cross_entropy(ignore_index=-1, mean) + masked arg-max accuracy, reference
+    models.py:308-314 / 321-329, without ever holding the [M,V] logits: the frames are walked in chunks of CE_CHUNK rows whose
+    logits tile is overwritten by its own gradient and consumed by the three gradient GEMMs before the next chunk (csrc/ce.cu).
+    The gradients are therefore produced in forward (scaled for dL/dloss = 1) and multiplied by the incoming dL/dloss in backward."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, bias, y):
+        x = _f32(feats)
+        M, K = x.shape
+        dev = x.device
+        w, b, Vp = _pad4_rows(weight.detach().contiguous(), bias.detach().contiguous())
+        V = weight.shape[0]
+        y = y.contiguous()
+        assert y.dtype == torch.int64 and y.numel() == M and K % 4 == 0
+        need_x = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        grad = need_x or need_w
+        st = _lib.stream()
+        sbuf = torch.empty(2 * M + 4, device=dev, dtype=torch.float32)          # row_loss | row_ok | n_valid, 1/n_valid | loss, acc
+        row_loss, row_ok, nv, out = sbuf[:M], sbuf[M:2 * M], sbuf[2 * M:2 * M + 2], sbuf[2 * M + 2:]
+        _lib.call("slu_ce_count", _lib.ptr(y), M, nv.data_ptr(), st)
+        R = min(M, max(128, CE_CHUNK))
+        tile = torch.empty(R, Vp, device=dev, dtype=torch.float32)
+        img_nt = presplit(w, *_form_nt(w))
+        img_nn = presplit(w, *_form_nn(w)) if need_x else None
+        dx = torch.empty(M, K, device=dev, dtype=torch.float32) if need_x else None
+        dwb = torch.zeros(Vp * K + Vp, device=dev, dtype=torch.float32) if need_w else None     # dW | db, accumulated over chunks
+        for r0 in range(0, M, R):
+            r = min(R, M - r0)
+            gemm_tc(x[r0:r0 + r], K, img_nt, r, Vp, K, tile, bias=b)
+            _lib.call("slu_ce_rows", tile.data_ptr(), Vp, Vp, y[r0:].data_ptr(), r, nv.data_ptr(), 1 if grad else 0,
+                      row_loss[r0:].data_ptr(), row_ok[r0:].data_ptr(), st)
+            if need_x:
+                gemm_tc(tile, Vp, img_nn, r, K, Vp, dx[r0:r0 + r])
+            if need_w:
+                wgrad_tc(tile, 0, Vp, Vp, x, r0 * K, K, K, 1, r, dwb, 0, K)
+                _lib.call("slu_colsum_acc", tile.data_ptr(), Vp, r, Vp, dwb[Vp * K:].data_ptr(), st)
+        _lib.call("slu_ce_finish", row_loss.data_ptr(), row_ok.data_ptr(), M, nv.data_ptr(), out.data_ptr(), st)
+        ctx.save_for_backward(dx, dwb)
+        ctx.dims = (V, Vp, K)
+        ctx.slot = _reserve(ctx, Vp * K + Vp) if need_w else None
+        loss, acc = out[0], out[1]
+        ctx.mark_non_differentiable(acc)
+        return loss, acc
+
+    @staticmethod
+    def backward(ctx, g_loss, g_acc):
+        dx, dwb = ctx.saved_tensors
+        V, Vp, K = ctx.dims
+        g = _f32(g_loss).reshape(1)
+        st = _lib.stream()
+        gx = gw = gb = None
+        if dx is not None:
+            gx = torch.empty_like(dx)
+            _lib.call("slu_scale", dx.data_ptr(), gx.data_ptr(), dx.numel(), g.data_ptr(), st)
+        if dwb is not None:
+            out = _zeros(ctx, ctx.slot, (Vp * K + Vp,))
+            _lib.call("slu_scale", dwb.data_ptr(), out.data_ptr(), dwb.numel(), g.data_ptr(), st)
+            gw, gb = out[:V * K].view(V, K), out[Vp * K:Vp * K + V]
+        return gx, gw, gb, None
+
+
+def linear_ce(feats, weight, bias, y):
+    """(loss, acc) of a frame-wise classification head; feats [..., K], y [...] int64 with -1 = ignore."""
+    return LinearCE.apply(feats.reshape(-1, feats.shape[-1]), weight, bias, y.reshape(-1))
+
+
+class LinearNT(torch.autograd.Function):
+    """x [..., K] @ W[V,K]^T + b on the tcgen05 GEMMs, differentiable (compute_posteriors, models.py:333-347)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = _f32(x).reshape(-1, x.shape[-1])
+        w, b, Vp = _pad4_rows(weight.detach().contiguous(), bias.detach().contiguous(), neg=0.0)
+        out = linear_nt(x2, w, b)
+        ctx.save_for_backward(x2, w)
+        ctx.shape = tuple(x.shape)
+        V = weight.shape[0]
+        return (out if Vp == V else out[:, :V].contiguous()).view(*x.shape[:-1], V)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w = ctx.saved_tensors
+        Vp, K = w.shape
+        M = x2.shape[0]
+        V = gy.shape[-1]
+        g = _f32(gy).reshape(M, V)
+        if Vp != V:
+            g = torch.nn.functional.pad(g, (0, Vp - V))
+        gx = matmul_nn(g, w).view(ctx.shape) if ctx.needs_input_grad[0] else None
+        gw = gb = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dwb = torch.zeros(Vp * K + Vp, device=g.device, dtype=torch.float32)
+            wgrad_tc(g, 0, Vp, Vp, x2, 0, K, K, 1, M, dwb, 0, K)
+            _lib.call("slu_colsum_acc", g.data_ptr(), Vp, M, Vp, dwb[Vp * K:].data_ptr(), _lib.stream())
+            gw, gb = dwb[:V * K].view(V, K), dwb[Vp * K:Vp * K + V]
+        return gx, gw, gb

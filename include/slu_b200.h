@@ -156,6 +156,23 @@ int slu_wgrad_tc(const float* G, long ldg, int M, const float* X, long ldx, int 
                  long s_m, long s_n, long s_tap, void* stream);
 
 /* tcgen05 self-test: C[128][N] = A[128][K] . B[N][K]^T (3-pass bf16 split, fp32 accumulate in TMEM). */
+/* ---- ASR heads: frame-wise cross-entropy without materialising [B*T', V] logits (reference models.py:308-314, 321-329:
+ * Linear(256 -> V) -> view(B*T', V) -> F.cross_entropy(ignore_index=-1) + masked arg-max accuracy).  The caller walks the frames
+ * in row chunks: slu_gemm_tc writes a chunk's logits tile, slu_ce_rows turns it IN PLACE into dL/dlogits (softmax - one-hot,
+ * scaled by 1/n_valid; rows with y == -1 become 0) and emits per-row loss / hit flags, the tile then feeds slu_gemm_tc (input
+ * gradient), slu_wgrad_tc (weight gradient) and slu_colsum_acc (bias gradient).
+ *   slu_ce_count : nvalid[0] = #(y != -1), nvalid[1] = 1 / nvalid[0]                       (y: M int64 labels)
+ *   slu_ce_rows  : logits [R][ld] (V <= ld, V <= 12288), y [R]; write_grad = 0 leaves the tile untouched (loss only).
+ *                  A label outside [0, V) other than -1 makes that row's loss NaN.
+ *   slu_ce_finish: loss_acc[0] = sum(row_loss) / n_valid, loss_acc[1] = sum(row_ok) / n_valid, fixed summation order.
+ *   slu_colsum_acc: out[c] += sum_r A[r*ld + c], c < C.      slu_scale: dst[i] = src[i] * g[0] (g on the device). */
+int slu_ce_count(const long long* y, long M, float* nvalid, void* stream);
+int slu_ce_rows(float* logits, long ld, int V, const long long* y, long R, const float* nvalid, int write_grad, float* row_loss,
+                float* row_ok, void* stream);
+int slu_ce_finish(const float* row_loss, const float* row_ok, long M, const float* nvalid, float* loss_acc, void* stream);
+int slu_colsum_acc(const float* A, long ld, long R, int C, float* out, void* stream);
+int slu_scale(const float* src, float* dst, long n, const float* g, void* stream);
+
 /* ---- optimizer step / gradient bucket (reference training.py:19, 64-66, 96-98: torch.optim.Adam, zero_grad/backward/step) ----
  * slu_adam_multi: one Adam step over `n` parameter tensors (fp32 or fp64, any sizes) in ceil(n/64) launches; torch.optim.Adam's
  * single-tensor arithmetic with PER-TENSOR step counts (parameters un-frozen later keep their own bias corrections):

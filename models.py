@@ -40,6 +40,11 @@ def _engine():
     return _pkg.engine
 
 
+def _ops():
+    _engine()
+    return _pkg.ops
+
+
 # ---------------------------------------------------------------------------------------------
 # small parameter-free layers (names kept: they appear in pickles / isinstance checks)
 # ---------------------------------------------------------------------------------------------
@@ -239,25 +244,32 @@ class PretrainedModel(torch.nn.Module):
         if self._on_gpu():
             y_phoneme, y_word = y_phoneme.cuda(), y_word.cuda()
         out, carry = self._phoneme_features(x, with_word=self.pretraining_type != 1)
-        logits = self.phoneme_linear(out)
-        logits = logits.reshape(-1, logits.shape[-1])
-        y_phoneme = y_phoneme.reshape(-1)
-        phoneme_loss = F.cross_entropy(logits, y_phoneme, ignore_index=-1)
-        phoneme_acc = _masked_acc(logits, y_phoneme)
+        phoneme_loss, phoneme_acc = self._frame_ce(self.phoneme_linear, out, y_phoneme)
         if self.pretraining_type == 1:          # phoneme-only pre-training: skip the word module
             return phoneme_loss, torch.tensor([0.]), phoneme_acc, torch.tensor([0.])
         out = self._word_features(out, carry)
-        logits = self.word_linear(out)
-        logits = logits.reshape(-1, logits.shape[-1])
-        y_word = y_word.reshape(-1)
-        word_loss = F.cross_entropy(logits, y_word, ignore_index=-1)
-        word_acc = _masked_acc(logits, y_word)
+        word_loss, word_acc = self._frame_ce(self.word_linear, out, y_word)
         return phoneme_loss, word_loss, phoneme_acc, word_acc
+
+    def _frame_ce(self, linear, feats, y):
+        """Frame-wise classification head: Linear -> cross_entropy(ignore_index=-1) + masked accuracy (models.py:308-314,
+        321-329).  On CUDA: the chunked tcgen05 head that never holds the [B*T', V] logits (ops.LinearCE); on the CPU: torch ops."""
+        if self.is_cuda:
+            return _ops().linear_ce(feats, linear.weight, linear.bias, y)
+        logits = linear(feats)
+        logits = logits.reshape(-1, logits.shape[-1])
+        y = y.reshape(-1)
+        return F.cross_entropy(logits, y, ignore_index=-1), _masked_acc(logits, y)
+
+    def _logits(self, linear, feats):
+        if self.is_cuda:
+            return _ops().LinearNT.apply(feats, linear.weight, linear.bias)
+        return linear(feats)
 
     def compute_posteriors(self, x):
         """(phoneme_logits [B,T/640,P], word_logits [B,T/2560,V]) (models.py:333-347)."""
         ph, carry = self._phoneme_features(x)
-        return self.phoneme_linear(ph), self.word_linear(self._word_features(ph, carry))
+        return self._logits(self.phoneme_linear, ph), self._logits(self.word_linear, self._word_features(ph, carry))
 
     def compute_features(self, x):
         """[B,T] -> [B, T/2560, 256] word-module features (models.py:349-361)."""

@@ -315,3 +315,48 @@ def test_wgrad_two_source_rows_and_frame_shift(pkg, B, T, shift):
         torch.cuda.synchronize()
         assert out[1 - d].abs().max().item() == 0                        # the other direction's block is untouched
         assert rel_err(out[d].cpu(), ref) < 1e-4, (d, rel_err(out[d].cpu(), ref))
+
+
+@pytest.mark.parametrize("M,V,chunk", [(300, 42, 4096), (5000, 10000, 2048), (130, 1000, 128), (64, 256, 4096)])
+def test_linear_ce_head_fwd_bwd(pkg, monkeypatch, M, V, chunk):
+    """Chunked Linear + cross-entropy(ignore_index=-1) + masked accuracy (ops.LinearCE) against fp64 torch: loss, accuracy,
+    dX, dW, db; V = 42 exercises the pad-to-4 path, chunk < M the multi-chunk accumulation with a ragged last chunk."""
+    monkeypatch.setattr(pkg.ops, "CE_CHUNK", chunk)
+    rs = np.random.RandomState(M + V)
+    x = torch.from_numpy(rs.standard_normal((M, 256)).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((V, 256)) / 16).astype(np.float32))
+    b = torch.from_numpy(rs.standard_normal(V).astype(np.float32))
+    y = torch.from_numpy(rs.randint(-1, V, size=M).astype(np.int64))
+    y[:3] = -1
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    logits = xr @ wr.t() + br
+    ref = torch.nn.functional.cross_entropy(logits, y, ignore_index=-1)
+    valid = y != -1
+    ref_acc = (logits.max(1)[1][valid] == y[valid]).double().mean()
+    (3.0 * ref).backward()
+    xd, wd, bd = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    loss, acc = pkg.ops.linear_ce(xd, wd, bd, y.cuda())
+    (3.0 * loss).backward()
+    assert abs(loss.item() - ref.item()) < 2e-5 * abs(ref.item())
+    assert abs(acc.item() - ref_acc.item()) < 1e-6
+    assert rel_err(xd.grad.cpu(), xr.grad) < GRAD_TOL
+    assert rel_err(wd.grad.cpu(), wr.grad) < GRAD_TOL
+    assert rel_err(bd.grad.cpu(), br.grad) < GRAD_TOL
+    with torch.no_grad():                                           # loss-only path (no gradient GEMMs)
+        l2, a2 = pkg.ops.linear_ce(xd, wd, bd, y.cuda())
+    assert abs(l2.item() - loss.item()) < 1e-6 * abs(loss.item()) and a2.item() == acc.item()
+    lg = pkg.ops.LinearNT.apply(xd, wd, bd)                        # the posterior path (compute_posteriors), differentiable
+    assert rel_err(lg.detach().cpu(), logits.detach()) < FWD_TOL
+    xd.grad = None
+    lg.square().sum().backward()
+    xr.grad = None
+    logits2 = xr @ wr.detach().t() + br.detach()
+    logits2.square().sum().backward()
+    assert rel_err(xd.grad.cpu(), xr.grad) < GRAD_TOL
+
+
+def test_linear_ce_out_of_range_label_is_nan(pkg):
+    x = torch.randn(8, 256, device="cuda"); w = torch.randn(44, 256, device="cuda"); b = torch.zeros(44, device="cuda")
+    y = torch.tensor([0, 1, 2, 44, 3, -1, 5, 6], device="cuda")
+    loss, _ = pkg.ops.linear_ce(x, w, b, y)
+    assert torch.isnan(loss)

@@ -14,7 +14,7 @@ from util import ckpt_params, golden, load_test_wav, make_config, rel_err
 pytestmark = pytest.mark.gpu
 LOGIT_TOL = 1e-3      # north star; we assert 10x tighter where fp32 kernels are used
 GRAD_TOL = 5e-3
-SINC_GRAD_TOL = 5e-3  # the two SincNet cut-off vectors (their chain through the max-normalisation cancels: see csrc/sinc_tc.cu)
+SINC_GRAD_TOL = 1e-2  # the two SincNet cut-off vectors (their chain through the max-normalisation cancels: see csrc/sinc_tc.cu)
 
 
 def gpu_model(params=None, train=False):
