@@ -21,6 +21,8 @@ SIGNATURES = {
     "slu_sincconv_bwd_simt": [_P, _P, _P, _I, _I, _P, _P],
     "slu_sincconv_fwd_tc": [_P, _P, _I, _I, _P, _P, _P, _P],
     "slu_sincconv_bwd_tc": [_P, _P, _P, _I, _I, _P, _P],
+    "slu_sincconv_bwd_jac_tc": [_P, _P, _P, _P, _I, _I, _P, _P, _P],
+    "slu_sinc_filters_jac": [_P, _P, _P, _P],
     "slu_gru_fwd_simt": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_gru_bwd_simt": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "slu_gru_fwd_tc": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
@@ -49,7 +51,7 @@ SIGNATURES = {
     "slu_ce_finish": [_P, _P, _L, _P, _P, _P],
     "slu_colsum_acc": [_P, _L, _L, _I, _P, _P],
     "slu_scale": [_P, _P, _L, _P, _P],
-    "slu_adam_multi": [_P, _I, _F, _F, _F, _F, _P],
+    "slu_adam_multi": [_P, _I, ctypes.c_double, ctypes.c_double, _F, _F, _P],
     "slu_f64_hilo_split": [_P, _P, _P, _I, _P],
     "slu_f64_hilo_merge": [_P, _P, _P, _I, _P],
     "slu_tc_selftest": [_P, _P, _P, _I, _I, _P],

@@ -33,17 +33,19 @@ struct AdamTable {
   int n;
 };
 
+// omb1 = 1 - beta1 and omb2 = 1 - beta2 are formed on the host in double precision (as torch does) and only then rounded.
 template <typename T>
-__device__ __forceinline__ void adam_elem(T& p, T g, T& m, T& v, T beta1, T beta2, T eps, T wd, T step_size, T bc2_sqrt) {
+__device__ __forceinline__ void adam_elem(T& p, T g, T& m, T& v, T omb1, T beta2, T omb2, T eps, T wd, T step_size, T bc2_sqrt) {
   if (wd != T(0)) g += wd * p;                       // L2 penalty (torch.optim.Adam weight_decay)
-  m = m + (g - m) * (T(1) - beta1);                  // exp_avg.lerp_(grad, 1 - beta1)
-  v = v * beta2 + (T(1) - beta2) * g * g;            // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  m = m + (g - m) * omb1;                            // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * beta2 + omb2 * g * g;                      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
   const T denom = sqrt(v) / bc2_sqrt + eps;
   p = p - step_size * (m / denom);                   // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
 
-__global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(const __grid_constant__ AdamTable tab, float beta1, float beta2,
+__global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(const __grid_constant__ AdamTable tab, double beta1d, double beta2d,
                                                                   float eps, float wd) {
+  const float omb1 = (float)(1.0 - beta1d), beta2 = (float)beta2d, omb2 = (float)(1.0 - beta2d);
   // which tensor does this CTA belong to: first_block is ascending, n <= 64
   int lo = 0, hi = tab.n - 1;
   const int blk = blockIdx.x;
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(const __grid_c
     double* p = (double*)t.p; const double* g = (const double*)t.g; double* m = (double*)t.m; double* v = (double*)t.v;
     for (long i = base + threadIdx.x; i < end; i += ADAM_THREADS) {
       double pi = p[i], mi = m[i], vi = v[i];
-      adam_elem<double>(pi, g[i], mi, vi, (double)beta1, (double)beta2, (double)eps, (double)wd, (double)t.step_size, (double)t.bc2_sqrt);
+      adam_elem<double>(pi, g[i], mi, vi, 1.0 - beta1d, beta2d, 1.0 - beta2d, (double)eps, (double)wd, (double)t.step_size, (double)t.bc2_sqrt);
       p[i] = pi; m[i] = mi; v[i] = vi;
     }
     return;
@@ -71,17 +73,17 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(const __grid_c
       const long i = base + (long)(r * ADAM_THREADS + threadIdx.x) * 4;
       float4 pi = *reinterpret_cast<float4*>(p + i), mi = *reinterpret_cast<float4*>(m + i), vi = *reinterpret_cast<float4*>(v + i);
       const float4 gi = __ldg(reinterpret_cast<const float4*>(g + i));
-      adam_elem<float>(pi.x, gi.x, mi.x, vi.x, beta1, beta2, eps, wd, t.step_size, t.bc2_sqrt);
-      adam_elem<float>(pi.y, gi.y, mi.y, vi.y, beta1, beta2, eps, wd, t.step_size, t.bc2_sqrt);
-      adam_elem<float>(pi.z, gi.z, mi.z, vi.z, beta1, beta2, eps, wd, t.step_size, t.bc2_sqrt);
-      adam_elem<float>(pi.w, gi.w, mi.w, vi.w, beta1, beta2, eps, wd, t.step_size, t.bc2_sqrt);
+      adam_elem<float>(pi.x, gi.x, mi.x, vi.x, omb1, beta2, omb2, eps, wd, t.step_size, t.bc2_sqrt);
+      adam_elem<float>(pi.y, gi.y, mi.y, vi.y, omb1, beta2, omb2, eps, wd, t.step_size, t.bc2_sqrt);
+      adam_elem<float>(pi.z, gi.z, mi.z, vi.z, omb1, beta2, omb2, eps, wd, t.step_size, t.bc2_sqrt);
+      adam_elem<float>(pi.w, gi.w, mi.w, vi.w, omb1, beta2, omb2, eps, wd, t.step_size, t.bc2_sqrt);
       *reinterpret_cast<float4*>(p + i) = pi; *reinterpret_cast<float4*>(m + i) = mi; *reinterpret_cast<float4*>(v + i) = vi;
     }
     return;
   }
   for (long i = base + threadIdx.x; i < end; i += ADAM_THREADS) {
     float pi = p[i], mi = m[i], vi = v[i];
-    adam_elem<float>(pi, g[i], mi, vi, beta1, beta2, eps, wd, t.step_size, t.bc2_sqrt);
+    adam_elem<float>(pi, g[i], mi, vi, omb1, beta2, omb2, eps, wd, t.step_size, t.bc2_sqrt);
     p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
@@ -103,7 +105,7 @@ __global__ void f64_hilo_merge_kernel(double* __restrict__ dst, const float* __r
 
 }  // namespace
 
-extern "C" int slu_adam_multi(const void* tensors, int n, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+extern "C" int slu_adam_multi(const void* tensors, int n, double beta1, double beta2, float eps, float weight_decay, void* stream) {
   if (n < 0) return (int)cudaErrorInvalidValue;
   const AdamTensor* src = (const AdamTensor*)tensors;
   for (int base = 0; base < n; base += ADAM_MAX) {

@@ -95,6 +95,44 @@ __global__ void __launch_bounds__(512) sinc_filters_bwd_kernel(const double* __r
   }
 }
 
+// Jacobian banks of the filter synthesis: J[0][c][k] = dW[c][k]/d filt_b1[c], J[1][c][k] = dW[c][k]/d filt_band[c] (fp32 values
+// of an fp64 evaluation of the same chain as sinc_filters_bwd_kernel, the max-normalisation term included).  With them
+//     dL/d theta[c] = sum_k dL/dW[c][k] J_theta[c][k] = sum_{b,t} g0[b][t][c] * (x * J_theta[c])[b][t]
+// i.e. the cut-off gradients are two more strided convolutions of the waveform (banks J_0, J_1) dotted with the routed output
+// gradient -- the heavy cancellation between the direct and the normalisation term happens HERE, analytically, instead of
+// between the rounding errors of a low-precision dW (sinc_tc.cu).
+__global__ void __launch_bounds__(512) sinc_filters_jac_kernel(const double* __restrict__ b1, const double* __restrict__ band,
+                                                               float* __restrict__ J) {
+  __shared__ float red[16];
+  __shared__ double dred[16];
+  const int c = blockIdx.x, k = threadIdx.x;
+  const double f1d = fabs(b1[c]) + 50.0 / 16000.0;
+  const double f2d = f1d + (fabs(band[c]) + 50.0 / 16000.0);
+  const float f1 = (float)f1d, f2 = (float)f2d;
+  const bool on = k < SLU_NTAPS;
+  float bp = -INFINITY;
+  if (on) bp = lowpass_tap(f2, f2 * 16000.0f, k) - lowpass_tap(f1, f1 * 16000.0f, k);
+  const float m = block_max(bp, red);
+  double c1 = 2.0, c2 = 2.0;
+  if (on && k != SLU_PAD) {
+    float t = (float)abs(k - SLU_PAD) / 16000.0f;
+    c1 = 2.0 * (double)cosf((6.283185307179586f * (f1 * 16000.0f)) * t);
+    c2 = 2.0 * (double)cosf((6.283185307179586f * (f2 * 16000.0f)) * t);
+  }
+  const bool tie = on && bp == m;
+  const double ties = block_sum(tie ? 1.0 : 0.0, dred);
+  const double C1 = block_sum(tie ? c1 : 0.0, dred) / ties;       // d max(bp) / d f1 = -C1, d max(bp) / d f2 = C2
+  const double C2 = block_sum(tie ? c2 : 0.0, dred) / ties;
+  if (on) {
+    const double win = (double)hamming_tap(k), md = (double)m, bpd = (double)bp;
+    const double j2 = win * (c2 / md - bpd * C2 / (md * md));       // dW/df2
+    const double j1 = win * (-c1 / md + bpd * C1 / (md * md));      // dW/df1
+    const double sb1 = (b1[c] > 0) - (b1[c] < 0), sbd = (band[c] > 0) - (band[c] < 0);
+    J[(0 * SLU_NFILT + c) * SLU_NTAPS + k] = (float)((j1 + j2) * sb1);   // f1 = |b1| + c0 feeds f2 as well
+    J[(1 * SLU_NFILT + c) * SLU_NTAPS + k] = (float)(j2 * sbd);
+  }
+}
+
 // ---------------- sinc conv + abs + maxpool(2, ceil): CUDA-core fp32 path ------------------------
 // CTA = (utterance b, 32 pooled frames = 64 conv frames); filters are symmetric (W[c][k]==W[c][400-k]),
 // so each thread folds the waveform window:  out = sum_{k<200} W[k]*(x[a+k]+x[a+400-k]) + W[200]*x[a+200].
@@ -229,6 +267,12 @@ extern "C" int slu_sinc_filters_fwd(const double* filt_b1, const double* filt_ba
 extern "C" int slu_sinc_filters_bwd(const double* filt_b1, const double* filt_band, const float* dW, double* d_b1,
                                     double* d_band, void* stream) {
   sinc_filters_bwd_kernel<<<SLU_NFILT, 512, 0, (cudaStream_t)stream>>>(filt_b1, filt_band, dW, d_b1, d_band);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int slu_sinc_filters_jac(const double* filt_b1, const double* filt_band, float* J, void* stream) {
+  sinc_filters_jac_kernel<<<SLU_NFILT, 512, 0, (cudaStream_t)stream>>>(filt_b1, filt_band, J);
   SLU_CHECK_LAUNCH();
   return 0;
 }

@@ -75,9 +75,15 @@ constexpr int WKC = 96 / 8;                                     // k-chunks per 
 // Filter taps arrive through a 2-slot TMA ring (the pre-split bank image is k-chunk-major: one bulk copy per 8-sample chunk
 // of all 80 filters), issued by one elected thread of warp 1 from the very start of the CTA -- they land while all warps
 // stage the waveform image; warp 0 issues the MMAs.  No block-wide barrier inside the tap loop.
+// GRAD = false: forward (epilogue = abs + max-pool + route bits).
+// GRAD = true : cut-off gradients.  `wimg` holds gridDim.z stacked banks (the Jacobian banks of slu_sinc_filters_jac, image rows
+//               z*80 .. z*80+79); the epilogue multiplies the convolution by the routed output gradient (read from gy_in / route)
+//               and reduces over frames: dsum[z*80 + c] += sum_t g0[t][c] * conv_z[t][c]   (fp64 atomics, one per filter per CTA).
+template <bool GRAD>
 __global__ void __launch_bounds__(THREADS, 2)
 sincconv_fwd_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wimg, int T, int L0, int L1,
-                       float* __restrict__ out, uint8_t* __restrict__ route) {
+                       float* __restrict__ out, uint8_t* __restrict__ route, const float* __restrict__ gy_in,
+                       double* __restrict__ dsum) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full_bar[2], empty_bar[2], acc_bar;
   __shared__ uint32_t tmem_base;
@@ -105,9 +111,10 @@ sincconv_fwd_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restr
     const int slot = tap & 1, nch = tap == 5 ? 2 : KC;
     uint8_t* w_hi = w_ring + slot * 2 * W_PART;
     mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(2 * nch * SLU_NFILT * 16));
+    const int n_img = SLU_NFILT * (int)gridDim.z;              // rows of the (stacked) bank image
     for (int part = 0; part < 2; ++part)
       for (int kc = 0; kc < nch; ++kc) {
-        const size_t e = ((((size_t)part * 6 + tap) * WKC + kc) * SLU_NFILT) * 8;
+        const size_t e = ((((size_t)part * 6 + tap) * WKC + kc) * n_img + (size_t)blockIdx.z * SLU_NFILT) * 8;
         tma_load_1d(w_hi + part * W_PART + kc * LBO_W, wimg + e, SLU_NFILT * 16, &full_bar[slot]);
       }
   };
@@ -150,9 +157,52 @@ sincconv_fwd_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restr
     }
   }
 
-  // ---- epilogue: |.| + max over frame pairs + route bits, coalesced along the 80 filters
   mbar_wait(&acc_bar, 0);
   fence_after_sync();
+  if (GRAD) {
+    // ---- epilogue (cut-off gradients): conv[t][c] * routed gradient g0[t][c], summed over the 128 frames of the tile
+    const int q = warp & 3, half = warp >> 2;
+    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 17);    // image buffers are free once acc_bar fired
+    double* part = reinterpret_cast<double*>(smem + 8 * 32 * 17 * 4); // [4 quarters][80] partial sums
+    const int t = t0 + q * 32 + lane;                                 // this thread's frame (TMEM lane)
+    const bool t_on = t < L0;
+    const size_t o = ((size_t)b * L1 + (t_on ? (t >> 1) : 0)) * SLU_NFILT;
+    for (int c0 = half * 48; c0 < (half ? SLU_NFILT : 48); c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      uint4 rt = make_uint4(0, 0, 0, 0);
+      float4 g4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t_on) {
+        rt = __ldg(reinterpret_cast<const uint4*>(route + o + c0));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g4[i] = __ldg(reinterpret_cast<const float4*>(gy_in + o + c0) + i);
+      }
+      const uint32_t rw[4] = {rt.x, rt.y, rt.z, rt.w};
+      const float gv[16] = {g4[0].x, g4[0].y, g4[0].z, g4[0].w, g4[1].x, g4[1].y, g4[1].z, g4[1].w,
+                            g4[2].x, g4[2].y, g4[2].z, g4[2].w, g4[3].x, g4[3].y, g4[3].z, g4[3].w};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t rb = (rw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+        const bool take = t_on && ((rb & 1u) == (uint32_t)(t & 1)) && !(rb & 4u);   // this frame won the pair and |.| has a gradient
+        tr[lane * 17 + i] = take ? ((rb & 2u) ? -gv[i] : gv[i]) * v[i] : 0.f;
+      }
+      __syncwarp();
+      if (lane < 16) {                                                // lane i sums column c0 + i over this warp's 32 frames
+        double s = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) s += (double)tr[r * 17 + lane];
+        part[q * SLU_NFILT + c0 + lane] = s;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (tid < SLU_NFILT)
+      atomicAdd(dsum + blockIdx.z * SLU_NFILT + tid, (part[tid] + part[SLU_NFILT + tid]) + (part[2 * SLU_NFILT + tid] + part[3 * SLU_NFILT + tid]));
+  } else
+  // ---- epilogue: |.| + max over frame pairs + route bits, coalesced along the 80 filters
   {
     const int q = warp & 3, half = warp >> 2;                         // TMEM lane quarter; columns [0,48) / [48,80) in 16-col steps
     float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 17);    // image buffers are free once acc_bar fired
@@ -334,9 +384,27 @@ extern "C" int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T,
   const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
   int e = slu_presplit_rows_cm(W, SLU_NTAPS, 1, SLU_STRIDE, 6, SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // bank[c][80a + k], 0 beyond tap 400
   if (e) return e;
-  SLU_SMEM_ONCE(sincconv_fwd_tc_kernel, FWD_SMEM);
+  SLU_SMEM_ONCE(sincconv_fwd_tc_kernel<false>, FWD_SMEM);
   dim3 grid((L0 + TF - 1) / TF, B);
-  sincconv_fwd_tc_kernel<<<grid, THREADS, FWD_SMEM, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)img, T, L0, L1, out, route);
+  sincconv_fwd_tc_kernel<false><<<grid, THREADS, FWD_SMEM, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)img, T, L0, L1, out, route,
+                                                                                   nullptr, nullptr);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}
+
+// Cut-off gradients without a dW detour: d[0..79] += dL/d filt_b1, d[80..159] += dL/d filt_band (fp64, caller-zeroed) as two
+// more strided convolutions of the waveform with the Jacobian banks J[2][80][401] (slu_sinc_filters_jac) dotted with the routed
+// output gradient.  `img` = scratch for the pre-split banks: 2*6*160*96 bf16 values.
+extern "C" int slu_sincconv_bwd_jac_tc(const float* x, const float* gy, const uint8_t* route, const float* J, int B, int T, double* d,
+                                       void* img, void* stream) {
+  if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
+  const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
+  int e = slu_presplit_rows_cm(J, SLU_NTAPS, 1, SLU_STRIDE, 6, 2 * SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // both banks: 160 image rows
+  if (e) return e;
+  SLU_SMEM_ONCE(sincconv_fwd_tc_kernel<true>, FWD_SMEM);
+  dim3 grid((L0 + TF - 1) / TF, B, 2);
+  sincconv_fwd_tc_kernel<true><<<grid, THREADS, FWD_SMEM, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)img, T, L0, L1, nullptr,
+                                                                                  const_cast<uint8_t*>(route), gy, d);
   SLU_CHECK_LAUNCH();
   return 0;
 }

@@ -250,7 +250,6 @@ class SincFrontend(torch.autograd.Function):
             _lib.call("slu_sincconv_fwd_simt", _lib.ptr(x), _lib.ptr(W), B, T, _lib.ptr(out), _lib.ptr(route), _lib.stream())
         if need:
             ctx.save_for_backward(x, b1, band, route)
-            ctx.slot_dw = _reserve(ctx, 80 * 401)                  # dW scratch shares the arena's single memset
             ctx.slot_f64 = _reserve(ctx, 160, f64=True)            # d_b1 | d_band (fp64, like the parameters)
         return out
 
@@ -259,15 +258,20 @@ class SincFrontend(torch.autograd.Function):
         x, b1, band, route = ctx.saved_tensors
         B, T = x.shape
         gy = _f32(gy)
-        dW = _zeros(ctx, ctx.slot_dw, (80, 401))
-        if SINC_IMPL == "tc":
-            _lib.call("slu_sincconv_bwd_tc", _lib.ptr(x), _lib.ptr(gy), _lib.ptr(route), B, T, _lib.ptr(dW), _lib.stream())
-        else:
-            _lib.call("slu_sincconv_bwd_simt", _lib.ptr(x), _lib.ptr(gy), _lib.ptr(route), B, T, _lib.ptr(dW), _lib.stream())
         d = _zeros(ctx, ctx.slot_f64, (160,), f64=True)
         d_b1, d_band = d[:80], d[80:]
-        _lib.call("slu_sinc_filters_bwd", _lib.ptr(b1), _lib.ptr(band), _lib.ptr(dW), d_b1.data_ptr(), d_band.data_ptr(),
-                  _lib.stream())
+        if SINC_IMPL == "tc":
+            # cut-off gradients = two more convolutions of the waveform (Jacobian banks) dotted with the routed gradient: no dW
+            J = torch.empty(2, 80, 401, device=x.device, dtype=torch.float32)
+            img = torch.empty(2 * 6 * 160 * 96, device=x.device, dtype=torch.bfloat16)
+            _lib.call("slu_sinc_filters_jac", _lib.ptr(b1), _lib.ptr(band), _lib.ptr(J), _lib.stream())
+            _lib.call("slu_sincconv_bwd_jac_tc", _lib.ptr(x), _lib.ptr(gy), _lib.ptr(route), _lib.ptr(J), B, T, d.data_ptr(),
+                      img.data_ptr(), _lib.stream())
+        else:
+            dW = torch.empty(80, 401, device=x.device, dtype=torch.float32)
+            _lib.call("slu_sincconv_bwd_simt", _lib.ptr(x), _lib.ptr(gy), _lib.ptr(route), B, T, _lib.ptr(dW), _lib.stream())
+            _lib.call("slu_sinc_filters_bwd", _lib.ptr(b1), _lib.ptr(band), _lib.ptr(dW), d_b1.data_ptr(), d_band.data_ptr(),
+                      _lib.stream())
         return None, d_b1, d_band
 
 

@@ -28,6 +28,10 @@ int slu_sinc_filters_fwd(const double* filt_b1, const double* filt_band, float* 
 int slu_sinc_filters_bwd(const double* filt_b1, const double* filt_band, const float* dW, double* d_b1, double* d_band,
                          void* stream);
 
+/* Jacobian banks J[2][80][401] of the synthesis: J[0] = dW/d filt_b1, J[1] = dW/d filt_band (per filter row; the
+ * max-normalisation and |.| terms included, evaluated in fp64) -- the operand of slu_sincconv_bwd_jac_tc. */
+int slu_sinc_filters_jac(const double* filt_b1, const double* filt_band, float* J, void* stream);
+
 /* conv1d(x[B][1][T], W, stride 80, pad 200) + Abs + MaxPool1d(2, ceil) -- replaces models.py:108, :163-168, :205
  * (LeakyReLU :211 is the identity on the non-negative result, Dropout(0) :218 likewise).
  * out[B][L1][80] (time-major), L0=(T-1)/80+1, L1=(L0+1)/2.  route[B][L1][80] (u8, may be NULL): bit0 = which
@@ -42,6 +46,13 @@ int slu_sincconv_bwd_simt(const float* x, const float* gy, const uint8_t* route,
  * `img` = scratch for the pre-split bank (2*6*80*96 bf16 values).  slu_sincconv_bwd_tc needs dW zero-filled (split-K atomics). */
 int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T, float* out, uint8_t* route, void* img, void* stream);
 int slu_sincconv_bwd_tc(const float* x, const float* gy, const uint8_t* route, int B, int T, float* dW, void* stream);
+/* The cut-off gradients directly (no dW): d[0..79] += dL/d filt_b1, d[80..159] += dL/d filt_band (fp64, caller-zeroed) =
+ * sum over frames of the routed output gradient times the convolution of the waveform with the Jacobian banks J
+ * (slu_sinc_filters_jac) -- same tcgen05 kernel as the forward, two stacked banks, reducing epilogue.  The cancellation between
+ * the direct and the max-normalisation term happens analytically inside J, so bf16 hi/lo operands keep fp32-class accuracy
+ * (the dW route loses ~3 digits there).  `img` = scratch for the pre-split banks (2*6*160*96 bf16 values). */
+int slu_sincconv_bwd_jac_tc(const float* x, const float* gy, const uint8_t* route, const float* J, int B, int T, double* d,
+                            void* img, void* stream);
 
 /* Persistent bidirectional GRU recurrence (h0 = 0) with fused gate non-linearities, Dropout mask multiply and
  * Downsample -- replaces nn.GRU (_VF.gru / cuDNN RNN) at models.py:232/262/686 plus RNNSelect :138-149,
@@ -186,7 +197,7 @@ struct SluAdamTensor {
   int is_f64;                                 /* 0: float, 1: double */
   int pad;
 };
-int slu_adam_multi(const void* tensors, int n, float beta1, float beta2, float eps, float weight_decay, void* stream);
+int slu_adam_multi(const void* tensors, int n, double beta1, double beta2, float eps, float weight_decay, void* stream);
 /* fp64 gradients inside an fp32 all-reduce bucket: split into (hi, lo) floats before the collective, merge after it. */
 int slu_f64_hilo_split(const double* src, float* hi, float* lo, int n, void* stream);
 int slu_f64_hilo_merge(double* dst, const float* hi, const float* lo, int n, void* stream);

@@ -124,8 +124,8 @@ def test_sinc_frontend_fwd_bwd(pkg, monkeypatch, impl, B, T):
     assert b1g.grad.dtype == torch.float64
     scale = max(b1.grad.abs().max().item(), band.grad.abs().max().item())
     for got, ref_g in ((b1g.grad.cpu(), b1.grad), (bandg.grad.cpu(), band.grad)):
-        # the analytic filter chain cancels heavily: the 2^-17 split error of the tcgen05 dW is amplified to <~0.5 %
-        tol = (5e-3 if impl == "tc" else GRAD_TOL) * scale + 1e-4
+        # the chain through the max-normalisation cancels heavily; the tcgen05 path resolves it analytically (Jacobian banks)
+        tol = GRAD_TOL * scale + 1e-4
         assert (got - ref_g).abs().max().item() < tol, ((got - ref_g).abs().max().item(), scale)
 
 

@@ -14,7 +14,8 @@ from util import ckpt_params, golden, load_test_wav, make_config, rel_err
 pytestmark = pytest.mark.gpu
 LOGIT_TOL = 1e-3      # north star; we assert 10x tighter where fp32 kernels are used
 GRAD_TOL = 5e-3
-SINC_GRAD_TOL = 1e-2  # the two SincNet cut-off vectors (their chain through the max-normalisation cancels: see csrc/sinc_tc.cu)
+SINC_GRAD_TOL = 1e-3  # the two SincNet cut-off vectors: their chain through the max-normalisation cancels, which the Jacobian-bank
+                      # backward (csrc/sinc_tc.cu, slu_sincconv_bwd_jac_tc) resolves analytically; measured ~2e-5
 
 
 def gpu_model(params=None, train=False):
