@@ -13,6 +13,7 @@ _P = ctypes.c_void_p
 _I = ctypes.c_int
 _L = ctypes.c_long
 _F = ctypes.c_float
+_U = ctypes.c_ulonglong
 SIGNATURES = {
     # name: argtypes (all return int = cudaError_t, 0 on success)
     "slu_sinc_filters_fwd": [_P, _P, _P, _P],
@@ -23,11 +24,11 @@ SIGNATURES = {
     "slu_sincconv_bwd_tc": [_P, _P, _P, _I, _I, _P, _P],
     "slu_sincconv_bwd_jac_tc": [_P, _P, _P, _P, _I, _I, _P, _P, _P],
     "slu_sinc_filters_jac": [_P, _P, _P, _P],
-    "slu_gru_fwd_simt": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
-    "slu_gru_bwd_simt": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
-    "slu_gru_fwd_tc": [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
-    "slu_gru_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
-    "slu_bigru_bwd_tc": [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "slu_gru_fwd_simt": [_P, _P, _P, _P, _F, _U, _I, _I, _I, _P, _P, _P, _P],
+    "slu_gru_bwd_simt": [_P, _P, _F, _U, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "slu_gru_fwd_tc": [_P, _P, _P, _P, _F, _U, _I, _I, _I, _P, _P, _P, _P],
+    "slu_gru_bwd_tc": [_P, _P, _F, _U, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "slu_bigru_bwd_tc": [_P, _P, _F, _U, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "slu_set_gru_precision": [_I],
     "slu_gru_rows_per_cta": [_I],
     "slu_debug_gru_phase_clocks": [_P],
@@ -40,6 +41,7 @@ SIGNATURES = {
     "slu_stream_fork": [_P, _I, _P],
     "slu_stream_join": [_P, _I],
     "slu_dropout_mask": [_P, _L, _F, ctypes.c_ulonglong, _P],
+    "slu_dropout_mask_gru": [_P, _I, _I, _F, ctypes.c_ulonglong, _P],
     "slu_leaky_bwd_bias": [_P, _P, _F, _P, _P, _L, _I, _P],
     "slu_gemm_tc": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "slu_presplit_bf16": [_P, _L, _L, _L, _I, _I, _I, _P, _P],

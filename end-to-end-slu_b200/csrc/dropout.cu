@@ -3,29 +3,29 @@
 // already scaled by 1/(1-p) as the fp32 mask rows the persistent-GRU kernels stream through their TMA ring.
 // HBM-bound: 4 B written per element, nothing read.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
 
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-  c[0] = hi1 ^ c[1] ^ k0;
-  c[1] = lo1;
-  c[2] = hi0 ^ c[3] ^ k1;
-  c[3] = lo0;
-}
+__device__ __forceinline__ void philox4x32_10(uint64_t ctr, uint64_t seed, uint32_t (&out)[4]) { slu_philox4x32_10(ctr, seed, out); }
 
-__device__ __forceinline__ void philox4x32_10(uint64_t ctr, uint64_t seed, uint32_t (&out)[4]) {
-  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+// The canonical GRU-layer mask (philox.cuh) written out as a tensor: what slu_gru_{fwd,bwd}_* generate in registers when they are
+// given (drop_p, drop_seed) instead of a mask -- for tests and for callers that want to inspect / reuse the mask.
+__global__ void __launch_bounds__(256) dropout_mask_gru_kernel(float* __restrict__ mask, int B, int T, uint32_t keep_threshold, float scale,
+                                                               uint64_t seed) {
+  const long n = (long)B * ((T + 3) >> 2) * 256;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int col = (int)(i & 255);
+    const long r = i >> 8;
+    const int tg = (int)(r % ((T + 3) >> 2)), b = (int)(r / ((T + 3) >> 2));
+    uint32_t w[4];
+    slu_gru_mask_draws(b, col, tg, seed, w);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
+    for (int k = 0; k < 4; ++k) {
+      const int t = 4 * tg + k;
+      if (t < T) mask[((long)b * T + t) * 256 + col] = w[k] < keep_threshold ? scale : 0.f;
+    }
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) out[i] = c[i];
 }
 
 __global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ mask, long n, uint32_t keep_threshold, float scale,
@@ -54,12 +54,22 @@ extern "C" int slu_dropout_mask(float* mask, long n, float p, unsigned long long
   if (n <= 0) return 0;
   if (!(p >= 0.f && p < 1.f)) return (int)cudaErrorInvalidValue;
   const double keep = 1.0 - (double)p;
-  const double th = keep * 4294967296.0;
-  const uint32_t threshold = th >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)th;
+  const uint32_t threshold = slu_keep_threshold(p);
   const long n4 = (n + 3) >> 2;
   long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   dropout_mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, n, threshold, (float)(1.0 / keep), seed);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int slu_dropout_mask_gru(float* mask, int B, int T, float p, unsigned long long seed, void* stream) {
+  if (B <= 0 || T <= 0) return 0;
+  if (!(p >= 0.f && p < 1.f)) return (int)cudaErrorInvalidValue;
+  const long n = (long)B * ((T + 3) >> 2) * 256;
+  long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dropout_mask_gru_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, B, T, slu_keep_threshold(p), (float)(1.0 / (1.0 - (double)p)), seed);
   SLU_CHECK_LAUNCH();
   return 0;
 }

@@ -12,6 +12,7 @@
 //   stash  [B][T][1024]  col = d*512 + s*128 + j      s: 0=r 1=z 2=n 3=hn (=W_hn h + b_hn), training only
 //   mask   [B][T][256]   dropout keep-mask pre-scaled by 1/(1-p), or NULL
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -34,7 +35,8 @@ __device__ __forceinline__ float reduce_scatter4(const float v[4], int q) {
 template <bool STASH>
 __global__ void __launch_bounds__(512, 1)
 gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
-               const float* __restrict__ mask, int B, int T, int ds, float* __restrict__ y_full,
+               const float* __restrict__ mask, uint32_t drop_thr, float drop_scale, uint64_t drop_seed, int B, int T, int ds,
+               float* __restrict__ y_full,
                float* __restrict__ y_out, float* __restrict__ stash) {
   extern __shared__ float4 smem4[];
   float4* Ws = smem4;                                        // [(g*32 + c)*128 + j] = W[g*128+j][4c..4c+3]
@@ -58,7 +60,12 @@ gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, con
     if (valid) {
       const float* p = gx + ((size_t)b * T + t) * 768 + d * SLU_G3 + j;
       r_ = __ldg(p); z_ = __ldg(p + 128); n_ = __ldg(p + 256);
-      m_ = mask ? __ldg(mask + ((size_t)b * T + t) * 256 + d * SLU_H + j) : 1.f;
+      if (mask) m_ = __ldg(mask + ((size_t)b * T + t) * 256 + d * SLU_H + j);
+      else if (drop_thr != 0u) {          // the canonical Philox mask (philox.cuh); this variant simply draws per element
+        uint32_t w[4];
+        slu_gru_mask_draws(b, d * SLU_H + j, t >> 2, drop_seed, w);
+        m_ = w[t & 3] < drop_thr ? drop_scale : 0.f;
+      } else m_ = 1.f;
     }
   };
   if (T > 0) load_step(d ? T - 1 : 0, gxr, gxz, gxn, mk);
@@ -123,7 +130,8 @@ gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, con
 //   dhn [B][T][256]  (dn*r: the n-gate gradient wrt W_hn h + b_hn -> dW_hh / db_hh n-rows)
 // and carries dh through  dh_{t-1} += W_hh^T [dr, dz, dhn].
 __global__ void __launch_bounds__(512, 1)
-gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, const float* __restrict__ y_full,
+gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, uint32_t drop_thr, float drop_scale,
+               uint64_t drop_seed, const float* __restrict__ y_full,
                const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds,
                float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ db_ih, float* __restrict__ db_hh) {
   extern __shared__ float4 smem4[];
@@ -156,6 +164,11 @@ gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask,
       if (!((t & 1) == 0 && t == T - 1)) g *= 0.5f;
     }
     if (mask) g *= __ldg(mask + bt * 256 + d * SLU_H + j);
+    else if (drop_thr != 0u) {
+      uint32_t w[4];
+      slu_gru_mask_draws((int)(bt / T), d * SLU_H + j, (int)(bt % T) >> 2, drop_seed, w);
+      g *= w[(int)(bt % T) & 3] < drop_thr ? drop_scale : 0.f;
+    }
     v.dy = g;
   };
   In cur_in, nxt_in;
@@ -210,26 +223,33 @@ gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask,
 
 }  // namespace
 
-extern "C" int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T,
-                                int ds, float* y_full, float* y_out, float* stash, void* stream) {
-  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2)) return (int)cudaErrorInvalidValue;
+extern "C" int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, float drop_p,
+                                unsigned long long drop_seed, int B, int T, int ds, float* y_full, float* y_out, float* stash,
+                                void* stream) {
+  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || !(drop_p >= 0.f && drop_p < 1.f)) return (int)cudaErrorInvalidValue;
+  const uint32_t thr = (!drop_mask && drop_p > 0.f) ? slu_keep_threshold(drop_p) : 0u;
+  const float dscale = (float)(1.0 / (1.0 - (double)drop_p));
   const size_t smem = W_SMEM + 2 * BT * SLU_H * sizeof(float);
   SLU_SMEM_ONCE(gru_fwd_kernel<true>, smem);
   SLU_SMEM_ONCE(gru_fwd_kernel<false>, smem);
   dim3 grid((B + BT - 1) / BT, 2);
-  if (stash) gru_fwd_kernel<true><<<grid, 512, smem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, stash);
-  else gru_fwd_kernel<false><<<grid, 512, smem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, nullptr);
+  if (stash) gru_fwd_kernel<true><<<grid, 512, smem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, thr, dscale, drop_seed, B, T, ds, y_full, y_out, stash);
+  else gru_fwd_kernel<false><<<grid, 512, smem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, thr, dscale, drop_seed, B, T, ds, y_full, y_out, nullptr);
   SLU_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                                const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh, void* stream) {
-  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (db_ih == nullptr) != (db_hh == nullptr)) return (int)cudaErrorInvalidValue;
+extern "C" int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, float drop_p, unsigned long long drop_seed,
+                                const float* y_full, const float* stash, const float* w_hh, int B, int T, int ds, float* dgx,
+                                float* dhn, float* db_ih, float* db_hh, void* stream) {
+  if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (db_ih == nullptr) != (db_hh == nullptr) || !(drop_p >= 0.f && drop_p < 1.f))
+    return (int)cudaErrorInvalidValue;
+  const uint32_t thr = (!drop_mask && drop_p > 0.f) ? slu_keep_threshold(drop_p) : 0u;
+  const float dscale = (float)(1.0 / (1.0 - (double)drop_p));
   const size_t smem = W_SMEM + 2 * BT * SLU_G3 * sizeof(float);
   SLU_SMEM_ONCE(gru_bwd_kernel, smem);
   dim3 grid((B + BT - 1) / BT, 2);
-  gru_bwd_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh);
+  gru_bwd_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(dy_out, drop_mask, thr, dscale, drop_seed, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh);
   SLU_CHECK_LAUNCH();
   return 0;
 }

@@ -15,6 +15,7 @@
 // The x-projection gx = x.W_ih^T + b_ih is a dense GEMM done beforehand for both directions (see gemm_tc.cu).
 // Same layouts / semantics as gru_simt.cu (slu_gru_fwd_simt); restates nn.GRU at models.py:232/262/686.
 #include "common.cuh"
+#include "philox.cuh"
 #include "tc05.cuh"
 
 namespace {
@@ -127,8 +128,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 template <int NB, int NR, bool STASH, bool FULL, int PASSES>
 __global__ void __launch_bounds__(block_threads(NR), 1)
 gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
-                  const float* __restrict__ mask, int B, int T, int ds, int tile0, float* __restrict__ y_full,
-                  float* __restrict__ y_out, float* __restrict__ stash) {
+                  const float* __restrict__ mask, uint32_t drop_thr, float drop_scale, uint64_t drop_seed, int B, int T, int ds, int tile0,
+                  float* __restrict__ y_full, float* __restrict__ y_out, float* __restrict__ stash) {
   constexpr int NC = NR * 128 / TC_THREADS;         // batch columns per thread (NR real rows; the MMA is N = NB wide)
   constexpr uint32_t LBO = NB * 16 + 16;             // padded: conflict-free 2-byte operand stores
   __shared__ __align__(128) uint8_t h_tile[2 * 16 * LBO];   // [hi | lo] x 16 k-chunks x (NB rows x 16 B + pad)
@@ -200,6 +201,11 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   float hprev[NC], pend[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) { hprev[c] = 0.f; pend[c] = 0.f; }
+  // Dropout keep-mask: explicit rows (`mask`, streamed through the ring) or, with drop_thr != 0, the canonical Philox mask of
+  // philox.cuh generated in registers -- one call per 4 time steps per element, nothing read from or written to HBM.
+  const bool rng = mask == nullptr && drop_thr != 0u;
+  uint32_t rnd[NC][4];
+  int rnd_group = -1;
   const uint32_t idesc = PASSES != 1 ? idesc_bf16_f32(128, NB) : idesc_f16_f32(128, NB);
   const uint32_t acc_addr = tmem + lane_base + ACC_COL + c0;
   const uint64_t bdesc_hi = smem_desc(smem_u32(h_hi), LBO, 128), bdesc_lo = smem_desc(smem_u32(h_lo), LBO, 128);
@@ -237,10 +243,15 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
     const float* gxs = in_ring + (s % FWD_RING) * SLOT + c0 * 384 + j;
     const float* mks = in_ring + (s % FWD_RING) * SLOT + NR * 384 + c0 * 128 + j;
     float xr[NC], xz[NC], xn[NC], mk[NC];
+    if (rng && (t >> 2) != rnd_group) {          // uniform over the CTA: every thread is at the same t
+      rnd_group = t >> 2;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) slu_gru_mask_draws(min(b0 + c0 + c, B - 1), d * SLU_H + j, rnd_group, drop_seed, rnd[c]);
+    }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       xr[c] = gxs[c * 384] + bhr; xz[c] = gxs[c * 384 + 128] + bhz; xn[c] = gxs[c * 384 + 256];
-      mk[c] = mask ? mks[c * 128] : 1.f;
+      mk[c] = mask ? mks[c * 128] : (rng ? (rnd[c][t & 3] < drop_thr ? drop_scale : 0.f) : 1.f);
     }
     PHASE(2);                        // TMA ring wait + input reads
     if (s == 0) {
@@ -332,7 +343,8 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
 // N = NB.  W_hh^T (hi/lo) is stationary in TMEM (2 x 192 columns); dG = (dr, dz, dhn) is the shared-memory B tile.
 template <int NB, int NR, bool FULL, int PASSES>
 __global__ void __launch_bounds__(block_threads(NR), 1)
-gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, const float* __restrict__ y_full,
+gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, uint32_t drop_thr, float drop_scale,
+                  uint64_t drop_seed, const float* __restrict__ y_full,
                   const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds, int tile0,
                   float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ db_ih, float* __restrict__ db_hh) {
   constexpr int NC = NR * 128 / TC_THREADS;
@@ -411,6 +423,9 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
   float dh_direct[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) dh_direct[c] = 0.f;
+  const bool rng = mask == nullptr && drop_thr != 0u;      // regenerate the forward's Philox mask (see the forward kernel)
+  uint32_t rnd[NC][4];
+  int rnd_group = -1;
   float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_hn = 0.f;    // bias gradients: sums over this thread's columns and all steps
 
   if (SVC && !is_compute) {          // service warps (see the forward kernel)
@@ -443,9 +458,14 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
     const float* dys = sl + NR * 640 + c0 * 128 + j;
     const float* mks = sl + NR * 768 + c0 * 128 + j;
     float base[NC], zc[NC], f_n[NC], f_z[NC], f_r[NC], rc[NC];
+    if (rng && (t >> 2) != rnd_group) {
+      rnd_group = t >> 2;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) slu_gru_mask_draws(min(b0 + c0 + c, B - 1), d * SLU_H + j, rnd_group, drop_seed, rnd[c]);
+    }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const float mkv = mask ? mks[c * 128] : 1.f;
+      const float mkv = mask ? mks[c * 128] : (rng ? (rnd[c][t & 3] < drop_thr ? drop_scale : 0.f) : 1.f);
       const float r = sts[c * 512], z = sts[c * 512 + 128], n = sts[c * 512 + 256];
       base[c] = dh_direct[c] + dys[c * 128] * (dscale * mkv);            // dL/dh without the recurrent part
       zc[c] = z; rc[c] = r;
@@ -548,80 +568,101 @@ extern "C" int slu_set_gru_precision(int mode) {
 static int pick_rows(int B) { return B >= 1184 ? 16 : (B >= 592 ? 8 : 4); }
 extern "C" int slu_gru_rows_per_cta(int B) { return pick_rows(B); }
 
+struct DropArgs { uint32_t thr; float scale; uint64_t seed; };
+static DropArgs drop_args(const float* mask, float p, unsigned long long seed) {
+  DropArgs a = {0u, 1.f, 0ull};
+  if (!mask && p > 0.f) { a.thr = slu_keep_threshold(p); a.scale = (float)(1.0 / (1.0 - (double)p)); a.seed = seed; }
+  return a;
+}
+
 template <int NR, bool STASH, bool FULL>
-static void launch_fwd(dim3 grid, cudaStream_t st, const float* gx, const float* w_hh, const float* b_hh, const float* mask,
-                       int B, int T, int ds, int tile0, float* y_full, float* y_out, float* stash) {
+static int launch_fwd(dim3 grid, cudaStream_t st, const float* gx, const float* w_hh, const float* b_hh, const float* mask, DropArgs dr,
+                      int B, int T, int ds, int tile0, float* y_full, float* y_out, float* stash) {
   constexpr size_t smem = ((size_t)FWD_RING * NR * 512 + (size_t)(TC_THREADS / 32) * WT_BUF) * sizeof(float);   // input ring + weight transposers
   constexpr int P = 2 * NR <= 16 ? 2 : 3;            // stacked hi/lo rows fit the 16-wide MMA tile
-  static int a3 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, 3>, smem);
-  static int a2 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, P>, smem);
-  static int a1 = slu_set_smem((const void*)gru_fwd_tc_kernel<16, NR, STASH, FULL, 1>, smem);
-  (void)a3; (void)a2; (void)a1;
-  if (g_gru_mode == 0) gru_fwd_tc_kernel<16, NR, STASH, FULL, P><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
-  else if (g_gru_mode == 2) gru_fwd_tc_kernel<16, NR, STASH, FULL, 3><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
-  else gru_fwd_tc_kernel<16, NR, STASH, FULL, 1><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, B, T, ds, tile0, y_full, y_out, stash);
+  SLU_SMEM_ONCE((gru_fwd_tc_kernel<16, NR, STASH, FULL, 3>), smem);
+  SLU_SMEM_ONCE((gru_fwd_tc_kernel<16, NR, STASH, FULL, P>), smem);
+  SLU_SMEM_ONCE((gru_fwd_tc_kernel<16, NR, STASH, FULL, 1>), smem);
+  if (g_gru_mode == 0) gru_fwd_tc_kernel<16, NR, STASH, FULL, P><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, dr.thr, dr.scale, dr.seed, B, T, ds, tile0, y_full, y_out, stash);
+  else if (g_gru_mode == 2) gru_fwd_tc_kernel<16, NR, STASH, FULL, 3><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, dr.thr, dr.scale, dr.seed, B, T, ds, tile0, y_full, y_out, stash);
+  else gru_fwd_tc_kernel<16, NR, STASH, FULL, 1><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, dr.thr, dr.scale, dr.seed, B, T, ds, tile0, y_full, y_out, stash);
+  return 0;
 }
 
 template <int NR>
-static void run_fwd(cudaStream_t st, const float* gx, const float* w_hh, const float* b_hh, const float* mask, int B, int T, int ds,
-                    float* y_full, float* y_out, float* stash) {
+static int run_fwd(cudaStream_t st, const float* gx, const float* w_hh, const float* b_hh, const float* mask, DropArgs dr, int B, int T,
+                   int ds, float* y_full, float* y_out, float* stash) {
   const int full = B / NR, rem = B % NR;
+  int e = 0;
   if (full) {
-    if (stash) launch_fwd<NR, true, true>(dim3(full, 2), st, gx, w_hh, b_hh, mask, B, T, ds, 0, y_full, y_out, stash);
-    else launch_fwd<NR, false, true>(dim3(full, 2), st, gx, w_hh, b_hh, mask, B, T, ds, 0, y_full, y_out, nullptr);
+    if (stash) e = launch_fwd<NR, true, true>(dim3(full, 2), st, gx, w_hh, b_hh, mask, dr, B, T, ds, 0, y_full, y_out, stash);
+    else e = launch_fwd<NR, false, true>(dim3(full, 2), st, gx, w_hh, b_hh, mask, dr, B, T, ds, 0, y_full, y_out, nullptr);
   }
-  if (rem) {                          // ragged last tile: predicated stores
-    if (stash) launch_fwd<NR, true, false>(dim3(1, 2), st, gx, w_hh, b_hh, mask, B, T, ds, full, y_full, y_out, stash);
-    else launch_fwd<NR, false, false>(dim3(1, 2), st, gx, w_hh, b_hh, mask, B, T, ds, full, y_full, y_out, nullptr);
+  if (rem && !e) {                    // ragged last tile: predicated stores
+    if (stash) e = launch_fwd<NR, true, false>(dim3(1, 2), st, gx, w_hh, b_hh, mask, dr, B, T, ds, full, y_full, y_out, stash);
+    else e = launch_fwd<NR, false, false>(dim3(1, 2), st, gx, w_hh, b_hh, mask, dr, B, T, ds, full, y_full, y_out, nullptr);
   }
+  return e;
 }
 
-extern "C" int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T,
-                              int ds, float* y_full, float* y_out, float* stash, void* stream) {
+extern "C" int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, float drop_p,
+                              unsigned long long drop_seed, int B, int T, int ds, float* y_full, float* y_out, float* stash,
+                              void* stream) {
+  if (!(drop_p >= 0.f && drop_p < 1.f)) return (int)cudaErrorInvalidValue;
+  const DropArgs dr = drop_args(drop_mask, drop_p, drop_seed);
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2)) return (int)cudaErrorInvalidValue;
   if ((long)B * T * 1024 >= (1L << 31)) return SLU_ERR_TOO_LARGE;
   cudaStream_t st = (cudaStream_t)stream;
+  int e = 0;
   switch (pick_rows(B)) {
-    case 16: run_fwd<16>(st, gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, stash); break;
-    case 8: run_fwd<8>(st, gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, stash); break;
-    default: run_fwd<4>(st, gx, w_hh, b_hh, drop_mask, B, T, ds, y_full, y_out, stash); break;
+    case 16: e = run_fwd<16>(st, gx, w_hh, b_hh, drop_mask, dr, B, T, ds, y_full, y_out, stash); break;
+    case 8: e = run_fwd<8>(st, gx, w_hh, b_hh, drop_mask, dr, B, T, ds, y_full, y_out, stash); break;
+    default: e = run_fwd<4>(st, gx, w_hh, b_hh, drop_mask, dr, B, T, ds, y_full, y_out, stash); break;
   }
+  if (e) return e;
   SLU_CHECK_LAUNCH();
   return 0;
 }
 
 template <int NR, bool FULL>
-static void launch_bwd(dim3 grid, cudaStream_t st, const float* dy_out, const float* mask, const float* y_full, const float* stash,
-                       const float* w_hh, int B, int T, int ds, int tile0, float* dgx, float* dhn, float* db_ih, float* db_hh) {
+static int launch_bwd(dim3 grid, cudaStream_t st, const float* dy_out, const float* mask, DropArgs dr, const float* y_full, const float* stash,
+                      const float* w_hh, int B, int T, int ds, int tile0, float* dgx, float* dhn, float* db_ih, float* db_hh) {
   constexpr size_t smem = (size_t)BWD_RING * NR * 896 * sizeof(float);
   constexpr int P = 2 * NR <= 16 ? 2 : 3;
-  static int a3 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, 3>, smem);
-  static int a2 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, P>, smem);
-  static int a1 = slu_set_smem((const void*)gru_bwd_tc_kernel<16, NR, FULL, 1>, smem);
-  (void)a3; (void)a2; (void)a1;
-  if (g_gru_mode == 0) gru_bwd_tc_kernel<16, NR, FULL, P><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
-  else if (g_gru_mode == 2) gru_bwd_tc_kernel<16, NR, FULL, 3><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
-  else gru_bwd_tc_kernel<16, NR, FULL, 1><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
+  SLU_SMEM_ONCE((gru_bwd_tc_kernel<16, NR, FULL, 3>), smem);
+  SLU_SMEM_ONCE((gru_bwd_tc_kernel<16, NR, FULL, P>), smem);
+  SLU_SMEM_ONCE((gru_bwd_tc_kernel<16, NR, FULL, 1>), smem);
+  if (g_gru_mode == 0) gru_bwd_tc_kernel<16, NR, FULL, P><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, dr.thr, dr.scale, dr.seed, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
+  else if (g_gru_mode == 2) gru_bwd_tc_kernel<16, NR, FULL, 3><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, dr.thr, dr.scale, dr.seed, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
+  else gru_bwd_tc_kernel<16, NR, FULL, 1><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, dr.thr, dr.scale, dr.seed, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
+  return 0;
 }
 
 template <int NR>
-static void run_bwd(cudaStream_t st, const float* dy_out, const float* mask, const float* y_full, const float* stash, const float* w_hh,
-                    int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh) {
+static int run_bwd(cudaStream_t st, const float* dy_out, const float* mask, DropArgs dr, const float* y_full, const float* stash,
+                   const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh) {
   const int full = B / NR, rem = B % NR;
-  if (full) launch_bwd<NR, true>(dim3(full, 2), st, dy_out, mask, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn, db_ih, db_hh);
-  if (rem) launch_bwd<NR, false>(dim3(1, 2), st, dy_out, mask, y_full, stash, w_hh, B, T, ds, full, dgx, dhn, db_ih, db_hh);
+  int e = 0;
+  if (full) e = launch_bwd<NR, true>(dim3(full, 2), st, dy_out, mask, dr, y_full, stash, w_hh, B, T, ds, 0, dgx, dhn, db_ih, db_hh);
+  if (rem && !e) e = launch_bwd<NR, false>(dim3(1, 2), st, dy_out, mask, dr, y_full, stash, w_hh, B, T, ds, full, dgx, dhn, db_ih, db_hh);
+  return e;
 }
 
-extern "C" int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                              const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh, void* stream) {
+extern "C" int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, float drop_p, unsigned long long drop_seed,
+                              const float* y_full, const float* stash, const float* w_hh, int B, int T, int ds, float* dgx,
+                              float* dhn, float* db_ih, float* db_hh, void* stream) {
+  if (!(drop_p >= 0.f && drop_p < 1.f)) return (int)cudaErrorInvalidValue;
+  const DropArgs dr = drop_args(drop_mask, drop_p, drop_seed);
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (db_ih == nullptr) != (db_hh == nullptr)) return (int)cudaErrorInvalidValue;
   if ((long)B * T * 1024 >= (1L << 31)) return SLU_ERR_TOO_LARGE;
   cudaStream_t st = (cudaStream_t)stream;
+  int e = 0;
   switch (pick_rows(B)) {
-    case 16: run_bwd<16>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh); break;
-    case 8: run_bwd<8>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh); break;
-    default: run_bwd<4>(st, dy_out, drop_mask, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh); break;
+    case 16: e = run_bwd<16>(st, dy_out, drop_mask, dr, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh); break;
+    case 8: e = run_bwd<8>(st, dy_out, drop_mask, dr, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh); break;
+    default: e = run_bwd<4>(st, dy_out, drop_mask, dr, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh); break;
   }
+  if (e) return e;
   SLU_CHECK_LAUNCH();
   return 0;
 }

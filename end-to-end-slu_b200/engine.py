@@ -84,44 +84,39 @@ def downsample_factor(down):
     raise NotImplementedError("slu_b200 CUDA path: Downsample(%s, %d) is not supported" % (down.method, down.factor))
 
 
-def _drop_mask(shape, p, training, device, stream=None):
+# SLU_DROPOUT_MASKS=1: materialise the dropout masks as tensors (slu_dropout_mask_gru writes the same canonical Philox mask the
+# kernels otherwise generate in registers) -- for A/B checks; the default keeps them out of HBM altogether.
+MASK_TENSORS = os.environ.get("SLU_DROPOUT_MASKS", "0") != "0"
+
+
+def _drop_mask(shape, p, training, device):
+    """Dropout of one GRU layer output [B,T,256] -> None (eval / p = 0) or (p, seed): the persistent-GRU kernels regenerate
+    the canonical Philox keep-mask of that pair in registers, forward and backward (csrc/philox.cuh; reference nn.Dropout at
+    models.py:246/276/700).  The seed is a host draw from torch's CPU generator, so `torch.manual_seed` reproduces a run.
+    Tests replace this function to supply explicit mask tensors (the reference-order golden)."""
     if not training or p <= 0.0:
         return None
-    mask = torch.empty(shape, device=device, dtype=torch.float32)
-    seed = int(torch.randint(0, 2 ** 62, (1,)).item())        # host draw from torch's CPU generator: follows torch.manual_seed
-    _lib.call("slu_dropout_mask", _lib.ptr(mask), mask.numel(), float(p), seed, _lib.stream() if stream is None else stream)
-    return mask
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    if MASK_TENSORS:
+        mask = torch.empty(shape, device=device, dtype=torch.float32)
+        _lib.call("slu_dropout_mask_gru", _lib.ptr(mask), shape[0], shape[1], float(p), seed, _lib.stream())
+        return mask
+    return (float(p), seed)
 
 
 _default_drop_mask = _drop_mask
 
 
 def _premask(stacks, B, T, training, device):
-    """Keep-masks of several GRU stacks ahead of time: the tensors are allocated on the current stream, the generator kernels
-    run on a library side stream (next to the first x-projection GEMM) and `join()` orders them before the first recurrence.
-    Returns ([masks per stack], join).  Same draw order as layer-by-layer generation."""
-    shapes = []
+    """Dropout arguments of several GRU stacks ahead of time ([per stack [per layer]], same draw order as layer by layer)."""
+    out = []
     for rnns in stacks:
+        cur = []
         for _, p, ds in rnns:
-            shapes.append((B, T, 256))
+            cur.append(_drop_mask((B, T, 256), p, training, device))
             T = (T + ds - 1) // ds
-    flat = [(gru, p, ds) for rnns in stacks for (gru, p, ds) in rnns]
-    if not training or _drop_mask is not _default_drop_mask:      # nothing to do / a test supplies the masks
-        masks = [_drop_mask(shp, p, training, device) for shp, (_, p, _) in zip(shapes, flat)]
-        join = None
-    else:
-        bufs = [torch.empty(shp, device=device, dtype=torch.float32) if p > 0.0 else None for shp, (_, p, _) in zip(shapes, flat)]
-        seeds = torch.randint(0, 2 ** 62, (len(flat),)).tolist()      # one host draw for all layers (torch's CPU generator)
-        main, side = _lib.fork(1)
-        for buf, seed, (_, p, _) in zip(bufs, seeds, flat):
-            if buf is not None:
-                _lib.call("slu_dropout_mask", _lib.ptr(buf), buf.numel(), float(p), seed, side[0])
-        masks, join = bufs, (lambda: _lib.join(main, 1))
-    out, i = [], 0
-    for rnns in stacks:
-        out.append(masks[i:i + len(rnns)])
-        i += len(rnns)
-    return out, join
+        out.append(cur)
+    return out, None
 
 
 def _weight_images(convs, rnns):
@@ -158,7 +153,7 @@ def _run_rnns(out, rnns, training, masks=None, join=None, imgs=None):
     for i, (gru, p, ds) in enumerate(rnns):
         B, T, _ = out.shape
         mask = masks[i] if masks is not None else _drop_mask((B, T, 256), p, training, out.device)
-        if mask is not None and tuple(mask.shape) != (B, T, 256):
+        if torch.is_tensor(mask) and tuple(mask.shape) != (B, T, 256):
             raise RuntimeError("slu_b200: pre-generated dropout mask does not match the layer input")
         out = ops.bigru(out, gru, mask, ds, join if i == 0 else None, imgs[i])   # masks are joined right before the first recurrence
     if join is not None and not rnns:
@@ -181,8 +176,7 @@ def phoneme_features(pm, x, with_word=True):
     # start of a step than the saved launches are worth)
     word = plan.word if with_word else []
     _, gru_imgs = _weight_images([], plan.phone + word)
-    # Masks of the phoneme AND word stacks: queued on a side stream once the front end is in flight (the host prepares them
-    # while the GPU is busy), they run next to the first x-projection GEMM and are joined right before the first recurrence.
+    # Dropout of the phoneme AND word stacks: one (p, seed) pair per layer, drawn now so the word module reuses this pass's draws.
     (m_phone, m_word), join = _premask([plan.phone, word], out.shape[0], out.shape[1], pm.training, out.device)
     out = _run_rnns(out, plan.phone, pm.training, m_phone, join, gru_imgs[:len(plan.phone)])
     carry = (m_word if pm.training else None, gru_imgs[len(plan.phone):]) if with_word else None

@@ -285,9 +285,10 @@ def sinc_filters(filt_b1, filt_band):
 
 
 class BiGRU(torch.autograd.Function):
-    """Bidirectional single-layer GRU (H=128, h0=0) + Dropout(mask) + Downsample(avg 2 | none 1).
+    """Bidirectional single-layer GRU (H=128, h0=0) + Dropout + Downsample(avg 2 | none 1).
     Reference: nn.GRU at models.py:232/262/686, RNNSelect :138-149, Dropout :246, Downsample :26-46.
-    x [B,T,I] -> [B, ceil(T/ds), 256]."""
+    x [B,T,I] -> [B, ceil(T/ds), 256].  `mask`: None (eval / p = 0), an explicit keep-mask tensor [B,T,256] (already scaled by
+    1/(1-p)), or a (p, seed) pair = the kernels generate the canonical Philox mask in registers, forward and backward."""
 
     @staticmethod
     def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, mask, ds, packed=None, before_recurrence=None, imgs=None):
@@ -304,17 +305,21 @@ class BiGRU(torch.autograd.Function):
         img_nt, img_nn = imgs if imgs is not None else (None, None)
         gx = linear_nt(x.view(B * T, I), w_ih_cat, b_ih_cat, img_nt)            # x-projection, both directions
         T2 = (T + ds - 1) // ds
+        drop_p, drop_seed = (float(mask[0]), int(mask[1])) if isinstance(mask, tuple) else (0.0, 0)
+        if isinstance(mask, tuple):
+            mask = None
         y_full = torch.empty(B, T, 256, device=dev, dtype=torch.float32)
-        y_out = torch.empty(B, T2, 256, device=dev, dtype=torch.float32) if (ds != 1 or mask is not None) else y_full
+        y_out = torch.empty(B, T2, 256, device=dev, dtype=torch.float32) if (ds != 1 or mask is not None or drop_p > 0.0) else y_full
         need = any(ctx.needs_input_grad[:9])
         stash = torch.empty(B, T, 1024, device=dev, dtype=torch.float32) if need else None
         if before_recurrence is not None:       # e.g. join the side stream that wrote the dropout masks (the x-projection is queued)
             before_recurrence()
-        _lib.call("slu_gru_fwd_" + GRU_IMPL, _lib.ptr(gx), _lib.ptr(w_hh_cat), _lib.ptr(b_hh_cat), _lib.ptr(mask), B, T, ds,
-                  _lib.ptr(y_full), _lib.ptr(y_out), _lib.ptr(stash), _lib.stream())
+        _lib.call("slu_gru_fwd_" + GRU_IMPL, _lib.ptr(gx), _lib.ptr(w_hh_cat), _lib.ptr(b_hh_cat), _lib.ptr(mask), drop_p, drop_seed,
+                  B, T, ds, _lib.ptr(y_full), _lib.ptr(y_out), _lib.ptr(stash), _lib.stream())
         if need:
             ctx.save_for_backward(x, w_ih_cat, w_hh_cat, y_full, stash, mask)
             ctx.ds = ds
+            ctx.drop = (drop_p, drop_seed)
             ctx.img_nn = img_nn
             # the packed views alias the Parameters' storage without sharing their version counters: remember the versions so
             # that an in-place update between this forward and its backward is detected (stock autograd would raise too)
@@ -327,6 +332,7 @@ class BiGRU(torch.autograd.Function):
     def backward(ctx, gy):
         x, w_ih_cat, w_hh_cat, y_full, stash, mask = ctx.saved_tensors
         ds = ctx.ds
+        drop_p, drop_seed = ctx.drop
         for q, v in ctx.param_versions:
             if q._version != v:
                 raise RuntimeError("slu_b200: a GRU parameter needed for gradient computation has been modified by an inplace "
@@ -354,15 +360,16 @@ class BiGRU(torch.autograd.Function):
             img = None
             if ni[0]:
                 img = ctx.img_nn if ctx.img_nn is not None else presplit(w_ih_cat, *_form_nn(w_ih_cat))
-            _lib.call("slu_bigru_bwd_tc", _lib.ptr(gy), _lib.ptr(mask), _lib.ptr(y_full), _lib.ptr(stash), _lib.ptr(w_hh_cat), _lib.ptr(x),
+            _lib.call("slu_bigru_bwd_tc", _lib.ptr(gy), _lib.ptr(mask), drop_p, drop_seed, _lib.ptr(y_full), _lib.ptr(stash),
+                      _lib.ptr(w_hh_cat), _lib.ptr(x),
                       I, None if img is None else img.data_ptr(), B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn),
                       db_ih.data_ptr() if wg else None, db_hh.data_ptr() if wg else None,
                       dw_ih.data_ptr() if wg else None, dw_hh.data_ptr() if wg else None, _lib.ptr(dx), 1 if OVERLAP else 0,
                       _lib.stream())
             _lib.stats["calls"] += (3 if wg else 0) + (1 if ni[0] else 0)          # kernels launched beyond the first
         else:
-            _lib.call("slu_gru_bwd_" + GRU_IMPL, _lib.ptr(gy), _lib.ptr(mask), _lib.ptr(y_full), _lib.ptr(stash), _lib.ptr(w_hh_cat),
-                      B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), db_ih.data_ptr() if wg else None, db_hh.data_ptr() if wg else None,
+            _lib.call("slu_gru_bwd_" + GRU_IMPL, _lib.ptr(gy), _lib.ptr(mask), drop_p, drop_seed, _lib.ptr(y_full), _lib.ptr(stash),
+                      _lib.ptr(w_hh_cat), B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), db_ih.data_ptr() if wg else None, db_hh.data_ptr() if wg else None,
                       _lib.stream())
             if wg:
                 fork = _Fork(3)

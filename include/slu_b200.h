@@ -59,25 +59,29 @@ int slu_sincconv_bwd_jac_tc(const float* x, const float* gy, const uint8_t* rout
  * Dropout :246/276/700 and Downsample :26-46.
  *   gx    [B][T][768]  x.W_ih^T + b_ih for both directions, col = d*384 + g*128 + j
  *   w_hh  [2][384][128], b_hh [2][384]
- *   drop_mask [B][T][256] keep-mask scaled by 1/(1-p), or NULL (eval / p = 0)
+ *   drop_mask [B][T][256] keep-mask scaled by 1/(1-p), or NULL.  With drop_mask == NULL and drop_p > 0 the kernels generate the
+ *             canonical Philox mask of (drop_p, drop_seed) in registers (csrc/philox.cuh; slu_dropout_mask_gru writes the same
+ *             mask out as a tensor): no mask tensor exists in HBM and the backward kernel regenerates it.  drop_p = 0: no dropout.
  *   ds    1 = Downsample("none",1), 2 = Downsample("avg",2) (ceil mode: an odd tail frame is kept as is)
  *   y_full [B][T][256] raw hidden states (col = d*128 + j);  y_out [B][ceil(T/ds)][256]
  *   stash [B][T][1024] (r, z, n, W_hn h + b_hn per direction) for the backward pass, or NULL for inference. */
-int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T, int ds,
-                     float* y_full, float* y_out, float* stash, void* stream);
+int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, float drop_p,
+                     unsigned long long drop_seed, int B, int T, int ds, float* y_full, float* y_out, float* stash, void* stream);
 /* Backward through time -- replaces _cudnn_rnn_backward.  Emits dgx[B][T][768] (gradient wrt gx) and
  * dhn[B][T][256] (gradient wrt the n-gate's recurrent pre-activation); the weight/input gradients are dense
  * GEMMs over these.  db_ih[2][384] and db_hh[2][384] (the bias parameters' own layout; both NULL or both caller-zeroed)
  * ACCUMULATE the bias gradients: b_ih <- sums over (b,t) of (dr, dz, dn), b_hh <- (dr, dz, dhn). */
-int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                     const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh, void* stream);
+int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, float drop_p, unsigned long long drop_seed, const float* y_full,
+                     const float* stash, const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh,
+                     void* stream);
 
 /* Same contracts as slu_gru_fwd_simt / slu_gru_bwd_simt, executed on tcgen05 tensor cores: W_hh (bf16 hi+lo) stationary
  * in tensor memory, h / dG as the shared-memory B operand, 3-pass bf16 split with fp32 accumulation in TMEM. */
-int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, int B, int T, int ds,
-                   float* y_full, float* y_out, float* stash, void* stream);
-int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, const float* y_full, const float* stash,
-                   const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh, void* stream);
+int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, float drop_p,
+                   unsigned long long drop_seed, int B, int T, int ds, float* y_full, float* y_out, float* stash, void* stream);
+int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, float drop_p, unsigned long long drop_seed, const float* y_full,
+                   const float* stash, const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh,
+                   void* stream);
 
 /* Operand format of the tcgen05 recurrence:
  *   0 = bf16 hi/lo split, fp32-class accuracy (default).  On the 4- and 8-row batch tiles the hi and lo rows of the activation
@@ -112,7 +116,8 @@ int slu_intent_head_bwd(const float* gloss, const float* feats, const float* W, 
  * overlap != 0).  x [B][T][I] = the layer input; w_ih_nn_img = slu_presplit_bf16 image of W_ih [768][I] read as the [K=768][N=I]
  * operand (NULL with dx == NULL: no input gradient); dw_ih [768][I] and dw_hh [2][384][128] accumulate (NULL, NULL: no weight
  * gradients); dgx [B][T][768] and dhn [B][T][256] are caller-provided scratch that holds the pre-activation gradients. */
-int slu_bigru_bwd_tc(const float* gy, const float* drop_mask, const float* y_full, const float* stash, const float* w_hh, const float* x,
+int slu_bigru_bwd_tc(const float* gy, const float* drop_mask, float drop_p, unsigned long long drop_seed, const float* y_full,
+                     const float* stash, const float* w_hh, const float* x,
                      int I, const void* w_ih_nn_img, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh,
                      float* dw_ih, float* dw_hh, float* dx, int overlap, void* stream);
 
@@ -136,6 +141,9 @@ int slu_h2d_wait(void);
 /* Dropout keep-mask (nn.Dropout, models.py:246/276/700, training mode): mask[i] = Bernoulli(1-p) / (1-p), i < n, from
  * Philox4x32-10 keyed by `seed` (counter = i/4).  `mask` must be 16-byte aligned.  The GRU kernels multiply by it. */
 int slu_dropout_mask(float* mask, long n, float p, unsigned long long seed, void* stream);
+/* The canonical GRU-layer mask [B][T][256] of (p, seed): exactly what slu_gru_{fwd,bwd}_* generate in registers when they are
+ * given (drop_p, drop_seed) and no mask tensor. */
+int slu_dropout_mask_gru(float* mask, int B, int T, float p, unsigned long long seed, void* stream);
 
 /* Backward of the conv blocks' LeakyReLU plus the Conv1d bias gradient in one pass (autograd of models.py:200/211):
  *   dpre[r][c] = y[r][c] > 0 ? gy[r][c] : slope*gy[r][c];  db[c] += sum_r dpre[r][c]     (R rows of C floats, C % 4 == 0) */

@@ -124,9 +124,53 @@ def test_sinc_frontend_fwd_bwd(pkg, monkeypatch, impl, B, T):
     assert b1g.grad.dtype == torch.float64
     scale = max(b1.grad.abs().max().item(), band.grad.abs().max().item())
     for got, ref_g in ((b1g.grad.cpu(), b1.grad), (bandg.grad.cpu(), band.grad)):
-        # the chain through the max-normalisation cancels heavily; the tcgen05 path resolves it analytically (Jacobian banks)
-        tol = GRAD_TOL * scale + 1e-4
+        # abs / max-pool ROUTING is discontinuous: the tcgen05 forward differs from fp32 by ~1e-5, which flips the winner of a
+        # fraction ~2e-5 of the frame pairs; each flip moves one of N random-signed terms, so the cut-off gradients move by
+        # ~sqrt(2e-5) = 4.5e-3 relative whatever N is (measured 2e-3..7e-3).  test_sinc_cutoff_gradients_given_the_routing pins the
+        # kernel itself to 1e-4; here the bound is the routing noise.
+        tol = (1e-2 if impl == "tc" else GRAD_TOL) * scale + 1e-4
         assert (got - ref_g).abs().max().item() < tol, ((got - ref_g).abs().max().item(), scale)
+
+
+@pytest.mark.parametrize("B,T", [(3, 12345), (2, 64000), (2, 1234)])
+def test_sinc_cutoff_gradients_given_the_routing(pkg, B, T):
+    """slu_sinc_filters_jac + slu_sincconv_bwd_jac_tc against autograd of the SAME routed objective: with the abs / max-pool
+    routing fixed to the route bits the CUDA forward produced, dL/d(filt_b1, filt_band) is a smooth function and the kernels
+    must agree with fp32 autograd to 1e-4 (this isolates them from the forward's routing flips)."""
+    p = R.synthetic_params()
+    x = R.synthetic_batch(B, T, seed=T)[0]
+    b1 = p[R.P + "phoneme_layers.0.filt_b1"].clone().requires_grad_(True)
+    band = p[R.P + "phoneme_layers.0.filt_band"].clone().requires_grad_(True)
+    L0 = (T - 1) // 80 + 1
+    L1 = (L0 + 1) // 2
+    rs = np.random.RandomState(2)
+    gy = torch.from_numpy(rs.standard_normal((B, L1, 80)).astype(np.float32))
+    xd, gyd = x.cuda(), gy.cuda()
+    b1d, bandd = b1.detach().cuda(), band.detach().cuda()
+    W = pkg.ops.sinc_filters(b1d, bandd)
+    out = torch.empty(B, L1, 80, device="cuda"); route = torch.empty(B, L1, 80, device="cuda", dtype=torch.uint8)
+    img = torch.empty(2 * 6 * 160 * 96, device="cuda", dtype=torch.bfloat16)
+    st = pkg._lib.stream()
+    pkg._lib.call("slu_sincconv_fwd_tc", xd.data_ptr(), W.data_ptr(), B, T, out.data_ptr(), route.data_ptr(), img.data_ptr(), st)
+    J = torch.empty(2, 80, 401, device="cuda")
+    d = torch.zeros(160, device="cuda", dtype=torch.float64)
+    pkg._lib.call("slu_sinc_filters_jac", b1d.data_ptr(), bandd.data_ptr(), J.data_ptr(), st)
+    pkg._lib.call("slu_sincconv_bwd_jac_tc", xd.data_ptr(), gyd.data_ptr(), route.data_ptr(), J.data_ptr(), B, T, d.data_ptr(),
+                  img.data_ptr(), st)
+    # the routed objective on the CPU: frame 2j + sel of every pair gets +-gy (0 where the winner was exactly 0)
+    rt = route.cpu().long()                                            # [B, L1, 80]
+    sel, neg, zero = rt & 1, (rt >> 1) & 1, (rt >> 2) & 1
+    G0 = torch.zeros(B, 2 * L1, 80)
+    val = gy * (1 - 2 * neg).float() * (1 - zero).float()
+    G0.scatter_(1, (2 * torch.arange(L1).view(1, L1, 1) + sel), val)
+    G0 = G0[:, :L0].transpose(1, 2)                                    # [B, 80, L0]
+    Wr = R.sinc_filters(b1, band)
+    conv = torch.nn.functional.conv1d(x.unsqueeze(1), Wr.unsqueeze(1), stride=80, padding=200)
+    (conv * G0).sum().backward()
+    scale = max(b1.grad.abs().max().item(), band.grad.abs().max().item())
+    dc = d.cpu()
+    assert (dc[:80] - b1.grad).abs().max().item() < 1e-4 * scale, (dc[:80] - b1.grad).abs().max().item() / scale
+    assert (dc[80:] - band.grad).abs().max().item() < 1e-4 * scale, (dc[80:] - band.grad).abs().max().item() / scale
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
@@ -360,3 +404,44 @@ def test_linear_ce_out_of_range_label_is_nan(pkg):
     y = torch.tensor([0, 1, 2, 44, 3, -1, 5, 6], device="cuda")
     loss, _ = pkg.ops.linear_ce(x, w, b, y)
     assert torch.isnan(loss)
+
+
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("B,T,I,ds,p", [(5, 23, 256, 2, 0.5), (4, 50, 60, 1, 0.3), (17, 9, 256, 2, 0.5)])
+def test_in_kernel_dropout_equals_the_explicit_canonical_mask(pkg, monkeypatch, impl, B, T, I, ds, p):
+    """(p, seed) given to the GRU kernels = the mask slu_dropout_mask_gru writes for the same pair, given as a tensor: identical
+    outputs and gradients, forward and backward (the backward kernel regenerates the mask instead of reading it)."""
+    monkeypatch.setattr(pkg.ops, "GRU_IMPL", impl)
+    rs = np.random.RandomState(B * 100 + T)
+    gru = torch.nn.GRU(I, 128, batch_first=True, bidirectional=True).cuda()
+    x = torch.from_numpy(rs.standard_normal((B, T, I)).astype(np.float32)).cuda()
+    seed = 123456789012345
+    mask = torch.empty(B, T, 256, device="cuda")
+    pkg._lib.call("slu_dropout_mask_gru", mask.data_ptr(), B, T, p, seed, pkg._lib.stream())
+    vals = torch.unique(mask).cpu().tolist()
+    assert len(vals) == 2 and vals[0] == 0.0 and abs(vals[1] - 1.0 / (1.0 - p)) < 1e-6
+    outs = []
+    for drop in (mask, (p, seed)):
+        xr = x.clone().requires_grad_(True)
+        gru.zero_grad()
+        y = pkg.ops.bigru(xr, gru, drop, ds)
+        y.square().sum().backward()
+        outs.append((y.detach().clone(), xr.grad.clone(), gru.weight_hh_l0.grad.clone(), gru.bias_ih_l0_reverse.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert (outs[0][0] == 0).float().mean().item() > 0.02           # something was dropped
+
+
+def test_canonical_dropout_mask_statistics(pkg):
+    B, T, p = 8, 403, 0.5
+    m = torch.empty(B, T, 256, device="cuda")
+    pkg._lib.call("slu_dropout_mask_gru", m.data_ptr(), B, T, p, 42, pkg._lib.stream())
+    keep = (m > 0).float()
+    assert abs(keep.mean().item() - 0.5) < 4 * 0.5 / np.sqrt(m.numel())
+    assert abs(keep.mean(dim=(0, 1)).sub(0.5).abs().max().item()) < 0.06          # per column
+    assert abs(keep.mean(dim=(0, 2)).sub(0.5).abs().max().item()) < 0.06          # per time step
+    k = keep.flatten()
+    assert abs(((k[1:] - 0.5) * (k[:-1] - 0.5)).mean().item()) < 4 * 0.25 / np.sqrt(k.numel())    # neighbours uncorrelated
+    m2 = torch.empty_like(m)
+    pkg._lib.call("slu_dropout_mask_gru", m2.data_ptr(), B, T, p, 43, pkg._lib.stream())
+    assert abs(((m2 > 0).float() * keep).mean().item() - 0.25) < 0.01              # different seeds: independent masks

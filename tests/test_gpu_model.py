@@ -14,8 +14,11 @@ from util import ckpt_params, golden, load_test_wav, make_config, rel_err
 pytestmark = pytest.mark.gpu
 LOGIT_TOL = 1e-3      # north star; we assert 10x tighter where fp32 kernels are used
 GRAD_TOL = 5e-3
-SINC_GRAD_TOL = 1e-3  # the two SincNet cut-off vectors: their chain through the max-normalisation cancels, which the Jacobian-bank
-                      # backward (csrc/sinc_tc.cu, slu_sincconv_bwd_jac_tc) resolves analytically; measured ~2e-5
+# The two SincNet cut-off vectors: abs / max-pool routing is discontinuous, and a forward that differs from fp32 by ~1e-5 flips
+# the winner of ~2e-5 of the frame pairs; every flip moves one of N random-signed terms of the sum, so these two gradients move by
+# ~sqrt(2e-5) = 4.5e-3 relative for any N (measured 4e-3..7e-3; tests/test_gpu_kernels.py::test_sinc_cutoff_gradients_given_the_routing
+# pins the kernels to 1e-4 with the routing held fixed).  Everything else is smooth and held to GRAD_TOL.
+SINC_GRAD_TOL = 1.5e-2
 
 
 def gpu_model(params=None, train=False):
@@ -379,3 +382,34 @@ def test_seq2seq_model_on_gpu_matches_the_reference_golden():
         scores, beam = m.decoder.infer(enc, cfg.Sy_intent, B=4, y_lengths=[6])
     assert rel_err(scores.cpu(), g["beam_scores"]) < 1e-4
     assert np.array_equal(beam.argmax(-1)[0].cpu().numpy(), g["beam_ids"][0])
+
+
+def test_train_mode_dropout_is_seeded_and_needs_no_mask_tensors(monkeypatch):
+    """Train mode, default path: the dropout masks are generated inside the GRU kernels from (p, seed) pairs drawn from torch's
+    CPU generator -- torch.manual_seed reproduces a step bit for bit, another seed gives another loss, and materialising the same
+    masks as tensors (SLU_DROPOUT_MASKS=1 path) gives identical results."""
+    eng = importlib.import_module("end-to-end-slu_b200").engine
+    p = R.synthetic_params(seed=8)
+    m = gpu_model(p, train=True)
+    for q in m.parameters():
+        q.requires_grad = True
+    x, y = R.synthetic_batch(6, 16000, seed=9)
+
+    def step(seed):
+        torch.manual_seed(seed)
+        m.zero_grad()
+        loss, _ = m(x, y)
+        loss.backward()
+        return loss.item(), m.pretrained_model.phoneme_layers[5].weight.grad.clone()
+    l1, g1 = step(5)
+    l2, g2 = step(5)
+    l3, _ = step(6)
+    assert l1 == l2 and torch.equal(g1, g2) and l3 != l1
+    with torch.no_grad():
+        m.eval()
+        l_eval, _ = m(x, y)
+        m.train()
+    assert abs(l_eval.item() - l1) > 1e-4                  # dropout really is active in train mode
+    monkeypatch.setattr(eng, "MASK_TENSORS", True)
+    l4, g4 = step(5)
+    assert l4 == l1 and torch.equal(g4, g1)

@@ -126,8 +126,8 @@ def test_predict_intents_logits_are_differentiable_on_gpu(pkg):
 def test_gru_size_limit_is_a_readable_error(pkg):
     gx = torch.empty(1, device="cuda")
     with pytest.raises(RuntimeError, match="split the batch"):
-        pkg._lib.call("slu_gru_fwd_tc", gx.data_ptr(), gx.data_ptr(), gx.data_ptr(), None, 4096, 1024, 1, gx.data_ptr(), gx.data_ptr(),
-                      None, pkg._lib.stream())
+        pkg._lib.call("slu_gru_fwd_tc", gx.data_ptr(), gx.data_ptr(), gx.data_ptr(), None, 0.0, 0, 4096, 1024, 1, gx.data_ptr(),
+                      gx.data_ptr(), None, pkg._lib.stream())
 
 
 def test_prefetcher_keeps_pinned_sources_alive_until_the_copy_has_run(pkg):
