@@ -1,0 +1,218 @@
+// Seq2seq intent decoder, teacher-forced training path (reference models.py:413-436 Attention,
+// 438-484 DecoderRNN = GRUCell stack, 500-556 Seq2SeqDecoder.forward).
+//
+// The reference runs, per output symbol, ~25 library launches forward (it even re-projects the encoder states to keys / values
+// inside every step) and as many again in autograd.  Here everything that does not depend on the recurrence is hoisted into dense
+// tcgen05 GEMMs over all symbols at once (keys, values, embeddings, the embedding half of the first cell's input projection, the
+// output projection + log-softmax + NLL), and the sequential part of a step is three small fused kernels between four GEMM launches:
+//   attn_step_*     one CTA per utterance: scores = keys.q / sqrt(K) -> softmax over the T encoder frames -> context = w.values;
+//                   backward accumulates dkeys / dvalues over the steps in place (a CTA owns its utterance: no atomics)
+//   grucell_*       the GRUCell gate math (torch.nn.GRUCell: r, z, n; h' = (1-z) n + z h) on pre-computed gi / gh, fused with the
+//                   Dropout(0.5) that feeds the next cell (Philox keyed by (seed, step, element)); backward emits dgi / dgh and
+//                   the direct dh path
+// All tensors fp32; B = utterances, D = decoder width (256), T = encoder frames, K / V = key / value widths.
+#include <math.h>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace {
+
+constexpr int ATT_THREADS = 128;
+constexpr int ATT_MAXT = 256;        // encoder frames per utterance (4 s -> 25, 15 s -> 94)
+
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float r = (red[0] + red[1]) + (red[2] + red[3]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_max_128(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float r = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  return r;
+}
+
+// q [B][ldq] (first K used), keys [B][T][K], values [B][T][V] -> w [B][T], ctx [B][V]
+__global__ void __launch_bounds__(ATT_THREADS) attn_step_fwd_kernel(const float* __restrict__ q, long ldq, const float* __restrict__ keys,
+                                                                    const float* __restrict__ values, int T, int K, int V,
+                                                                    float inv_scale, float* __restrict__ w, float* __restrict__ ctx) {
+  __shared__ float qs[512], sc[ATT_MAXT], red[4];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int k = tid; k < K; k += ATT_THREADS) qs[k] = q[(long)b * ldq + k];
+  __syncthreads();
+  for (int t = warp; t < T; t += ATT_THREADS / 32) {          // a warp per frame: coalesced key row, shuffle reduction
+    const float* kr = keys + ((long)b * T + t) * K;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(kr[k], qs[k], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sc[t] = s * inv_scale;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int t = tid; t < T; t += ATT_THREADS) m = fmaxf(m, sc[t]);
+  m = block_max_128(m, red);
+  float e = 0.f;
+  for (int t = tid; t < T; t += ATT_THREADS) { const float v = expf(sc[t] - m); sc[t] = v; e += v; }
+  e = block_sum_128(e, red);
+  const float inv = 1.f / e;
+  for (int t = tid; t < T; t += ATT_THREADS) { const float v = sc[t] * inv; sc[t] = v; w[(long)b * T + t] = v; }
+  __syncthreads();
+  for (int v = tid; v < V; v += ATT_THREADS) {                // coalesced over v for every frame
+    float a = 0.f;
+    const float* vr = values + (long)b * T * V + v;
+    for (int t = 0; t < T; ++t) a = fmaf(sc[t], vr[(long)t * V], a);
+    ctx[(long)b * V + v] = a;
+  }
+}
+
+// dctx [B][V], w [B][T], q [B][ldq] -> dq [B][lddq] (first K), dkeys [B][T][K] += , dvalues [B][T][V] +=
+__global__ void __launch_bounds__(ATT_THREADS) attn_step_bwd_kernel(const float* __restrict__ dctx, const float* __restrict__ w,
+                                                                    const float* __restrict__ q, long ldq, const float* __restrict__ keys,
+                                                                    const float* __restrict__ values, int T, int K, int V,
+                                                                    float inv_scale, float* __restrict__ dq, long lddq,
+                                                                    float* __restrict__ dkeys, float* __restrict__ dvalues) {
+  __shared__ float dc[512], qs[512], ws[ATT_MAXT], ds[ATT_MAXT], red[4];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int v = tid; v < V; v += ATT_THREADS) dc[v] = dctx[(long)b * V + v];
+  for (int k = tid; k < K; k += ATT_THREADS) qs[k] = q[(long)b * ldq + k];
+  for (int t = tid; t < T; t += ATT_THREADS) ws[t] = w[(long)b * T + t];
+  __syncthreads();
+  for (int t = warp; t < T; t += ATT_THREADS / 32) {          // dw[t] = dctx . values[t];  dvalues[t] += w[t] dctx
+    const long o = ((long)b * T + t) * V;
+    const float wt = ws[t];
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) {
+      s = fmaf(dc[v], values[o + v], s);
+      dvalues[o + v] += wt * dc[v];
+    }
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+    if (lane == 0) ds[t] = s;
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int t = tid; t < T; t += ATT_THREADS) dot += ws[t] * ds[t];
+  dot = block_sum_128(dot, red);
+  for (int t = tid; t < T; t += ATT_THREADS) ds[t] = ws[t] * (ds[t] - dot) * inv_scale;     // d(scaled score)
+  __syncthreads();
+  for (int k = tid; k < K; k += ATT_THREADS) {
+    float a = 0.f;
+    const float qk = qs[k];
+    for (int t = 0; t < T; ++t) {
+      const long o = ((long)b * T + t) * K + k;
+      a = fmaf(ds[t], keys[o], a);
+      dkeys[o] += ds[t] * qk;
+    }
+    dq[(long)b * lddq + k] = a;
+  }
+}
+
+__device__ __forceinline__ float cell_mask(uint64_t seed, int step, long elem, uint32_t thr, float scale) {
+  uint32_t r[4];
+  slu_philox4x32_10(((uint64_t)(uint32_t)step << 40) | (uint64_t)(elem >> 2), seed, r);
+  const int k = (int)(elem & 3);
+  const uint32_t word = k < 2 ? (k == 0 ? r[0] : r[1]) : (k == 2 ? r[2] : r[3]);
+  return word < thr ? scale : 0.f;
+}
+
+// gi = gi_a[b*lda + .] (+ gi_b[b*ldb + .]), gh [b*ldh + .] (3D wide: r | z | n, biases included), hprev [B][D] (NULL: one row h0[D]
+// broadcast) -> h [B][D], stash [B][4D] = r | z | n | gh_n, dropped [B][D] = h * mask (NULL: no dropout output wanted)
+__global__ void grucell_fwd_kernel(const float* __restrict__ gi_a, long lda, const float* __restrict__ gi_b, long ldb,
+                                   const float* __restrict__ gh, long ldh, const float* __restrict__ hprev, const float* __restrict__ h0,
+                                   int B, int D, uint32_t thr, float scale, uint64_t seed, int step, float* __restrict__ h,
+                                   float* __restrict__ stash, float* __restrict__ dropped) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)B * D) return;
+  const int b = (int)(i / D), j = (int)(i - (long)b * D);
+  const float* a = gi_a + (long)b * lda;
+  const float* g = gh + (long)b * ldh;
+  float ir = a[j], iz = a[D + j], in_ = a[2 * D + j];
+  if (gi_b) { const float* c = gi_b + (long)b * ldb; ir += c[j]; iz += c[D + j]; in_ += c[2 * D + j]; }
+  const float hn = g[2 * D + j];
+  const float r = 1.f / (1.f + expf(-(ir + g[j])));
+  const float z = 1.f / (1.f + expf(-(iz + g[D + j])));
+  const float n = tanhf(in_ + r * hn);
+  const float hp = hprev ? hprev[i] : h0[j];
+  const float hv = (1.f - z) * n + z * hp;
+  h[i] = hv;
+  if (stash) { float* s = stash + (long)b * 4 * D; s[j] = r; s[D + j] = z; s[2 * D + j] = n; s[3 * D + j] = hn; }
+  if (dropped) dropped[i] = thr ? hv * cell_mask(seed, step, i, thr, scale) : hv;
+}
+
+// dh = (da (* mask if thr) ) + db + dc   (any of db, dc may be NULL)  ->  dgi [B][ldgi] (dr, dz, dn pre-activations),
+// dgh [B][ldgh] (dr, dz, dn*r), dh_direct [B][D] = dh * z
+__global__ void grucell_bwd_kernel(const float* __restrict__ da, const float* __restrict__ db, const float* __restrict__ dc,
+                                   const float* __restrict__ stash, const float* __restrict__ hprev, const float* __restrict__ h0, int B,
+                                   int D, uint32_t thr, float scale, uint64_t seed, int step, float* __restrict__ dgi, long ldgi,
+                                   float* __restrict__ dgh, long ldgh, float* __restrict__ dh_direct) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)B * D) return;
+  const int b = (int)(i / D), j = (int)(i - (long)b * D);
+  float dh = da[i];
+  if (thr) dh *= cell_mask(seed, step, i, thr, scale);
+  if (db) dh += db[i];
+  if (dc) dh += dc[i];
+  const float* s = stash + (long)b * 4 * D;
+  const float r = s[j], z = s[D + j], n = s[2 * D + j], hn = s[3 * D + j];
+  const float hp = hprev ? hprev[i] : h0[j];
+  const float dn_pre = dh * (1.f - z) * (1.f - n * n);
+  const float dz_pre = dh * (hp - n) * z * (1.f - z);
+  const float dr_pre = dn_pre * hn * r * (1.f - r);
+  float* gi = dgi + (long)b * ldgi;
+  float* gh = dgh + (long)b * ldgh;
+  gi[j] = dr_pre; gi[D + j] = dz_pre; gi[2 * D + j] = dn_pre;
+  gh[j] = dr_pre; gh[D + j] = dz_pre; gh[2 * D + j] = dn_pre * r;
+  dh_direct[i] = dh * z;
+}
+
+}  // namespace
+
+extern "C" int slu_attn_step_fwd(const float* q, long ldq, const float* keys, const float* values, int B, int T, int K, int V,
+                                 float inv_scale, float* w, float* ctx, void* stream) {
+  if (B <= 0 || T <= 0 || T > ATT_MAXT || K <= 0 || K > 512 || V <= 0 || V > 512) return (int)cudaErrorInvalidValue;
+  attn_step_fwd_kernel<<<B, ATT_THREADS, 0, (cudaStream_t)stream>>>(q, ldq, keys, values, T, K, V, inv_scale, w, ctx);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int slu_attn_step_bwd(const float* dctx, const float* w, const float* q, long ldq, const float* keys, const float* values, int B,
+                                 int T, int K, int V, float inv_scale, float* dq, long lddq, float* dkeys, float* dvalues, void* stream) {
+  if (B <= 0 || T <= 0 || T > ATT_MAXT || K <= 0 || K > 512 || V <= 0 || V > 512) return (int)cudaErrorInvalidValue;
+  attn_step_bwd_kernel<<<B, ATT_THREADS, 0, (cudaStream_t)stream>>>(dctx, w, q, ldq, keys, values, T, K, V, inv_scale, dq, lddq, dkeys,
+                                                                    dvalues);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int slu_grucell_fwd(const float* gi_a, long lda, const float* gi_b, long ldb, const float* gh, long ldh, const float* hprev,
+                               const float* h0, int B, int D, float drop_p, unsigned long long drop_seed, int step, float* h, float* stash,
+                               float* dropped, void* stream) {
+  if (B <= 0 || D <= 0 || (!hprev && !h0) || !(drop_p >= 0.f && drop_p < 1.f)) return (int)cudaErrorInvalidValue;
+  const uint32_t thr = drop_p > 0.f ? slu_keep_threshold(drop_p) : 0u;
+  const long n = (long)B * D;
+  grucell_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      gi_a, lda, gi_b, ldb, gh, ldh, hprev, h0, B, D, thr, (float)(1.0 / (1.0 - (double)drop_p)), drop_seed, step, h, stash, dropped);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int slu_grucell_bwd(const float* da, const float* db, const float* dc, const float* stash, const float* hprev, const float* h0,
+                               int B, int D, float drop_p, unsigned long long drop_seed, int step, float* dgi, long ldgi, float* dgh,
+                               long ldgh, float* dh_direct, void* stream) {
+  if (B <= 0 || D <= 0 || (!hprev && !h0) || !(drop_p >= 0.f && drop_p < 1.f)) return (int)cudaErrorInvalidValue;
+  const uint32_t thr = drop_p > 0.f ? slu_keep_threshold(drop_p) : 0u;
+  const long n = (long)B * D;
+  grucell_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      da, db, dc, stash, hprev, h0, B, D, thr, (float)(1.0 / (1.0 - (double)drop_p)), drop_seed, step, dgi, ldgi, dgh, ldgh, dh_direct);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}

@@ -13,17 +13,18 @@ __device__ __forceinline__ void philox4x32_10(uint64_t ctr, uint64_t seed, uint3
 // given (drop_p, drop_seed) instead of a mask -- for tests and for callers that want to inspect / reuse the mask.
 __global__ void __launch_bounds__(256) dropout_mask_gru_kernel(float* __restrict__ mask, int B, int T, uint32_t keep_threshold, float scale,
                                                                uint64_t seed) {
-  const long n = (long)B * ((T + 3) >> 2) * 256;
+  const int groups = (T + 7) >> 3;
+  const long n = (long)B * groups * 256;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const int col = (int)(i & 255);
     const long r = i >> 8;
-    const int tg = (int)(r % ((T + 3) >> 2)), b = (int)(r / ((T + 3) >> 2));
+    const int tg = (int)(r % groups), b = (int)(r / groups);
     uint32_t w[4];
     slu_gru_mask_draws(b, col, tg, seed, w);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int t = 4 * tg + k;
-      if (t < T) mask[((long)b * T + t) * 256 + col] = w[k] < keep_threshold ? scale : 0.f;
+    for (int k = 0; k < 8; ++k) {
+      const int t = 8 * tg + k;
+      if (t < T) mask[((long)b * T + t) * 256 + col] = slu_gru_mask_draw16(w, k) < keep_threshold ? scale : 0.f;
     }
   }
 }
@@ -66,10 +67,10 @@ extern "C" int slu_dropout_mask(float* mask, long n, float p, unsigned long long
 extern "C" int slu_dropout_mask_gru(float* mask, int B, int T, float p, unsigned long long seed, void* stream) {
   if (B <= 0 || T <= 0) return 0;
   if (!(p >= 0.f && p < 1.f)) return (int)cudaErrorInvalidValue;
-  const long n = (long)B * ((T + 3) >> 2) * 256;
+  const long n = (long)B * ((T + 7) >> 3) * 256;
   long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  dropout_mask_gru_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, B, T, slu_keep_threshold(p), (float)(1.0 / (1.0 - (double)p)), seed);
+  dropout_mask_gru_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, B, T, slu_keep_threshold16(p), (float)(1.0 / (1.0 - (double)p)), seed);
   SLU_CHECK_LAUNCH();
   return 0;
 }

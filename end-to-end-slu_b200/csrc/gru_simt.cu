@@ -63,8 +63,8 @@ gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, con
       if (mask) m_ = __ldg(mask + ((size_t)b * T + t) * 256 + d * SLU_H + j);
       else if (drop_thr != 0u) {          // the canonical Philox mask (philox.cuh); this variant simply draws per element
         uint32_t w[4];
-        slu_gru_mask_draws(b, d * SLU_H + j, t >> 2, drop_seed, w);
-        m_ = w[t & 3] < drop_thr ? drop_scale : 0.f;
+        slu_gru_mask_draws(b, d * SLU_H + j, t >> 3, drop_seed, w);
+        m_ = slu_gru_mask_draw16(w, t) < drop_thr ? drop_scale : 0.f;
       } else m_ = 1.f;
     }
   };
@@ -166,8 +166,8 @@ gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask,
     if (mask) g *= __ldg(mask + bt * 256 + d * SLU_H + j);
     else if (drop_thr != 0u) {
       uint32_t w[4];
-      slu_gru_mask_draws((int)(bt / T), d * SLU_H + j, (int)(bt % T) >> 2, drop_seed, w);
-      g *= w[(int)(bt % T) & 3] < drop_thr ? drop_scale : 0.f;
+      slu_gru_mask_draws((int)(bt / T), d * SLU_H + j, (int)(bt % T) >> 3, drop_seed, w);
+      g *= slu_gru_mask_draw16(w, (int)(bt % T)) < drop_thr ? drop_scale : 0.f;
     }
     v.dy = g;
   };
@@ -227,7 +227,7 @@ extern "C" int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float*
                                 unsigned long long drop_seed, int B, int T, int ds, float* y_full, float* y_out, float* stash,
                                 void* stream) {
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || !(drop_p >= 0.f && drop_p < 1.f)) return (int)cudaErrorInvalidValue;
-  const uint32_t thr = (!drop_mask && drop_p > 0.f) ? slu_keep_threshold(drop_p) : 0u;
+  const uint32_t thr = (!drop_mask && drop_p > 0.f) ? slu_keep_threshold16(drop_p) : 0u;
   const float dscale = (float)(1.0 / (1.0 - (double)drop_p));
   const size_t smem = W_SMEM + 2 * BT * SLU_H * sizeof(float);
   SLU_SMEM_ONCE(gru_fwd_kernel<true>, smem);
@@ -244,7 +244,7 @@ extern "C" int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, flo
                                 float* dhn, float* db_ih, float* db_hh, void* stream) {
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (db_ih == nullptr) != (db_hh == nullptr) || !(drop_p >= 0.f && drop_p < 1.f))
     return (int)cudaErrorInvalidValue;
-  const uint32_t thr = (!drop_mask && drop_p > 0.f) ? slu_keep_threshold(drop_p) : 0u;
+  const uint32_t thr = (!drop_mask && drop_p > 0.f) ? slu_keep_threshold16(drop_p) : 0u;
   const float dscale = (float)(1.0 / (1.0 - (double)drop_p));
   const size_t smem = W_SMEM + 2 * BT * SLU_G3 * sizeof(float);
   SLU_SMEM_ONCE(gru_bwd_kernel, smem);

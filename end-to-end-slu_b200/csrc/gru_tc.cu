@@ -202,7 +202,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
 #pragma unroll
   for (int c = 0; c < NC; ++c) { hprev[c] = 0.f; pend[c] = 0.f; }
   // Dropout keep-mask: explicit rows (`mask`, streamed through the ring) or, with drop_thr != 0, the canonical Philox mask of
-  // philox.cuh generated in registers -- one call per 4 time steps per element, nothing read from or written to HBM.
+  // philox.cuh generated in registers -- one call per 8 time steps per element, nothing read from or written to HBM.
   const bool rng = mask == nullptr && drop_thr != 0u;
   uint32_t rnd[NC][4];
   int rnd_group = -1;
@@ -243,15 +243,15 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
     const float* gxs = in_ring + (s % FWD_RING) * SLOT + c0 * 384 + j;
     const float* mks = in_ring + (s % FWD_RING) * SLOT + NR * 384 + c0 * 128 + j;
     float xr[NC], xz[NC], xn[NC], mk[NC];
-    if (rng && (t >> 2) != rnd_group) {          // uniform over the CTA: every thread is at the same t
-      rnd_group = t >> 2;
+    if (rng && (t >> 3) != rnd_group) {          // uniform over the CTA: every thread is at the same t
+      rnd_group = t >> 3;
 #pragma unroll
       for (int c = 0; c < NC; ++c) slu_gru_mask_draws(min(b0 + c0 + c, B - 1), d * SLU_H + j, rnd_group, drop_seed, rnd[c]);
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       xr[c] = gxs[c * 384] + bhr; xz[c] = gxs[c * 384 + 128] + bhz; xn[c] = gxs[c * 384 + 256];
-      mk[c] = mask ? mks[c * 128] : (rng ? (rnd[c][t & 3] < drop_thr ? drop_scale : 0.f) : 1.f);
+      mk[c] = mask ? mks[c * 128] : (rng ? (slu_gru_mask_draw16(rnd[c], t) < drop_thr ? drop_scale : 0.f) : 1.f);
     }
     PHASE(2);                        // TMA ring wait + input reads
     if (s == 0) {
@@ -458,14 +458,14 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
     const float* dys = sl + NR * 640 + c0 * 128 + j;
     const float* mks = sl + NR * 768 + c0 * 128 + j;
     float base[NC], zc[NC], f_n[NC], f_z[NC], f_r[NC], rc[NC];
-    if (rng && (t >> 2) != rnd_group) {
-      rnd_group = t >> 2;
+    if (rng && (t >> 3) != rnd_group) {
+      rnd_group = t >> 3;
 #pragma unroll
       for (int c = 0; c < NC; ++c) slu_gru_mask_draws(min(b0 + c0 + c, B - 1), d * SLU_H + j, rnd_group, drop_seed, rnd[c]);
     }
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const float mkv = mask ? mks[c * 128] : (rng ? (rnd[c][t & 3] < drop_thr ? drop_scale : 0.f) : 1.f);
+      const float mkv = mask ? mks[c * 128] : (rng ? (slu_gru_mask_draw16(rnd[c], t) < drop_thr ? drop_scale : 0.f) : 1.f);
       const float r = sts[c * 512], z = sts[c * 512 + 128], n = sts[c * 512 + 256];
       base[c] = dh_direct[c] + dys[c * 128] * (dscale * mkv);            // dL/dh without the recurrent part
       zc[c] = z; rc[c] = r;
@@ -571,7 +571,7 @@ extern "C" int slu_gru_rows_per_cta(int B) { return pick_rows(B); }
 struct DropArgs { uint32_t thr; float scale; uint64_t seed; };
 static DropArgs drop_args(const float* mask, float p, unsigned long long seed) {
   DropArgs a = {0u, 1.f, 0ull};
-  if (!mask && p > 0.f) { a.thr = slu_keep_threshold(p); a.scale = (float)(1.0 / (1.0 - (double)p)); a.seed = seed; }
+  if (!mask && p > 0.f) { a.thr = slu_keep_threshold16(p); a.scale = (float)(1.0 / (1.0 - (double)p)); a.seed = seed; }
   return a;
 }
 

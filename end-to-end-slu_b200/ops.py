@@ -615,11 +615,11 @@ class LinearCE(torch.autograd.Function):
         ctx.dims = (V, Vp, K)
         ctx.slot = _reserve(ctx, Vp * K + Vp) if need_w else None
         loss, acc = out[0], out[1]
-        ctx.mark_non_differentiable(acc)
-        return loss, acc
+        ctx.mark_non_differentiable(acc, row_loss)
+        return loss, acc, row_loss              # row_loss [M]: per-row NLL (0 on ignored rows), values only
 
     @staticmethod
-    def backward(ctx, g_loss, g_acc):
+    def backward(ctx, g_loss, g_acc, g_rows):
         dx, dwb = ctx.saved_tensors
         V, Vp, K = ctx.dims
         g = _f32(g_loss).reshape(1)
@@ -637,7 +637,7 @@ class LinearCE(torch.autograd.Function):
 
 def linear_ce(feats, weight, bias, y):
     """(loss, acc) of a frame-wise classification head; feats [..., K], y [...] int64 with -1 = ignore."""
-    return LinearCE.apply(feats.reshape(-1, feats.shape[-1]), weight, bias, y.reshape(-1))
+    return LinearCE.apply(feats.reshape(-1, feats.shape[-1]), weight, bias, y.reshape(-1))[:2]
 
 
 class LinearNT(torch.autograd.Function):

@@ -192,6 +192,27 @@ int slu_ce_finish(const float* row_loss, const float* row_ok, long M, const floa
 int slu_colsum_acc(const float* A, long ld, long R, int C, float* out, void* stream);
 int slu_scale(const float* src, float* dst, long n, const float* g, void* stream);
 
+/* ---- seq2seq intent decoder, teacher-forced training path (reference models.py:413-436 Attention, 438-484 DecoderRNN,
+ * 500-556 Seq2SeqDecoder.forward).  Everything outside the recurrence runs as dense slu_gemm_tc / slu_wgrad_tc calls over all
+ * output symbols at once; per symbol the sequential part is these kernels between four small GEMMs (see csrc/decoder.cu).
+ *   slu_attn_step_fwd: q [B][ldq] (K used), keys [B][T][K], values [B][T][V] -> w [B][T] = softmax_t(keys.q * inv_scale),
+ *                      ctx [B][V] = sum_t w[t] values[t]           (T <= 256, K, V <= 512)
+ *   slu_attn_step_bwd: dctx [B][V] -> dq [B][lddq]; dkeys, dvalues ACCUMULATE (one launch per symbol, walked backwards)
+ *   slu_grucell_fwd  : torch.nn.GRUCell gate math on precomputed gi = gi_a (+ gi_b) and gh (rows of 3D: r | z | n, biases
+ *                      included): h = (1-z) n + z hprev; hprev == NULL: the row h0[D] for every utterance (initial state);
+ *                      stash [B][4D] = r | z | n | gh_n; dropped [B][D] (may be NULL) = h * Philox keep-mask(drop_p, drop_seed, step)
+ *   slu_grucell_bwd  : dh = da * mask(step) + db + dc (db, dc may be NULL) -> dgi [B][ldgi], dgh [B][ldgh], dh_direct = dh * z */
+int slu_attn_step_fwd(const float* q, long ldq, const float* keys, const float* values, int B, int T, int K, int V, float inv_scale,
+                      float* w, float* ctx, void* stream);
+int slu_attn_step_bwd(const float* dctx, const float* w, const float* q, long ldq, const float* keys, const float* values, int B, int T,
+                      int K, int V, float inv_scale, float* dq, long lddq, float* dkeys, float* dvalues, void* stream);
+int slu_grucell_fwd(const float* gi_a, long lda, const float* gi_b, long ldb, const float* gh, long ldh, const float* hprev,
+                    const float* h0, int B, int D, float drop_p, unsigned long long drop_seed, int step, float* h, float* stash,
+                    float* dropped, void* stream);
+int slu_grucell_bwd(const float* da, const float* db, const float* dc, const float* stash, const float* hprev, const float* h0, int B,
+                    int D, float drop_p, unsigned long long drop_seed, int step, float* dgi, long ldgi, float* dgh, long ldgh,
+                    float* dh_direct, void* stream);
+
 /* ---- optimizer step / gradient bucket (reference training.py:19, 64-66, 96-98: torch.optim.Adam, zero_grad/backward/step) ----
  * slu_adam_multi: one Adam step over `n` parameter tensors (fp32 or fp64, any sizes) in ceil(n/64) launches; torch.optim.Adam's
  * single-tensor arithmetic with PER-TENSOR step counts (parameters un-frozen later keep their own bias corrections):

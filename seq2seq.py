@@ -2,9 +2,11 @@
 
 Reference: models.py:381-411 (Seq2SeqEncoder), 413-436 (Attention), 438-484 (DecoderRNN), 486-651 (sort_beam,
 Seq2SeqDecoder.forward / infer).  SURVEY.md section 8 keeps the decoder OUT of the hot path ("stays stock PyTorch on top of
-the encoder kernels"): the encoder's bidirectional GRU runs on the sm_100a persistent-GRU kernel when its parameters are on
-a CUDA device; attention, the GRUCell stack and beam search are plain torch ops, written batched (gather/scatter instead
-of the reference's per-element python loops) with identical results.  Parameter names match the reference so its seq2seq
+the encoder kernels"): on a CUDA device the encoder's bidirectional GRU runs on the sm_100a persistent-GRU kernel and the teacher-forced
+decoder (`Seq2SeqDecoder.forward`, the training path) on the library's decoder kernels (end-to-end-slu_b200/decoder.py:
+batched tcgen05 GEMMs outside the recurrence, fused attention / GRUCell step kernels inside it, hand-written backward
+through time).  The CPU path and beam search (`infer`, evaluation prints only) are plain torch ops, written batched
+(gather/scatter instead of the reference's per-element python loops) with identical results.  Parameter names match the reference so its seq2seq
 checkpoints (`encoder.layers.0.*`, `decoder.{initial_state, embed, attention.*, rnn.layers.{0,2,..}, linear}`) load strictly.
 """
 import torch
@@ -109,6 +111,10 @@ class Seq2SeqDecoder(torch.nn.Module):
 
     def forward(self, encoder_outputs, y, y_lengths=None):
         """encoder_outputs (B, T, 2*encoder_dim); y (B, U, num_labels) one-hot.  Returns log p(y|x) per example."""
+        if encoder_outputs.is_cuda:       # the library's decoder kernels (end-to-end-slu_b200/decoder.py); no torch fallback on CUDA
+            import importlib
+            dec = importlib.import_module("end-to-end-slu_b200").decoder
+            return dec.teacher_forced_log_likelihood(self, encoder_outputs, y, self.training)
         B, U, S = y.shape
         state = self.initial_state.unsqueeze(0).expand(B, -1, -1)
         y_prev = torch.zeros(B, S, device=y.device)

@@ -427,8 +427,9 @@ def test_in_kernel_dropout_equals_the_explicit_canonical_mask(pkg, monkeypatch, 
         y = pkg.ops.bigru(xr, gru, drop, ds)
         y.square().sum().backward()
         outs.append((y.detach().clone(), xr.grad.clone(), gru.weight_hh_l0.grad.clone(), gru.bias_ih_l0_reverse.grad.clone()))
-    for a, b in zip(*outs):
-        assert torch.equal(a, b)
+    assert torch.equal(outs[0][0], outs[1][0])                       # same mask, same arithmetic: bit-identical forward
+    for a, b in zip(outs[0][1:], outs[1][1:]):                       # gradients: split-K / atomic accumulation order varies
+        assert rel_err(a, b) < 1e-5
     assert (outs[0][0] == 0).float().mean().item() > 0.02           # something was dropped
 
 
