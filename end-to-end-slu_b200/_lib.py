@@ -48,6 +48,7 @@ SIGNATURES = {
     "slu_presplit_multi": [_P, _I, _P],
     "slu_wgrad2_tc": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P],
     "slu_wgrad_tc": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _L, _L, _P],
+    "slu_skinny_gemm": [_P, _L, _P, _L, _L, _P, _P, _L, _I, _I, _I, _P],
     "slu_attn_step_fwd": [_P, _L, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P],
     "slu_attn_step_bwd": [_P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P, _L, _P, _P, _P],
     "slu_grucell_fwd": [_P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _F, _U, _I, _P, _P, _P, _P],

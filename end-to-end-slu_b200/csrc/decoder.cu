@@ -216,3 +216,61 @@ extern "C" int slu_grucell_bwd(const float* da, const float* db, const float* dc
   SLU_CHECK_LAUNCH();
   return 0;
 }
+
+// ---- skinny GEMM for the decoder's per-symbol projections: C[m][n] = sum_k A[m*lda + k] * W[n*sn + k*sk] (+ bias[n]), M <= 64.
+// These are latency-bound GEMV-like products (64 utterances x a few hundred outputs, 28 MFLOP at most): a persistent tensor-core
+// pipeline costs more to start than the product takes, so this is an exact-fp32 CUDA-core kernel -- a CTA owns 16 output columns,
+// stages the activation rows and its weight rows through shared memory in K chunks of 128, every thread accumulates 4 outputs.
+namespace {
+constexpr int SK_M = 64, SK_N = 16, SK_KC = 128;
+
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restrict__ A, long lda, const float* __restrict__ W, long sn, long sk,
+                                                          const float* __restrict__ bias, float* __restrict__ C, long ldc, int M, int N,
+                                                          int K) {
+  __shared__ float As[SK_M][SK_KC + 1];
+  __shared__ float Ws[SK_N][SK_KC + 1];
+  const int tid = threadIdx.x, m = tid & 63, ng = tid >> 6;            // 64 rows x 4 groups of 4 columns
+  const int n0 = blockIdx.x * SK_N;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < K; k0 += SK_KC) {
+    const int kc = min(SK_KC, K - k0);
+    __syncthreads();
+    for (int i = tid; i < SK_M * SK_KC; i += 256) {                     // activation chunk: coalesced along k
+      const int r = i / SK_KC, k = i - r * SK_KC;
+      As[r][k] = (r < M && k < kc) ? A[(long)r * lda + k0 + k] : 0.f;
+    }
+    if (sk == 1) {                                                      // weight rows contiguous along k
+      for (int i = tid; i < SK_N * SK_KC; i += 256) {
+        const int r = i / SK_KC, k = i - r * SK_KC;
+        Ws[r][k] = (n0 + r < N && k < kc) ? W[(long)(n0 + r) * sn + k0 + k] : 0.f;
+      }
+    } else {                                                            // transposed view: contiguous along n
+      for (int i = tid; i < SK_N * SK_KC; i += 256) {
+        const int k = i / SK_N, r = i - k * SK_N;
+        Ws[r][k] = (n0 + r < N && k < kc) ? W[(long)(n0 + r) * sn + (long)(k0 + k) * sk] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < SK_KC; ++k) {
+      const float a = As[m][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, Ws[ng * 4 + j][k], acc[j]);
+    }
+  }
+  if (m < M)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + ng * 4 + j;
+      if (n < N) C[(long)m * ldc + n] = acc[j] + (bias ? bias[n] : 0.f);
+    }
+}
+}  // namespace
+
+extern "C" int slu_skinny_gemm(const float* A, long lda, const float* W, long sn, long sk, const float* bias, float* C, long ldc, int M,
+                               int N, int K, void* stream) {
+  if (M <= 0 || M > SK_M || N <= 0 || K <= 0) return (int)cudaErrorInvalidValue;
+  skinny_gemm_kernel<<<(N + SK_N - 1) / SK_N, 256, 0, (cudaStream_t)stream>>>(A, lda, W, sn, sk, bias, C, ldc, M, N, K);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}

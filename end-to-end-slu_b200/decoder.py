@@ -6,7 +6,7 @@ every step) and as many again in autograd.  Here
   * everything outside the recurrence is one dense tcgen05 GEMM over ALL symbols: keys, values, the embeddings of the previous
     symbols, the embedding half of the first cell's input projection, and the output projection fused with log-softmax + NLL
     (ops.LinearNT / ops.LinearCE -- the output logits [B*U, |S|] are never needed as a tensor);
-  * the recurrence itself is `DecoderStates`: per symbol 4 small GEMMs (slu_gemm_tc) + 3 fused kernels (csrc/decoder.cu:
+  * the recurrence itself is `DecoderStates`: per symbol 4 small projections (slu_skinny_gemm up to 64 utterances, slu_gemm_tc beyond) + 3 fused kernels (csrc/decoder.cu:
     attention step, two GRUCell gate kernels with the inter-cell Dropout), with a hand-written backward through time whose weight
     gradients are 4 weight-gradient GEMMs over all symbols at the end (slu_wgrad_tc) instead of per-step accumulations.
 Two cells (num_intent_decoder_layers = 2) of equal width, as in every reference cfg that enables seq2seq; other depths raise.
@@ -20,8 +20,34 @@ from . import _lib, ops
 _f32 = ops._f32
 
 
-def _gemm_nt(x2, img, M, N, K, out, bias=None):
-    return ops.gemm_tc(x2, K, img, M, N, K, out, bias=bias)
+SKINNY_MAX_ROWS = 64        # csrc/decoder.cu skinny_gemm_kernel: the per-symbol projections of up to 64 utterances
+
+
+class _W:
+    """One recurrent weight in both operand forms of the per-symbol projections: `nt` (x @ W^T) and `nn` (g @ W).  Up to 64
+    utterances take the exact-fp32 skinny kernel straight on the weight (no operand image); larger batches the tcgen05 GEMM."""
+
+    def __init__(self, w, need_nn, B):
+        self.w = w
+        self.skinny = B <= SKINNY_MAX_ROWS
+        self.img_nt = self.img_nn = None
+        if not self.skinny:
+            self.img_nt = ops.presplit(w, *ops._form_nt(w))
+            self.img_nn = ops.presplit(w, *ops._form_nn(w)) if need_nn else None
+
+    def nt(self, x2, M, out, bias=None):          # out [M, N] = x2 [M, K] @ W[N, K]^T
+        N, K = self.w.shape
+        if self.skinny:
+            _lib.call("slu_skinny_gemm", x2.data_ptr(), K, self.w.data_ptr(), K, 1, _lib.ptr(bias), out.data_ptr(), N, M, N, K, _lib.stream())
+        else:
+            ops.gemm_tc(x2, K, self.img_nt, M, N, K, out, bias=bias)
+
+    def nn(self, g2, M, out):                     # out [M, K] = g2 [M, N] @ W[N, K]
+        N, K = self.w.shape
+        if self.skinny:
+            _lib.call("slu_skinny_gemm", g2.data_ptr(), N, self.w.data_ptr(), 1, K, None, out.data_ptr(), K, M, K, N, _lib.stream())
+        else:
+            ops.gemm_tc(g2, N, self.img_nn, M, K, N, out)
 
 
 class DecoderStates(torch.autograd.Function):
@@ -45,10 +71,7 @@ class DecoderStates(torch.autograd.Function):
         w_c_, w_hh0_, w_ih1_ = w_c.detach().contiguous(), w_hh0.detach().contiguous(), w_ih1.detach().contiguous()
         N1 = G + K
         need = any(ctx.needs_input_grad)
-        items = [(wcat1, ops._form_nt(wcat1)), (w_hh0_, ops._form_nt(w_hh0_)), (w_c_, ops._form_nt(w_c_)), (w_ih1_, ops._form_nt(w_ih1_))]
-        if need:
-            items += [(wcat1, ops._form_nn(wcat1)), (w_hh0_, ops._form_nn(w_hh0_)), (w_c_, ops._form_nn(w_c_)), (w_ih1_, ops._form_nn(w_ih1_))]
-        imgs = ops.presplit_many(items)
+        Wcat1, Whh0, Wc, Wih1 = (_W(w, need, B) for w in (wcat1, w_hh0_, w_c_, w_ih1_))
         s0 = f(U + 1, B, D); s1 = f(U + 1, B, D)                                        # [0] = initial state, [u+1] = after symbol u
         s0[0].copy_(init_state[0].detach().expand(B, D)); s1[0].copy_(init_state[1].detach().expand(B, D))
         g1 = f(U, B, N1)                                                                # gh1 | query of every step
@@ -58,19 +81,19 @@ class DecoderStates(torch.autograd.Function):
         inv_scale = 1.0 / math.sqrt(float(K))
         b_hh0_, b_ih1_ = b_hh0.detach().contiguous(), b_ih1.detach().contiguous()
         for u in range(U):
-            _gemm_nt(s1[u], imgs[0], B, N1, D, g1[u], bias=bcat1)                       # s1 -> gh1 | q
-            _gemm_nt(s0[u], imgs[1], B, G, D, gh0, bias=b_hh0_)                         # s0 -> gh0
+            Wcat1.nt(s1[u], B, g1[u], bcat1)                                            # s1 -> gh1 | q
+            Whh0.nt(s0[u], B, gh0, b_hh0_)                                              # s0 -> gh0
             _lib.call("slu_attn_step_fwd", g1[u].data_ptr() + 4 * G, N1, keys.data_ptr(), values.data_ptr(), B, T, K, V, inv_scale,
                       watt[u].data_ptr(), ctxs[u].data_ptr(), st)
-            _gemm_nt(ctxs[u], imgs[2], B, G, V, gi0c)                                   # context half of the first cell's input
+            Wc.nt(ctxs[u], B, gi0c)                                                     # context half of the first cell's input
             _lib.call("slu_grucell_fwd", ge_all[u].data_ptr(), G, gi0c.data_ptr(), G, gh0.data_ptr(), G, s0[u].data_ptr(), None, B, D,
                       float(drop_p), int(drop_seed), u, s0[u + 1].data_ptr(), stash0[u].data_ptr(), d0[u].data_ptr(), st)
-            _gemm_nt(d0[u], imgs[3], B, G, D, gi1, bias=b_ih1_)
+            Wih1.nt(d0[u], B, gi1, b_ih1_)
             _lib.call("slu_grucell_fwd", gi1.data_ptr(), G, None, 0, g1[u].data_ptr(), N1, s1[u].data_ptr(), None, B, D,
                       0.0, 0, u, s1[u + 1].data_ptr(), stash1[u].data_ptr(), None, st)
         if need:
             ctx.save_for_backward(keys, values, s0, s1, g1, watt, ctxs, d0, stash0, stash1)
-            ctx.imgs = imgs[4:]
+            ctx.weights = (Wcat1, Whh0, Wc, Wih1)
             ctx.drop = (float(drop_p), int(drop_seed))
             ctx.dims = (B, T, K, V, U, D)
         return s1[1:]
@@ -78,7 +101,7 @@ class DecoderStates(torch.autograd.Function):
     @staticmethod
     def backward(ctx, ds_all):
         keys, values, s0, s1, g1, watt, ctxs, d0, stash0, stash1 = ctx.saved_tensors
-        img_cat1, img_hh0, img_c, img_ih1 = ctx.imgs
+        Wcat1, Whh0, Wc, Wih1 = ctx.weights
         drop_p, drop_seed = ctx.drop
         B, T, K, V, U, D = ctx.dims
         G, N1 = 3 * D, 3 * D + K
@@ -100,16 +123,16 @@ class DecoderStates(torch.autograd.Function):
             _lib.call("slu_grucell_bwd", ds_all[u].data_ptr(), dir1[nxt].data_ptr() if have_next else None,
                       rec1[nxt].data_ptr() if have_next else None, stash1[u].data_ptr(), s1[u].data_ptr(), None, B, D, 0.0, 0, u,
                       dgi1[u].data_ptr(), G, dg1[u].data_ptr(), N1, dir1[cur].data_ptr(), st)
-            _gemm_nt(dgi1[u], img_ih1, B, D, G, dd0)                                    # -> d(dropped s0')
+            Wih1.nn(dgi1[u], B, dd0)                                                    # -> d(dropped s0')
             # first cell: dh = dd0 * mask (+ what step u+1 sent back)
             _lib.call("slu_grucell_bwd", dd0.data_ptr(), dir0[nxt].data_ptr() if have_next else None,
                       rec0[nxt].data_ptr() if have_next else None, stash0[u].data_ptr(), s0[u].data_ptr(), None, B, D, drop_p, drop_seed,
                       u, dgi0[u].data_ptr(), G, dgh0[u].data_ptr(), G, dir0[cur].data_ptr(), st)
-            _gemm_nt(dgi0[u], img_c, B, V, G, dctx)
+            Wc.nn(dgi0[u], B, dctx)
             _lib.call("slu_attn_step_bwd", dctx.data_ptr(), watt[u].data_ptr(), g1[u].data_ptr() + 4 * G, N1, keys.data_ptr(),
                       values.data_ptr(), B, T, K, V, inv_scale, dg1[u].data_ptr() + 4 * G, N1, dkeys.data_ptr(), dvalues.data_ptr(), st)
-            _gemm_nt(dg1[u], img_cat1, B, D, N1, rec1[cur])                             # (dgh1 | dq) -> ds1[u-1]
-            _gemm_nt(dgh0[u], img_hh0, B, D, G, rec0[cur])                              # dgh0 -> ds0[u-1]
+            Wcat1.nn(dg1[u], B, rec1[cur])                                              # (dgh1 | dq) -> ds1[u-1]
+            Whh0.nn(dgh0[u], B, rec0[cur])                                              # dgh0 -> ds0[u-1]
             have_next = True
         # initial state: sum over the batch of what step 0 sent back (direct + recurrent)
         dinit = z(2, D)

@@ -201,7 +201,11 @@ int slu_scale(const float* src, float* dst, long n, const float* g, void* stream
  *   slu_grucell_fwd  : torch.nn.GRUCell gate math on precomputed gi = gi_a (+ gi_b) and gh (rows of 3D: r | z | n, biases
  *                      included): h = (1-z) n + z hprev; hprev == NULL: the row h0[D] for every utterance (initial state);
  *                      stash [B][4D] = r | z | n | gh_n; dropped [B][D] (may be NULL) = h * Philox keep-mask(drop_p, drop_seed, step)
- *   slu_grucell_bwd  : dh = da * mask(step) + db + dc (db, dc may be NULL) -> dgi [B][ldgi], dgh [B][ldgh], dh_direct = dh * z */
+ *   slu_grucell_bwd  : dh = da * mask(step) + db + dc (db, dc may be NULL) -> dgi [B][ldgi], dgh [B][ldgh], dh_direct = dh * z
+ *   slu_skinny_gemm  : C[m][n] = sum_k A[m*lda + k] * W[n*sn + k*sk] (+ bias[n]) for M <= 64 rows: the per-symbol projections are
+ *                      latency-bound (a persistent tensor-core pipeline costs more to start than they take): exact-fp32 CUDA cores. */
+int slu_skinny_gemm(const float* A, long lda, const float* W, long sn, long sk, const float* bias, float* C, long ldc, int M, int N, int K,
+                    void* stream);
 int slu_attn_step_fwd(const float* q, long ldq, const float* keys, const float* values, int B, int T, int K, int V, float inv_scale,
                       float* w, float* ctx, void* stream);
 int slu_attn_step_bwd(const float* dctx, const float* w, const float* q, long ldq, const float* keys, const float* values, int B, int T,
