@@ -24,11 +24,11 @@ SIGNATURES = {
     "slu_sincconv_bwd_tc": [_P, _P, _P, _I, _I, _P, _P],
     "slu_sincconv_bwd_jac_tc": [_P, _P, _P, _P, _I, _I, _P, _P, _P],
     "slu_sinc_filters_jac": [_P, _P, _P, _P],
-    "slu_gru_fwd_simt": [_P, _P, _P, _P, _F, _U, _I, _I, _I, _P, _P, _P, _P],
-    "slu_gru_bwd_simt": [_P, _P, _F, _U, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
-    "slu_gru_fwd_tc": [_P, _P, _P, _P, _F, _U, _I, _I, _I, _P, _P, _P, _P],
-    "slu_gru_bwd_tc": [_P, _P, _F, _U, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
-    "slu_bigru_bwd_tc": [_P, _P, _F, _U, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "slu_gru_fwd_simt": [_P, _P, _P, _P, _F, _U, _P, _I, _I, _I, _P, _P, _P, _P],
+    "slu_gru_bwd_simt": [_P, _P, _F, _U, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "slu_gru_fwd_tc": [_P, _P, _P, _P, _F, _U, _P, _I, _I, _I, _P, _P, _P, _P],
+    "slu_gru_bwd_tc": [_P, _P, _F, _U, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "slu_bigru_bwd_tc": [_P, _P, _F, _U, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "slu_set_gru_precision": [_I],
     "slu_gru_rows_per_cta": [_I],
     "slu_debug_gru_phase_clocks": [_P],
@@ -51,8 +51,9 @@ SIGNATURES = {
     "slu_skinny_gemm": [_P, _L, _P, _L, _L, _P, _P, _L, _I, _I, _I, _P],
     "slu_attn_step_fwd": [_P, _L, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P],
     "slu_attn_step_bwd": [_P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P, _L, _P, _P, _P],
-    "slu_grucell_fwd": [_P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _F, _U, _I, _P, _P, _P, _P],
-    "slu_grucell_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _U, _I, _P, _L, _P, _L, _P, _P],
+    "slu_grucell_fwd": [_P, _L, _P, _L, _P, _L, _P, _P, _I, _I, _F, _U, _P, _I, _P, _P, _P, _P],
+    "slu_grucell_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _U, _P, _I, _P, _L, _P, _L, _P, _P],
+    "slu_seed_advance": [_P, _P],
     "slu_ce_count": [_P, _L, _P, _P],
     "slu_ce_rows": [_P, _L, _I, _P, _L, _P, _I, _P, _P, _P],
     "slu_ce_finish": [_P, _P, _L, _P, _P, _P],

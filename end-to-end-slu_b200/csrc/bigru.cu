@@ -10,13 +10,14 @@
 #include "common.cuh"
 #include "../../include/slu_b200.h"
 
-extern "C" int slu_bigru_bwd_tc(const float* gy, const float* drop_mask, float drop_p, unsigned long long drop_seed, const float* y_full, const float* stash, const float* w_hh,
+extern "C" int slu_bigru_bwd_tc(const float* gy, const float* drop_mask, float drop_p, unsigned long long drop_seed,
+                                const unsigned long long* drop_seed_dev, const float* y_full, const float* stash, const float* w_hh,
                                 const float* x, int I, const void* w_ih_nn_img, int B, int T, int ds, float* dgx, float* dhn,
                                 float* db_ih, float* db_hh, float* dw_ih, float* dw_hh, float* dx, int overlap, void* stream) {
   if (B <= 0 || T <= 0 || I <= 0 || !dgx || !dhn) return (int)cudaErrorInvalidValue;
   if (dx && !w_ih_nn_img) return (int)cudaErrorInvalidValue;
   if ((dw_ih == nullptr) != (dw_hh == nullptr)) return (int)cudaErrorInvalidValue;
-  int e = slu_gru_bwd_tc(gy, drop_mask, drop_p, drop_seed, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh, stream);
+  int e = slu_gru_bwd_tc(gy, drop_mask, drop_p, drop_seed, drop_seed_dev, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh, stream);
   if (e) return e;
   void* side[3] = {stream, stream, stream};
   const int ns = (dw_ih && overlap) ? 3 : 0;

@@ -128,8 +128,9 @@ __device__ __forceinline__ float cell_mask(uint64_t seed, int step, long elem, u
 // broadcast) -> h [B][D], stash [B][4D] = r | z | n | gh_n, dropped [B][D] = h * mask (NULL: no dropout output wanted)
 __global__ void grucell_fwd_kernel(const float* __restrict__ gi_a, long lda, const float* __restrict__ gi_b, long ldb,
                                    const float* __restrict__ gh, long ldh, const float* __restrict__ hprev, const float* __restrict__ h0,
-                                   int B, int D, uint32_t thr, float scale, uint64_t seed, int step, float* __restrict__ h,
-                                   float* __restrict__ stash, float* __restrict__ dropped) {
+                                   int B, int D, uint32_t thr, float scale, uint64_t seed_in, const unsigned long long* __restrict__ seed_dev,
+                                   int step, float* __restrict__ h, float* __restrict__ stash, float* __restrict__ dropped) {
+  const uint64_t seed = seed_dev ? (seed_in ^ (uint64_t)__ldg(seed_dev)) : seed_in;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)B * D) return;
   const int b = (int)(i / D), j = (int)(i - (long)b * D);
@@ -152,8 +153,10 @@ __global__ void grucell_fwd_kernel(const float* __restrict__ gi_a, long lda, con
 // dgh [B][ldgh] (dr, dz, dn*r), dh_direct [B][D] = dh * z
 __global__ void grucell_bwd_kernel(const float* __restrict__ da, const float* __restrict__ db, const float* __restrict__ dc,
                                    const float* __restrict__ stash, const float* __restrict__ hprev, const float* __restrict__ h0, int B,
-                                   int D, uint32_t thr, float scale, uint64_t seed, int step, float* __restrict__ dgi, long ldgi,
-                                   float* __restrict__ dgh, long ldgh, float* __restrict__ dh_direct) {
+                                   int D, uint32_t thr, float scale, uint64_t seed_in, const unsigned long long* __restrict__ seed_dev,
+                                   int step, float* __restrict__ dgi, long ldgi, float* __restrict__ dgh, long ldgh,
+                                   float* __restrict__ dh_direct) {
+  const uint64_t seed = seed_dev ? (seed_in ^ (uint64_t)__ldg(seed_dev)) : seed_in;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)B * D) return;
   const int b = (int)(i / D), j = (int)(i - (long)b * D);
@@ -194,55 +197,60 @@ extern "C" int slu_attn_step_bwd(const float* dctx, const float* w, const float*
 }
 
 extern "C" int slu_grucell_fwd(const float* gi_a, long lda, const float* gi_b, long ldb, const float* gh, long ldh, const float* hprev,
-                               const float* h0, int B, int D, float drop_p, unsigned long long drop_seed, int step, float* h, float* stash,
-                               float* dropped, void* stream) {
+                               const float* h0, int B, int D, float drop_p, unsigned long long drop_seed,
+                               const unsigned long long* drop_seed_dev, int step, float* h, float* stash, float* dropped, void* stream) {
   if (B <= 0 || D <= 0 || (!hprev && !h0) || !(drop_p >= 0.f && drop_p < 1.f)) return (int)cudaErrorInvalidValue;
   const uint32_t thr = drop_p > 0.f ? slu_keep_threshold(drop_p) : 0u;
   const long n = (long)B * D;
   grucell_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      gi_a, lda, gi_b, ldb, gh, ldh, hprev, h0, B, D, thr, (float)(1.0 / (1.0 - (double)drop_p)), drop_seed, step, h, stash, dropped);
+      gi_a, lda, gi_b, ldb, gh, ldh, hprev, h0, B, D, thr, (float)(1.0 / (1.0 - (double)drop_p)), drop_seed, drop_seed_dev, step, h, stash, dropped);
   SLU_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int slu_grucell_bwd(const float* da, const float* db, const float* dc, const float* stash, const float* hprev, const float* h0,
-                               int B, int D, float drop_p, unsigned long long drop_seed, int step, float* dgi, long ldgi, float* dgh,
-                               long ldgh, float* dh_direct, void* stream) {
+                               int B, int D, float drop_p, unsigned long long drop_seed, const unsigned long long* drop_seed_dev, int step,
+                               float* dgi, long ldgi, float* dgh, long ldgh, float* dh_direct, void* stream) {
   if (B <= 0 || D <= 0 || (!hprev && !h0) || !(drop_p >= 0.f && drop_p < 1.f)) return (int)cudaErrorInvalidValue;
   const uint32_t thr = drop_p > 0.f ? slu_keep_threshold(drop_p) : 0u;
   const long n = (long)B * D;
   grucell_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      da, db, dc, stash, hprev, h0, B, D, thr, (float)(1.0 / (1.0 - (double)drop_p)), drop_seed, step, dgi, ldgi, dgh, ldgh, dh_direct);
+      da, db, dc, stash, hprev, h0, B, D, thr, (float)(1.0 / (1.0 - (double)drop_p)), drop_seed, drop_seed_dev, step, dgi, ldgi, dgh, ldgh, dh_direct);
   SLU_CHECK_LAUNCH();
   return 0;
 }
 
 // ---- skinny GEMM for the decoder's per-symbol projections: C[m][n] = sum_k A[m*lda + k] * W[n*sn + k*sk] (+ bias[n]), M <= 64.
 // These are latency-bound GEMV-like products (64 utterances x a few hundred outputs, 28 MFLOP at most): a persistent tensor-core
-// pipeline costs more to start than the product takes, so this is an exact-fp32 CUDA-core kernel -- a CTA owns 16 output columns,
-// stages the activation rows and its weight rows through shared memory in K chunks of 128, every thread accumulates 4 outputs.
+// pipeline costs more to start than the product takes, so this is an exact-fp32 CUDA-core kernel.  A CTA owns 8 output columns
+// (N = 200..868 -> 25..109 CTAs), stages the activation rows and its weight rows through shared memory in K chunks of 128 and every
+// thread accumulates 2 outputs with 128-bit shared-memory loads (3 LDS.128 per 8 FMAs: the loop is FMA-, not LSU-bound).
 namespace {
-constexpr int SK_M = 64, SK_N = 16, SK_KC = 128;
+constexpr int SK_M = 64, SK_N = 8, SK_KC = 128, SK_LD = SK_KC + 4;      // row pitch 132 floats: 16-byte rows, conflict-free LDS.128
 
 __global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restrict__ A, long lda, const float* __restrict__ W, long sn, long sk,
                                                           const float* __restrict__ bias, float* __restrict__ C, long ldc, int M, int N,
                                                           int K) {
-  __shared__ float As[SK_M][SK_KC + 1];
-  __shared__ float Ws[SK_N][SK_KC + 1];
-  const int tid = threadIdx.x, m = tid & 63, ng = tid >> 6;            // 64 rows x 4 groups of 4 columns
+  __shared__ __align__(16) float As[SK_M][SK_LD];
+  __shared__ __align__(16) float Ws[SK_N][SK_LD];
+  const int tid = threadIdx.x, m = tid & 63, cg = tid >> 6;            // 64 rows x 4 groups of 2 columns
   const int n0 = blockIdx.x * SK_N;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc0 = 0.f, acc1 = 0.f;
   for (int k0 = 0; k0 < K; k0 += SK_KC) {
-    const int kc = min(SK_KC, K - k0);
+    const int kc = min(SK_KC, K - k0);                                  // K % 4 == 0 -> kc % 4 == 0
     __syncthreads();
-    for (int i = tid; i < SK_M * SK_KC; i += 256) {                     // activation chunk: coalesced along k
-      const int r = i / SK_KC, k = i - r * SK_KC;
-      As[r][k] = (r < M && k < kc) ? A[(long)r * lda + k0 + k] : 0.f;
+    for (int i = tid; i < SK_M * (SK_KC / 4); i += 256) {               // activation chunk: float4 along k
+      const int r = i / (SK_KC / 4), k4 = (i - r * (SK_KC / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < M && k4 < kc) v = *reinterpret_cast<const float4*>(A + (long)r * lda + k0 + k4);
+      *reinterpret_cast<float4*>(&As[r][k4]) = v;
     }
     if (sk == 1) {                                                      // weight rows contiguous along k
-      for (int i = tid; i < SK_N * SK_KC; i += 256) {
-        const int r = i / SK_KC, k = i - r * SK_KC;
-        Ws[r][k] = (n0 + r < N && k < kc) ? W[(long)(n0 + r) * sn + k0 + k] : 0.f;
+      for (int i = tid; i < SK_N * (SK_KC / 4); i += 256) {
+        const int r = i / (SK_KC / 4), k4 = (i - r * (SK_KC / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + r < N && k4 < kc) v = *reinterpret_cast<const float4*>(W + (long)(n0 + r) * sn + k0 + k4);
+        *reinterpret_cast<float4*>(&Ws[r][k4]) = v;
       }
     } else {                                                            // transposed view: contiguous along n
       for (int i = tid; i < SK_N * SK_KC; i += 256) {
@@ -251,25 +259,28 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restric
       }
     }
     __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < SK_KC; ++k) {
-      const float a = As[m][k];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, Ws[ng * 4 + j][k], acc[j]);
+    const float4* a4 = reinterpret_cast<const float4*>(&As[m][0]);
+    const float4* w0 = reinterpret_cast<const float4*>(&Ws[cg * 2][0]);
+    const float4* w1 = reinterpret_cast<const float4*>(&Ws[cg * 2 + 1][0]);
+#pragma unroll 8
+    for (int k4 = 0; k4 < SK_KC / 4; ++k4) {
+      const float4 a = a4[k4], x = w0[k4], y = w1[k4];
+      acc0 = fmaf(a.x, x.x, acc0); acc0 = fmaf(a.y, x.y, acc0); acc0 = fmaf(a.z, x.z, acc0); acc0 = fmaf(a.w, x.w, acc0);
+      acc1 = fmaf(a.x, y.x, acc1); acc1 = fmaf(a.y, y.y, acc1); acc1 = fmaf(a.z, y.z, acc1); acc1 = fmaf(a.w, y.w, acc1);
     }
   }
-  if (m < M)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + ng * 4 + j;
-      if (n < N) C[(long)m * ldc + n] = acc[j] + (bias ? bias[n] : 0.f);
-    }
+  if (m < M) {
+    const int n = n0 + cg * 2;
+    if (n < N) C[(long)m * ldc + n] = acc0 + (bias ? bias[n] : 0.f);
+    if (n + 1 < N) C[(long)m * ldc + n + 1] = acc1 + (bias ? bias[n + 1] : 0.f);
+  }
 }
 }  // namespace
 
 extern "C" int slu_skinny_gemm(const float* A, long lda, const float* W, long sn, long sk, const float* bias, float* C, long ldc, int M,
                                int N, int K, void* stream) {
-  if (M <= 0 || M > SK_M || N <= 0 || K <= 0) return (int)cudaErrorInvalidValue;
+  if (M <= 0 || M > SK_M || N <= 0 || K <= 0 || (K & 3) || (lda & 3) || (reinterpret_cast<uintptr_t>(A) & 15)) return (int)cudaErrorInvalidValue;
+  if (sk == 1 && ((sn & 3) || (reinterpret_cast<uintptr_t>(W) & 15))) return (int)cudaErrorInvalidValue;
   skinny_gemm_kernel<<<(N + SK_N - 1) / SK_N, 256, 0, (cudaStream_t)stream>>>(A, lda, W, sn, sk, bias, C, ldc, M, N, K);
   SLU_CHECK_LAUNCH();
   return 0;

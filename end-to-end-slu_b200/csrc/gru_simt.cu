@@ -35,9 +35,10 @@ __device__ __forceinline__ float reduce_scatter4(const float v[4], int q) {
 template <bool STASH>
 __global__ void __launch_bounds__(512, 1)
 gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
-               const float* __restrict__ mask, uint32_t drop_thr, float drop_scale, uint64_t drop_seed, int B, int T, int ds,
-               float* __restrict__ y_full,
+               const float* __restrict__ mask, uint32_t drop_thr, float drop_scale, uint64_t drop_seed_in,
+               const unsigned long long* __restrict__ drop_seed_dev, int B, int T, int ds, float* __restrict__ y_full,
                float* __restrict__ y_out, float* __restrict__ stash) {
+  const uint64_t drop_seed = drop_seed_dev ? (drop_seed_in ^ (uint64_t)__ldg(drop_seed_dev)) : drop_seed_in;
   extern __shared__ float4 smem4[];
   float4* Ws = smem4;                                        // [(g*32 + c)*128 + j] = W[g*128+j][4c..4c+3]
   float* hs = reinterpret_cast<float*>(smem4 + 3 * 32 * 128);  // [2][BT][128]
@@ -131,9 +132,10 @@ gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, con
 // and carries dh through  dh_{t-1} += W_hh^T [dr, dz, dhn].
 __global__ void __launch_bounds__(512, 1)
 gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, uint32_t drop_thr, float drop_scale,
-               uint64_t drop_seed, const float* __restrict__ y_full,
+               uint64_t drop_seed_in, const unsigned long long* __restrict__ drop_seed_dev, const float* __restrict__ y_full,
                const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds,
                float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ db_ih, float* __restrict__ db_hh) {
+  const uint64_t drop_seed = drop_seed_dev ? (drop_seed_in ^ (uint64_t)__ldg(drop_seed_dev)) : drop_seed_in;
   extern __shared__ float4 smem4[];
   float4* Wt = smem4;                                          // [c*128 + k] = W[4c..4c+3][k], c < 96
   float* gs = reinterpret_cast<float*>(smem4 + 96 * 128);      // [2][BT][384]
@@ -224,8 +226,8 @@ gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask,
 }  // namespace
 
 extern "C" int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, float drop_p,
-                                unsigned long long drop_seed, int B, int T, int ds, float* y_full, float* y_out, float* stash,
-                                void* stream) {
+                                unsigned long long drop_seed, const unsigned long long* drop_seed_dev, int B, int T, int ds,
+                                float* y_full, float* y_out, float* stash, void* stream) {
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || !(drop_p >= 0.f && drop_p < 1.f)) return (int)cudaErrorInvalidValue;
   const uint32_t thr = (!drop_mask && drop_p > 0.f) ? slu_keep_threshold16(drop_p) : 0u;
   const float dscale = (float)(1.0 / (1.0 - (double)drop_p));
@@ -233,15 +235,15 @@ extern "C" int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float*
   SLU_SMEM_ONCE(gru_fwd_kernel<true>, smem);
   SLU_SMEM_ONCE(gru_fwd_kernel<false>, smem);
   dim3 grid((B + BT - 1) / BT, 2);
-  if (stash) gru_fwd_kernel<true><<<grid, 512, smem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, thr, dscale, drop_seed, B, T, ds, y_full, y_out, stash);
-  else gru_fwd_kernel<false><<<grid, 512, smem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, thr, dscale, drop_seed, B, T, ds, y_full, y_out, nullptr);
+  if (stash) gru_fwd_kernel<true><<<grid, 512, smem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, thr, dscale, drop_seed, drop_seed_dev, B, T, ds, y_full, y_out, stash);
+  else gru_fwd_kernel<false><<<grid, 512, smem, (cudaStream_t)stream>>>(gx, w_hh, b_hh, drop_mask, thr, dscale, drop_seed, drop_seed_dev, B, T, ds, y_full, y_out, nullptr);
   SLU_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, float drop_p, unsigned long long drop_seed,
-                                const float* y_full, const float* stash, const float* w_hh, int B, int T, int ds, float* dgx,
-                                float* dhn, float* db_ih, float* db_hh, void* stream) {
+                                const unsigned long long* drop_seed_dev, const float* y_full, const float* stash, const float* w_hh,
+                                int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh, void* stream) {
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (db_ih == nullptr) != (db_hh == nullptr) || !(drop_p >= 0.f && drop_p < 1.f))
     return (int)cudaErrorInvalidValue;
   const uint32_t thr = (!drop_mask && drop_p > 0.f) ? slu_keep_threshold16(drop_p) : 0u;
@@ -249,7 +251,7 @@ extern "C" int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, flo
   const size_t smem = W_SMEM + 2 * BT * SLU_G3 * sizeof(float);
   SLU_SMEM_ONCE(gru_bwd_kernel, smem);
   dim3 grid((B + BT - 1) / BT, 2);
-  gru_bwd_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(dy_out, drop_mask, thr, dscale, drop_seed, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh);
+  gru_bwd_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(dy_out, drop_mask, thr, dscale, drop_seed, drop_seed_dev, y_full, stash, w_hh, B, T, ds, dgx, dhn, db_ih, db_hh);
   SLU_CHECK_LAUNCH();
   return 0;
 }

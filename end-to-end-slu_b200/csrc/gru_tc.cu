@@ -128,8 +128,11 @@ constexpr float kLog2e = 1.4426950408889634f;
 template <int NB, int NR, bool STASH, bool FULL, int PASSES>
 __global__ void __launch_bounds__(block_threads(NR), 1)
 gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
-                  const float* __restrict__ mask, uint32_t drop_thr, float drop_scale, uint64_t drop_seed, int B, int T, int ds, int tile0,
+                  const float* __restrict__ mask, uint32_t drop_thr, float drop_scale, uint64_t drop_seed_in,
+                  const unsigned long long* __restrict__ drop_seed_dev, int B, int T, int ds, int tile0,
                   float* __restrict__ y_full, float* __restrict__ y_out, float* __restrict__ stash) {
+  // drop_seed_dev != NULL: a per-step word in device memory is mixed into the seed (CUDA-graph replays draw fresh masks)
+  const uint64_t drop_seed = drop_seed_dev ? (drop_seed_in ^ (uint64_t)__ldg(drop_seed_dev)) : drop_seed_in;
   constexpr int NC = NR * 128 / TC_THREADS;         // batch columns per thread (NR real rows; the MMA is N = NB wide)
   constexpr uint32_t LBO = NB * 16 + 16;             // padded: conflict-free 2-byte operand stores
   __shared__ __align__(128) uint8_t h_tile[2 * 16 * LBO];   // [hi | lo] x 16 k-chunks x (NB rows x 16 B + pad)
@@ -344,11 +347,12 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
 template <int NB, int NR, bool FULL, int PASSES>
 __global__ void __launch_bounds__(block_threads(NR), 1)
 gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask, uint32_t drop_thr, float drop_scale,
-                  uint64_t drop_seed, const float* __restrict__ y_full,
+                  uint64_t drop_seed_in, const unsigned long long* __restrict__ drop_seed_dev, const float* __restrict__ y_full,
                   const float* __restrict__ stash, const float* __restrict__ w_hh, int B, int T, int ds, int tile0,
                   float* __restrict__ dgx, float* __restrict__ dhn_out, float* __restrict__ db_ih, float* __restrict__ db_hh) {
   constexpr int NC = NR * 128 / TC_THREADS;
   constexpr uint32_t LBO = NB * 16 + 16;
+  const uint64_t drop_seed = drop_seed_dev ? (drop_seed_in ^ (uint64_t)__ldg(drop_seed_dev)) : drop_seed_in;
   __shared__ __align__(128) uint8_t g_tile[2 * 48 * LBO];   // [hi | lo] x 48 k-chunks (384 gate rows)
   __shared__ uint64_t bar, in_bar[BWD_RING];
   __shared__ uint32_t tmem_base;
@@ -568,10 +572,10 @@ extern "C" int slu_set_gru_precision(int mode) {
 static int pick_rows(int B) { return B >= 1184 ? 16 : (B >= 592 ? 8 : 4); }
 extern "C" int slu_gru_rows_per_cta(int B) { return pick_rows(B); }
 
-struct DropArgs { uint32_t thr; float scale; uint64_t seed; };
-static DropArgs drop_args(const float* mask, float p, unsigned long long seed) {
-  DropArgs a = {0u, 1.f, 0ull};
-  if (!mask && p > 0.f) { a.thr = slu_keep_threshold16(p); a.scale = (float)(1.0 / (1.0 - (double)p)); a.seed = seed; }
+struct DropArgs { uint32_t thr; float scale; uint64_t seed; const unsigned long long* seed_dev; };
+static DropArgs drop_args(const float* mask, float p, unsigned long long seed, const unsigned long long* seed_dev) {
+  DropArgs a = {0u, 1.f, 0ull, nullptr};
+  if (!mask && p > 0.f) { a.thr = slu_keep_threshold16(p); a.scale = (float)(1.0 / (1.0 - (double)p)); a.seed = seed; a.seed_dev = seed_dev; }
   return a;
 }
 
@@ -583,9 +587,9 @@ static int launch_fwd(dim3 grid, cudaStream_t st, const float* gx, const float* 
   SLU_SMEM_ONCE((gru_fwd_tc_kernel<16, NR, STASH, FULL, 3>), smem);
   SLU_SMEM_ONCE((gru_fwd_tc_kernel<16, NR, STASH, FULL, P>), smem);
   SLU_SMEM_ONCE((gru_fwd_tc_kernel<16, NR, STASH, FULL, 1>), smem);
-  if (g_gru_mode == 0) gru_fwd_tc_kernel<16, NR, STASH, FULL, P><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, dr.thr, dr.scale, dr.seed, B, T, ds, tile0, y_full, y_out, stash);
-  else if (g_gru_mode == 2) gru_fwd_tc_kernel<16, NR, STASH, FULL, 3><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, dr.thr, dr.scale, dr.seed, B, T, ds, tile0, y_full, y_out, stash);
-  else gru_fwd_tc_kernel<16, NR, STASH, FULL, 1><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, dr.thr, dr.scale, dr.seed, B, T, ds, tile0, y_full, y_out, stash);
+  if (g_gru_mode == 0) gru_fwd_tc_kernel<16, NR, STASH, FULL, P><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, dr.thr, dr.scale, dr.seed, dr.seed_dev, B, T, ds, tile0, y_full, y_out, stash);
+  else if (g_gru_mode == 2) gru_fwd_tc_kernel<16, NR, STASH, FULL, 3><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, dr.thr, dr.scale, dr.seed, dr.seed_dev, B, T, ds, tile0, y_full, y_out, stash);
+  else gru_fwd_tc_kernel<16, NR, STASH, FULL, 1><<<grid, block_threads(NR), smem, st>>>(gx, w_hh, b_hh, mask, dr.thr, dr.scale, dr.seed, dr.seed_dev, B, T, ds, tile0, y_full, y_out, stash);
   return 0;
 }
 
@@ -606,10 +610,10 @@ static int run_fwd(cudaStream_t st, const float* gx, const float* w_hh, const fl
 }
 
 extern "C" int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, float drop_p,
-                              unsigned long long drop_seed, int B, int T, int ds, float* y_full, float* y_out, float* stash,
-                              void* stream) {
+                              unsigned long long drop_seed, const unsigned long long* drop_seed_dev, int B, int T, int ds, float* y_full,
+                              float* y_out, float* stash, void* stream) {
   if (!(drop_p >= 0.f && drop_p < 1.f)) return (int)cudaErrorInvalidValue;
-  const DropArgs dr = drop_args(drop_mask, drop_p, drop_seed);
+  const DropArgs dr = drop_args(drop_mask, drop_p, drop_seed, drop_seed_dev);
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2)) return (int)cudaErrorInvalidValue;
   if ((long)B * T * 1024 >= (1L << 31)) return SLU_ERR_TOO_LARGE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -632,9 +636,9 @@ static int launch_bwd(dim3 grid, cudaStream_t st, const float* dy_out, const flo
   SLU_SMEM_ONCE((gru_bwd_tc_kernel<16, NR, FULL, 3>), smem);
   SLU_SMEM_ONCE((gru_bwd_tc_kernel<16, NR, FULL, P>), smem);
   SLU_SMEM_ONCE((gru_bwd_tc_kernel<16, NR, FULL, 1>), smem);
-  if (g_gru_mode == 0) gru_bwd_tc_kernel<16, NR, FULL, P><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, dr.thr, dr.scale, dr.seed, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
-  else if (g_gru_mode == 2) gru_bwd_tc_kernel<16, NR, FULL, 3><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, dr.thr, dr.scale, dr.seed, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
-  else gru_bwd_tc_kernel<16, NR, FULL, 1><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, dr.thr, dr.scale, dr.seed, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
+  if (g_gru_mode == 0) gru_bwd_tc_kernel<16, NR, FULL, P><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, dr.thr, dr.scale, dr.seed, dr.seed_dev, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
+  else if (g_gru_mode == 2) gru_bwd_tc_kernel<16, NR, FULL, 3><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, dr.thr, dr.scale, dr.seed, dr.seed_dev, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
+  else gru_bwd_tc_kernel<16, NR, FULL, 1><<<grid, block_threads(NR), smem, st>>>(dy_out, mask, dr.thr, dr.scale, dr.seed, dr.seed_dev, y_full, stash, w_hh, B, T, ds, tile0, dgx, dhn, db_ih, db_hh);
   return 0;
 }
 
@@ -649,10 +653,10 @@ static int run_bwd(cudaStream_t st, const float* dy_out, const float* mask, Drop
 }
 
 extern "C" int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, float drop_p, unsigned long long drop_seed,
-                              const float* y_full, const float* stash, const float* w_hh, int B, int T, int ds, float* dgx,
-                              float* dhn, float* db_ih, float* db_hh, void* stream) {
+                              const unsigned long long* drop_seed_dev, const float* y_full, const float* stash, const float* w_hh,
+                              int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh, void* stream) {
   if (!(drop_p >= 0.f && drop_p < 1.f)) return (int)cudaErrorInvalidValue;
-  const DropArgs dr = drop_args(drop_mask, drop_p, drop_seed);
+  const DropArgs dr = drop_args(drop_mask, drop_p, drop_seed, drop_seed_dev);
   if (B <= 0 || T <= 0 || (ds != 1 && ds != 2) || (db_ih == nullptr) != (db_hh == nullptr)) return (int)cudaErrorInvalidValue;
   if ((long)B * T * 1024 >= (1L << 31)) return SLU_ERR_TOO_LARGE;
   cudaStream_t st = (cudaStream_t)stream;

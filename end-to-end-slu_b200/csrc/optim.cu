@@ -103,7 +103,19 @@ __global__ void f64_hilo_merge_kernel(double* __restrict__ dst, const float* __r
   if (i < n) dst[i] = (double)hi[i] + (double)lo[i];
 }
 
+__global__ void seed_advance_kernel(unsigned long long* state) {
+  state[0] = state[0] * 6364136223846793005ull + 1442695040888963407ull;      // 64-bit LCG step
+}
+
 }  // namespace
+
+// The per-step word the dropout seeds are mixed with when a train step runs as a CUDA graph (the by-value seeds are frozen into
+// the graph; this kernel is its first node, so every replay draws fresh masks).
+extern "C" int slu_seed_advance(unsigned long long* state, void* stream) {
+  seed_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+  SLU_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int slu_adam_multi(const void* tensors, int n, double beta1, double beta2, float eps, float weight_decay, void* stream) {
   if (n < 0) return (int)cudaErrorInvalidValue;

@@ -55,7 +55,8 @@ class DecoderStates(torch.autograd.Function):
     weights -> top-layer states after every symbol [U,B,D] (what the output projection reads; models.py:520-556)."""
 
     @staticmethod
-    def forward(ctx, keys, values, ge_all, init_state, wq, bq, w_c, w_hh0, b_hh0, w_ih1, b_ih1, w_hh1, b_hh1, drop_p, drop_seed):
+    def forward(ctx, keys, values, ge_all, init_state, wq, bq, w_c, w_hh0, b_hh0, w_ih1, b_ih1, w_hh1, b_hh1, drop_p, drop_seed,
+                seed_dev=None):
         keys, values, ge_all = _f32(keys), _f32(values), _f32(ge_all)
         B, T, K = keys.shape
         V = values.shape[2]
@@ -87,14 +88,14 @@ class DecoderStates(torch.autograd.Function):
                       watt[u].data_ptr(), ctxs[u].data_ptr(), st)
             Wc.nt(ctxs[u], B, gi0c)                                                     # context half of the first cell's input
             _lib.call("slu_grucell_fwd", ge_all[u].data_ptr(), G, gi0c.data_ptr(), G, gh0.data_ptr(), G, s0[u].data_ptr(), None, B, D,
-                      float(drop_p), int(drop_seed), u, s0[u + 1].data_ptr(), stash0[u].data_ptr(), d0[u].data_ptr(), st)
+                      float(drop_p), int(drop_seed), _lib.ptr(seed_dev), u, s0[u + 1].data_ptr(), stash0[u].data_ptr(), d0[u].data_ptr(), st)
             Wih1.nt(d0[u], B, gi1, b_ih1_)
             _lib.call("slu_grucell_fwd", gi1.data_ptr(), G, None, 0, g1[u].data_ptr(), N1, s1[u].data_ptr(), None, B, D,
-                      0.0, 0, u, s1[u + 1].data_ptr(), stash1[u].data_ptr(), None, st)
+                      0.0, 0, None, u, s1[u + 1].data_ptr(), stash1[u].data_ptr(), None, st)
         if need:
             ctx.save_for_backward(keys, values, s0, s1, g1, watt, ctxs, d0, stash0, stash1)
             ctx.weights = (Wcat1, Whh0, Wc, Wih1)
-            ctx.drop = (float(drop_p), int(drop_seed))
+            ctx.drop = (float(drop_p), int(drop_seed), seed_dev)
             ctx.dims = (B, T, K, V, U, D)
         return s1[1:]
 
@@ -102,7 +103,7 @@ class DecoderStates(torch.autograd.Function):
     def backward(ctx, ds_all):
         keys, values, s0, s1, g1, watt, ctxs, d0, stash0, stash1 = ctx.saved_tensors
         Wcat1, Whh0, Wc, Wih1 = ctx.weights
-        drop_p, drop_seed = ctx.drop
+        drop_p, drop_seed, seed_dev = ctx.drop
         B, T, K, V, U, D = ctx.dims
         G, N1 = 3 * D, 3 * D + K
         dev = keys.device
@@ -121,13 +122,13 @@ class DecoderStates(torch.autograd.Function):
             cur, nxt = u & 1, (u + 1) & 1
             # second cell: dh = dL/ds1[u] (+ what step u+1 sent back)
             _lib.call("slu_grucell_bwd", ds_all[u].data_ptr(), dir1[nxt].data_ptr() if have_next else None,
-                      rec1[nxt].data_ptr() if have_next else None, stash1[u].data_ptr(), s1[u].data_ptr(), None, B, D, 0.0, 0, u,
+                      rec1[nxt].data_ptr() if have_next else None, stash1[u].data_ptr(), s1[u].data_ptr(), None, B, D, 0.0, 0, None, u,
                       dgi1[u].data_ptr(), G, dg1[u].data_ptr(), N1, dir1[cur].data_ptr(), st)
             Wih1.nn(dgi1[u], B, dd0)                                                    # -> d(dropped s0')
             # first cell: dh = dd0 * mask (+ what step u+1 sent back)
             _lib.call("slu_grucell_bwd", dd0.data_ptr(), dir0[nxt].data_ptr() if have_next else None,
                       rec0[nxt].data_ptr() if have_next else None, stash0[u].data_ptr(), s0[u].data_ptr(), None, B, D, drop_p, drop_seed,
-                      u, dgi0[u].data_ptr(), G, dgh0[u].data_ptr(), G, dir0[cur].data_ptr(), st)
+                      _lib.ptr(seed_dev), u, dgi0[u].data_ptr(), G, dgh0[u].data_ptr(), G, dir0[cur].data_ptr(), st)
             Wc.nn(dgi0[u], B, dctx)
             _lib.call("slu_attn_step_bwd", dctx.data_ptr(), watt[u].data_ptr(), g1[u].data_ptr() + 4 * G, N1, keys.data_ptr(),
                       values.data_ptr(), B, T, K, V, inv_scale, dg1[u].data_ptr() + 4 * G, N1, dkeys.data_ptr(), dvalues.data_ptr(), st)
@@ -158,7 +159,7 @@ class DecoderStates(torch.autograd.Function):
         _lib.call("slu_colsum_acc", dgh0.data_ptr(), G, R, G, db_hh0.data_ptr(), st)
         _lib.call("slu_colsum_acc", dgi1.data_ptr(), G, R, G, db_ih1.data_ptr(), st)
         return (dkeys, dvalues, dgi0, dinit, dwcat1[G:], dbcat1[G:], dw_c, dw_hh0, db_hh0, dw_ih1, db_ih1, dwcat1[:G], dbcat1[:G],
-                None, None)
+                None, None, None)
 
 
 def teacher_forced_log_likelihood(dec, encoder_outputs, y, training):
@@ -182,9 +183,11 @@ def teacher_forced_log_likelihood(dec, encoder_outputs, y, training):
     ge_all = ops.LinearNT.apply(emb, cell0.weight_ih[:, :D], cell0.bias_ih)                    # embedding half of cell 0's input
     p = dec.rnn.layers[1].p if training else 0.0
     seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0.0 else 0
+    from . import engine
+    seed_word = engine.graph_seed_word() if p > 0.0 else None          # set while the step is being captured as a CUDA graph
     states = DecoderStates.apply(keys, values, ge_all, dec.initial_state, att.query_linear.weight, att.query_linear.bias,
                                  cell0.weight_ih[:, D:], cell0.weight_hh, cell0.bias_hh, cell1.weight_ih, cell1.bias_ih,
-                                 cell1.weight_hh, cell1.bias_hh, p, seed)
+                                 cell1.weight_hh, cell1.bias_hh, p, seed, seed_word)
     targets = y.argmax(-1).transpose(0, 1).contiguous().view(-1)                               # [U*B], symbol-major like `states`
     mean_nll, _, row_nll = ops.LinearCE.apply(states.reshape(U * B, D), dec.linear.weight, dec.linear.bias, targets)
     total = -float(U) * mean_nll                                                               # = mean_b log p(y_b | x_b)

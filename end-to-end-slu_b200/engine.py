@@ -97,6 +97,8 @@ def _drop_mask(shape, p, training, device):
     if not training or p <= 0.0:
         return None
     seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    if _graph_seed_word is not None:                 # the step is being captured as a CUDA graph: see graphed_train_step
+        return (float(p), seed, _graph_seed_word)
     if MASK_TENSORS:
         mask = torch.empty(shape, device=device, dtype=torch.float32)
         _lib.call("slu_dropout_mask_gru", _lib.ptr(mask), shape[0], shape[1], float(p), seed, _lib.stream())
@@ -215,3 +217,127 @@ def intent_loss_acc(model, x, y_intent):
     out = _run_rnns(model.pretrained_model.compute_features(x), model._intent_rnns, model.training)
     loss, acc, _ = ops.IntentHead.apply(out, lin.weight, lin.bias, y_intent, slots)
     return loss, acc
+
+
+# ---- the SLU train step as two CUDA graphs (forward, backward) ------------------------------------------------------------------
+# A train step at these sizes is ~55 kernel launches for ~2.8 ms of GPU work (600+ launches for the seq2seq decoder): close to
+# host-bound, and the reference's Trainer reads the loss back every step (training.py:99-100), so the host cannot run ahead.
+# When the same training forward (shapes, trainable set, parameter addresses) has been seen twice, its third occurrence is
+# CAPTURED: graph F = seed word advance + forward (-> static loss / acc), graph B = the backward pass of that loss given a
+# static dL/dloss (torch.autograd.grad inside the capture: the gradients are the arena views the kernels write).  From then
+# on `Model.forward` = copy the batch into the static input buffers + replay F; `loss.backward()` = copy dL/dloss + replay B +
+# hand the static gradient tensors to the parameters.  The Trainer is unchanged; the optimizer step and the data-parallel
+# all-reduce stay outside the graphs.  Dropout seeds are frozen into a graph as by-value arguments, so the kernels XOR them with
+# a device word that graph F advances on every replay (slu_seed_advance).  SLU_STEP_GRAPH=0 disables all of this.
+STEP_GRAPH = os.environ.get("SLU_STEP_GRAPH", "1") != "0"
+GRAPH_WARMUP = 2                    # eager occurrences of a key before it is captured
+GRAPH_CACHE = 3                     # captured steps kept per model (least recently used goes)
+_graph_seed_word = None             # set while a step is being captured: _drop_mask hands it to the kernels
+
+
+def graph_seed_word():
+    return _graph_seed_word
+
+
+class _GraphedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dummy, runner):
+        ctx.runner, ctx.epoch = runner, runner.epoch
+        acc = runner.acc.clone()
+        ctx.mark_non_differentiable(acc)
+        return runner.loss.clone(), acc
+
+    @staticmethod
+    def backward(ctx, g_loss, g_acc):
+        r = ctx.runner
+        if ctx.epoch != r.epoch:
+            raise RuntimeError("slu_b200: backward through a graphed train step whose buffers a later forward has already reused "
+                               "(call backward before the next forward, or set SLU_STEP_GRAPH=0)")
+        r.g_in.copy_(g_loss.reshape(r.g_in.shape))
+        r.bwd.replay()
+        _lib.stats["calls"] += r.n_bwd
+        for p, g in r.grads:
+            p.grad = g if p.grad is None else p.grad + g
+        return None, None
+
+
+def grads_arena_of(pairs):
+    for _, g in pairs:
+        a = grads.find(g)
+        if a is not None:
+            return grads.pin(a)
+    return None
+
+
+class _StepGraph:
+    def __init__(self, model, x, y, eager):
+        dev = next(model.parameters()).device
+        self.sx = torch.empty(tuple(x.shape), device=dev, dtype=torch.float32)
+        self.sy = torch.empty(tuple(y.shape), device=dev, dtype=y.dtype)
+        self.sx.copy_(x); self.sy.copy_(y)
+        self.seed_word = torch.randint(0, 2 ** 62, (1,)).to(dev)
+        self.g_in = torch.ones((), device=dev, dtype=torch.float32)
+        self.dummy = torch.zeros((), device=dev, requires_grad=True)
+        self.epoch = 0
+        params = [p for p in model.parameters() if p.requires_grad]
+        saved = [(p, p.grad) for p in params]
+        global _graph_seed_word
+        torch.cuda.synchronize()
+        self.fwd, self.bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        c0 = _lib.stats["calls"]
+        try:
+            _graph_seed_word = self.seed_word
+            with torch.cuda.graph(self.fwd, capture_error_mode="thread_local"):
+                _lib.call("slu_seed_advance", self.seed_word.data_ptr(), _lib.stream())
+                loss, acc = eager(self.sx, self.sy)
+            c1 = _lib.stats["calls"]
+            with torch.cuda.graph(self.bwd, pool=self.fwd.pool(), capture_error_mode="thread_local"):
+                grads = torch.autograd.grad((loss,), params, (self.g_in.reshape(loss.shape),), allow_unused=True)
+        finally:
+            _graph_seed_word = None
+        self.n_fwd, self.n_bwd = c1 - c0, _lib.stats["calls"] - c1
+        _lib.stats["calls"] = c0                     # nothing ran during capture
+        self.loss, self.acc = loss.detach(), acc.detach().to(dev) if not acc.is_cuda else acc.detach()
+        self.grads = [(p, g) for p, g in zip(params, grads) if g is not None]
+        # the arena the captured backward writes into lives as long as this graph: keep it findable for dp.py's in-place all-reduce
+        self.arena = grads_arena_of(self.grads)
+        for p, g in saved:
+            p.grad = g
+
+    def run(self, x, y):
+        self.sx.copy_(x, non_blocking=True)
+        self.sy.copy_(y, non_blocking=True)
+        self.epoch += 1
+        self.fwd.replay()
+        _lib.stats["calls"] += self.n_fwd
+        return _GraphedLoss.apply(self.dummy, self)
+
+
+def graphed_train_step(model, x, y, eager):
+    """Model.forward's training path on CUDA: replay the captured step when there is one for this (shapes, trainable set,
+    parameter addresses), count occurrences / capture otherwise.  Returns (loss, acc) or None = run `eager` yourself."""
+    if not STEP_GRAPH or _lib._prof is not None or torch.cuda.is_current_stream_capturing():
+        return None
+    params = list(model.parameters())
+    if any(p.requires_grad and p.grad is not None for p in params):
+        return None                                   # gradient accumulation across steps: stock semantics, eager
+    key = (tuple(x.shape), tuple(y.shape), y.dtype, tuple(p.requires_grad for p in params), tuple(p.data_ptr() for p in params),
+           ops.GRU_IMPL, ops.SINC_IMPL, _drop_mask is _default_drop_mask)
+    cache = model.__dict__.setdefault("_step_graphs", {})
+    entry = cache.get(key)
+    if isinstance(entry, _StepGraph):
+        cache[key] = cache.pop(key)                   # most recently used last
+        return entry.run(x, y)
+    if not key[-1]:
+        return None                                   # a test supplies explicit mask tensors: eager only
+    seen = (entry or 0) + 1
+    if seen <= GRAPH_WARMUP:
+        cache[key] = seen
+        for k in [k for k, v in cache.items() if not isinstance(v, _StepGraph)][:-8]:
+            del cache[k]                              # bound the bookkeeping of one-off shapes
+        return None
+    graphs = [k for k, v in cache.items() if isinstance(v, _StepGraph)]
+    for k in graphs[:max(0, len(graphs) - GRAPH_CACHE + 1)]:
+        del cache[k]
+    runner = cache[key] = _StepGraph(model, x, y, eager)
+    return runner.run(x, y)

@@ -99,10 +99,23 @@ def current():
     return _current
 
 
+_pinned = []          # arenas of captured CUDA-graph steps (engine._StepGraph): static buffers that outlive their forward pass
+
+
+def pin(arena):
+    if arena is not None and arena not in _pinned:
+        _pinned.append(arena)
+        del _pinned[:-16]
+    return arena
+
+
 def find(t):
     """The live arena whose buffer `t` is a view of, or None."""
     for ref in reversed(_recent):
         a = ref()
         if a is not None and a.owns(t):
+            return a
+    for a in reversed(_pinned):
+        if a.owns(t):
             return a
     return None

@@ -288,7 +288,8 @@ class BiGRU(torch.autograd.Function):
     """Bidirectional single-layer GRU (H=128, h0=0) + Dropout + Downsample(avg 2 | none 1).
     Reference: nn.GRU at models.py:232/262/686, RNNSelect :138-149, Dropout :246, Downsample :26-46.
     x [B,T,I] -> [B, ceil(T/ds), 256].  `mask`: None (eval / p = 0), an explicit keep-mask tensor [B,T,256] (already scaled by
-    1/(1-p)), or a (p, seed) pair = the kernels generate the canonical Philox mask in registers, forward and backward."""
+    1/(1-p)), or a (p, seed[, seed_word]) tuple = the kernels generate the canonical Philox mask in registers, forward and
+    backward (seed_word: an int64 device tensor XOR-ed into the seed at run time, for CUDA-graph replays)."""
 
     @staticmethod
     def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, mask, ds, packed=None, before_recurrence=None, imgs=None):
@@ -305,7 +306,8 @@ class BiGRU(torch.autograd.Function):
         img_nt, img_nn = imgs if imgs is not None else (None, None)
         gx = linear_nt(x.view(B * T, I), w_ih_cat, b_ih_cat, img_nt)            # x-projection, both directions
         T2 = (T + ds - 1) // ds
-        drop_p, drop_seed = (float(mask[0]), int(mask[1])) if isinstance(mask, tuple) else (0.0, 0)
+        drop_p, drop_seed, seed_dev = (float(mask[0]), int(mask[1]), mask[2] if len(mask) > 2 else None) if isinstance(mask, tuple) \
+            else (0.0, 0, None)
         if isinstance(mask, tuple):
             mask = None
         y_full = torch.empty(B, T, 256, device=dev, dtype=torch.float32)
@@ -315,11 +317,11 @@ class BiGRU(torch.autograd.Function):
         if before_recurrence is not None:       # e.g. join the side stream that wrote the dropout masks (the x-projection is queued)
             before_recurrence()
         _lib.call("slu_gru_fwd_" + GRU_IMPL, _lib.ptr(gx), _lib.ptr(w_hh_cat), _lib.ptr(b_hh_cat), _lib.ptr(mask), drop_p, drop_seed,
-                  B, T, ds, _lib.ptr(y_full), _lib.ptr(y_out), _lib.ptr(stash), _lib.stream())
+                  _lib.ptr(seed_dev), B, T, ds, _lib.ptr(y_full), _lib.ptr(y_out), _lib.ptr(stash), _lib.stream())
         if need:
             ctx.save_for_backward(x, w_ih_cat, w_hh_cat, y_full, stash, mask)
             ctx.ds = ds
-            ctx.drop = (drop_p, drop_seed)
+            ctx.drop = (drop_p, drop_seed, seed_dev)
             ctx.img_nn = img_nn
             # the packed views alias the Parameters' storage without sharing their version counters: remember the versions so
             # that an in-place update between this forward and its backward is detected (stock autograd would raise too)
@@ -332,7 +334,7 @@ class BiGRU(torch.autograd.Function):
     def backward(ctx, gy):
         x, w_ih_cat, w_hh_cat, y_full, stash, mask = ctx.saved_tensors
         ds = ctx.ds
-        drop_p, drop_seed = ctx.drop
+        drop_p, drop_seed, seed_dev = ctx.drop
         for q, v in ctx.param_versions:
             if q._version != v:
                 raise RuntimeError("slu_b200: a GRU parameter needed for gradient computation has been modified by an inplace "
@@ -360,7 +362,7 @@ class BiGRU(torch.autograd.Function):
             img = None
             if ni[0]:
                 img = ctx.img_nn if ctx.img_nn is not None else presplit(w_ih_cat, *_form_nn(w_ih_cat))
-            _lib.call("slu_bigru_bwd_tc", _lib.ptr(gy), _lib.ptr(mask), drop_p, drop_seed, _lib.ptr(y_full), _lib.ptr(stash),
+            _lib.call("slu_bigru_bwd_tc", _lib.ptr(gy), _lib.ptr(mask), drop_p, drop_seed, _lib.ptr(seed_dev), _lib.ptr(y_full), _lib.ptr(stash),
                       _lib.ptr(w_hh_cat), _lib.ptr(x),
                       I, None if img is None else img.data_ptr(), B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn),
                       db_ih.data_ptr() if wg else None, db_hh.data_ptr() if wg else None,
@@ -368,7 +370,7 @@ class BiGRU(torch.autograd.Function):
                       _lib.stream())
             _lib.stats["calls"] += (3 if wg else 0) + (1 if ni[0] else 0)          # kernels launched beyond the first
         else:
-            _lib.call("slu_gru_bwd_" + GRU_IMPL, _lib.ptr(gy), _lib.ptr(mask), drop_p, drop_seed, _lib.ptr(y_full), _lib.ptr(stash),
+            _lib.call("slu_gru_bwd_" + GRU_IMPL, _lib.ptr(gy), _lib.ptr(mask), drop_p, drop_seed, _lib.ptr(seed_dev), _lib.ptr(y_full), _lib.ptr(stash),
                       _lib.ptr(w_hh_cat), B, T, ds, _lib.ptr(dgx), _lib.ptr(dhn), db_ih.data_ptr() if wg else None, db_hh.data_ptr() if wg else None,
                       _lib.stream())
             if wg:

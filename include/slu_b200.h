@@ -62,25 +62,29 @@ int slu_sincconv_bwd_jac_tc(const float* x, const float* gy, const uint8_t* rout
  *   drop_mask [B][T][256] keep-mask scaled by 1/(1-p), or NULL.  With drop_mask == NULL and drop_p > 0 the kernels generate the
  *             canonical Philox mask of (drop_p, drop_seed) in registers (csrc/philox.cuh; slu_dropout_mask_gru writes the same
  *             mask out as a tensor): no mask tensor exists in HBM and the backward kernel regenerates it.  drop_p = 0: no dropout.
+ *             drop_seed_dev (may be NULL): one device word XOR-ed into drop_seed at run time -- a train step captured as a CUDA
+ *             graph freezes its by-value arguments, slu_seed_advance(word) as the graph's first node gives every replay new masks.
  *   ds    1 = Downsample("none",1), 2 = Downsample("avg",2) (ceil mode: an odd tail frame is kept as is)
  *   y_full [B][T][256] raw hidden states (col = d*128 + j);  y_out [B][ceil(T/ds)][256]
  *   stash [B][T][1024] (r, z, n, W_hn h + b_hn per direction) for the backward pass, or NULL for inference. */
 int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, float drop_p,
-                     unsigned long long drop_seed, int B, int T, int ds, float* y_full, float* y_out, float* stash, void* stream);
+                     unsigned long long drop_seed, const unsigned long long* drop_seed_dev, int B, int T, int ds, float* y_full,
+                     float* y_out, float* stash, void* stream);
 /* Backward through time -- replaces _cudnn_rnn_backward.  Emits dgx[B][T][768] (gradient wrt gx) and
  * dhn[B][T][256] (gradient wrt the n-gate's recurrent pre-activation); the weight/input gradients are dense
  * GEMMs over these.  db_ih[2][384] and db_hh[2][384] (the bias parameters' own layout; both NULL or both caller-zeroed)
  * ACCUMULATE the bias gradients: b_ih <- sums over (b,t) of (dr, dz, dn), b_hh <- (dr, dz, dhn). */
-int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, float drop_p, unsigned long long drop_seed, const float* y_full,
-                     const float* stash, const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh,
+int slu_gru_bwd_simt(const float* dy_out, const float* drop_mask, float drop_p, unsigned long long drop_seed,
+                     const unsigned long long* drop_seed_dev, const float* y_full, const float* stash, const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh,
                      void* stream);
 
 /* Same contracts as slu_gru_fwd_simt / slu_gru_bwd_simt, executed on tcgen05 tensor cores: W_hh (bf16 hi+lo) stationary
  * in tensor memory, h / dG as the shared-memory B operand, 3-pass bf16 split with fp32 accumulation in TMEM. */
 int slu_gru_fwd_tc(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, float drop_p,
-                   unsigned long long drop_seed, int B, int T, int ds, float* y_full, float* y_out, float* stash, void* stream);
-int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, float drop_p, unsigned long long drop_seed, const float* y_full,
-                   const float* stash, const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh,
+                   unsigned long long drop_seed, const unsigned long long* drop_seed_dev, int B, int T, int ds, float* y_full,
+                   float* y_out, float* stash, void* stream);
+int slu_gru_bwd_tc(const float* dy_out, const float* drop_mask, float drop_p, unsigned long long drop_seed,
+                   const unsigned long long* drop_seed_dev, const float* y_full, const float* stash, const float* w_hh, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh,
                    void* stream);
 
 /* Operand format of the tcgen05 recurrence:
@@ -116,7 +120,8 @@ int slu_intent_head_bwd(const float* gloss, const float* feats, const float* W, 
  * overlap != 0).  x [B][T][I] = the layer input; w_ih_nn_img = slu_presplit_bf16 image of W_ih [768][I] read as the [K=768][N=I]
  * operand (NULL with dx == NULL: no input gradient); dw_ih [768][I] and dw_hh [2][384][128] accumulate (NULL, NULL: no weight
  * gradients); dgx [B][T][768] and dhn [B][T][256] are caller-provided scratch that holds the pre-activation gradients. */
-int slu_bigru_bwd_tc(const float* gy, const float* drop_mask, float drop_p, unsigned long long drop_seed, const float* y_full,
+int slu_bigru_bwd_tc(const float* gy, const float* drop_mask, float drop_p, unsigned long long drop_seed,
+                     const unsigned long long* drop_seed_dev, const float* y_full,
                      const float* stash, const float* w_hh, const float* x,
                      int I, const void* w_ih_nn_img, int B, int T, int ds, float* dgx, float* dhn, float* db_ih, float* db_hh,
                      float* dw_ih, float* dw_hh, float* dx, int overlap, void* stream);
@@ -211,11 +216,11 @@ int slu_attn_step_fwd(const float* q, long ldq, const float* keys, const float* 
 int slu_attn_step_bwd(const float* dctx, const float* w, const float* q, long ldq, const float* keys, const float* values, int B, int T,
                       int K, int V, float inv_scale, float* dq, long lddq, float* dkeys, float* dvalues, void* stream);
 int slu_grucell_fwd(const float* gi_a, long lda, const float* gi_b, long ldb, const float* gh, long ldh, const float* hprev,
-                    const float* h0, int B, int D, float drop_p, unsigned long long drop_seed, int step, float* h, float* stash,
-                    float* dropped, void* stream);
+                    const float* h0, int B, int D, float drop_p, unsigned long long drop_seed, const unsigned long long* drop_seed_dev,
+                    int step, float* h, float* stash, float* dropped, void* stream);
 int slu_grucell_bwd(const float* da, const float* db, const float* dc, const float* stash, const float* hprev, const float* h0, int B,
-                    int D, float drop_p, unsigned long long drop_seed, int step, float* dgi, long ldgi, float* dgh, long ldgh,
-                    float* dh_direct, void* stream);
+                    int D, float drop_p, unsigned long long drop_seed, const unsigned long long* drop_seed_dev, int step, float* dgi,
+                    long ldgi, float* dgh, long ldgh, float* dh_direct, void* stream);
 
 /* ---- optimizer step / gradient bucket (reference training.py:19, 64-66, 96-98: torch.optim.Adam, zero_grad/backward/step) ----
  * slu_adam_multi: one Adam step over `n` parameter tensors (fp32 or fp64, any sizes) in ceil(n/64) launches; torch.optim.Adam's
@@ -230,6 +235,7 @@ struct SluAdamTensor {
   int is_f64;                                 /* 0: float, 1: double */
   int pad;
 };
+int slu_seed_advance(unsigned long long* state, void* stream);   /* state[0] <- LCG(state[0]): see drop_seed_dev above */
 int slu_adam_multi(const void* tensors, int n, double beta1, double beta2, float eps, float weight_decay, void* stream);
 /* fp64 gradients inside an fp32 all-reduce bucket: split into (hi, lo) floats before the collective, merge after it. */
 int slu_f64_hilo_split(const double* src, float* hi, float* lo, int n, void* stream);

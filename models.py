@@ -395,6 +395,15 @@ class Model(torch.nn.Module):
     def forward(self, x, y_intent):
         """x (B,T); y_intent (B, n_slots) long [or (B,U,|S|) one-hot for seq2seq].  Returns (loss, acc)."""
         on_gpu = self.pretrained_model._on_gpu()
+        if on_gpu and self.training and torch.is_grad_enabled():
+            # the training step as captured CUDA graphs once its shape has been seen a few times (engine.graphed_train_step)
+            out = _engine().graphed_train_step(self, x, y_intent, self._forward_eager)
+            if out is not None:
+                return out
+        return self._forward_eager(x, y_intent)
+
+    def _forward_eager(self, x, y_intent):
+        on_gpu = self.pretrained_model._on_gpu()
         if on_gpu:
             y_intent = y_intent.cuda()
         if self.seq2seq:

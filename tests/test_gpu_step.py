@@ -126,7 +126,7 @@ def test_predict_intents_logits_are_differentiable_on_gpu(pkg):
 def test_gru_size_limit_is_a_readable_error(pkg):
     gx = torch.empty(1, device="cuda")
     with pytest.raises(RuntimeError, match="split the batch"):
-        pkg._lib.call("slu_gru_fwd_tc", gx.data_ptr(), gx.data_ptr(), gx.data_ptr(), None, 0.0, 0, 4096, 1024, 1, gx.data_ptr(),
+        pkg._lib.call("slu_gru_fwd_tc", gx.data_ptr(), gx.data_ptr(), gx.data_ptr(), None, 0.0, 0, None, 4096, 1024, 1, gx.data_ptr(),
                       gx.data_ptr(), None, pkg._lib.stream())
 
 
@@ -145,3 +145,87 @@ def test_prefetcher_keeps_pinned_sources_alive_until_the_copy_has_run(pkg):
             a, b = seen.pop(0)
             assert a.min().item() == a.max().item() == float(b[0, 0].item())
     assert not pf._keep
+
+
+def _train_model(cfg_over=None, seq2seq=False):
+    from util import make_config
+    if seq2seq:
+        cfg = make_config("seq2seq")
+        cfg.Sy_intent = ["<sos>"] + list("abcdefghij {}:'\",") + ["<eos>"]
+    else:
+        cfg = make_config(**(cfg_over or {}))
+    torch.manual_seed(0)
+    m = models.Model(cfg).train()
+    for q in m.parameters():
+        q.requires_grad = True
+    return m, cfg
+
+
+@pytest.mark.parametrize("seq2seq", [False, True])
+def test_graphed_train_step_equals_the_eager_step(pkg, monkeypatch, seq2seq):
+    """The training forward/backward captured as two CUDA graphs (engine.graphed_train_step) against eager execution, dropout
+    probabilities set to 0 so both are deterministic: same loss, same gradients for every parameter, for new inputs on every
+    replay, with the unchanged zero_grad / backward / optimizer.step sequence of the Trainer; dL/dloss != 1 is honoured."""
+    eng = pkg.engine
+    over = dict(phone_rnn_drop=[0.0, 0.0], word_rnn_drop=[0.0, 0.0], intent_rnn_drop=[0.0])
+    m, cfg = _train_model(over, seq2seq)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    rs = np.random.RandomState(0)
+    S = len(cfg.Sy_intent) if seq2seq else 0
+
+    def batch(i):
+        x = torch.from_numpy((0.1 * rs.standard_normal((6, 8000))).astype(np.float32))
+        if seq2seq:
+            idx = rs.randint(1, S - 1, size=(6, 7)); idx[:, 0] = 0; idx[:, -1] = S - 1
+            return x, torch.nn.functional.one_hot(torch.from_numpy(idx), S).float()
+        return x, torch.from_numpy(np.stack([rs.randint(0, v, size=6) for v in (6, 14, 4)], 1))
+    batches = [batch(i) for i in range(6)]
+
+    def run(graph):
+        monkeypatch.setattr(eng, "STEP_GRAPH", graph)
+        m.__dict__.pop("_step_graphs", None)
+        out = []
+        for i, (x, y) in enumerate(batches):
+            m.zero_grad()
+            loss, _ = m(x, y)
+            (loss * (2.0 if i == 4 else 1.0)).backward()
+            out.append((loss.item(), {k: q.grad.detach().clone() for k, q in m.named_parameters() if q.grad is not None}))
+        return out
+    eager = run(False)
+    graphed = run(True)
+    assert any(isinstance(v, eng._StepGraph) for v in m._step_graphs.values())          # the third occurrence was captured
+    for (le, ge), (lg, gg) in zip(eager, graphed):
+        assert abs(le - lg) < 1e-6 * abs(le)
+        assert set(ge) == set(gg)
+        for k in ge:
+            assert ge[k].dtype == gg[k].dtype and rel_err(gg[k], ge[k]) < 2e-5, k
+    # stale backward is refused, gradient accumulation falls back to eager semantics
+    l_a, _ = m(*batches[0]); l_b, _ = m(*batches[1])
+    with pytest.raises(RuntimeError, match="later forward"):
+        l_a.backward()
+    m.zero_grad()
+    l1, _ = m(*batches[0]); l1.backward()
+    l2, _ = m(*batches[0]); l2.backward()                      # .grad is not None -> eager, accumulates
+    for k, q in m.named_parameters():
+        if q.grad is not None:
+            assert rel_err(q.grad, 2 * eager[0][1][k]) < 2e-5, k
+
+
+def test_graphed_train_step_draws_new_dropout_masks_every_replay(pkg):
+    m, _ = _train_model()
+    x, y = R.synthetic_batch(6, 8000, seed=3)
+    torch.manual_seed(1)
+    losses = []
+    for i in range(7):
+        m.zero_grad()
+        loss, _ = m(x, y)
+        loss.backward()
+        losses.append(loss.item())
+    assert any(isinstance(v, pkg.engine._StepGraph) for v in m._step_graphs.values())
+    assert len(set(losses[2:])) == len(losses[2:])              # same input, different masks on every replay
+    m.eval()
+    with torch.no_grad():
+        l_eval = m(x, y)[0].item()
+    assert abs(np.mean(losses) - l_eval) < 0.5 * abs(l_eval)    # and still the same model
