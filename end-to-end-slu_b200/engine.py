@@ -279,7 +279,15 @@ class _StepGraph:
         self.g_in = torch.ones((), device=dev, dtype=torch.float32)
         self.dummy = torch.zeros((), device=dev, requires_grad=True)
         self.epoch = 0
-        params = [p for p in model.parameters() if p.requires_grad]
+        # The capture runs on torch's capture stream, but a Parameter's AccumulateGrad node remembers the stream it was created on
+        # (the default stream, if anything of an earlier eager step -- e.g. the loss the Trainer still holds -- keeps it alive), and
+        # the autograd engine would then try to make that stream wait for the capturing one.  So the captured forward runs on fresh
+        # leaf ALIASES of the parameters (same storage, new autograd identity) swapped into the module tree for the duration.
+        from torch.nn.utils.stateless import _reparametrize_module
+        named = list(model.named_parameters())
+        alias = {n: p.detach().requires_grad_(p.requires_grad) for n, p in named}
+        params = [p for _, p in named if p.requires_grad]
+        leaves = [alias[n] for n, p in named if p.requires_grad]
         saved = [(p, p.grad) for p in params]
         global _graph_seed_word
         torch.cuda.synchronize()
@@ -289,10 +297,11 @@ class _StepGraph:
             _graph_seed_word = self.seed_word
             with torch.cuda.graph(self.fwd, capture_error_mode="thread_local"):
                 _lib.call("slu_seed_advance", self.seed_word.data_ptr(), _lib.stream())
-                loss, acc = eager(self.sx, self.sy)
+                with _reparametrize_module(model, alias):
+                    loss, acc = eager(self.sx, self.sy)
             c1 = _lib.stats["calls"]
             with torch.cuda.graph(self.bwd, pool=self.fwd.pool(), capture_error_mode="thread_local"):
-                grads = torch.autograd.grad((loss,), params, (self.g_in.reshape(loss.shape),), allow_unused=True)
+                grads = torch.autograd.grad((loss,), leaves, (self.g_in.reshape(loss.shape),), allow_unused=True)
         finally:
             _graph_seed_word = None
         self.n_fwd, self.n_bwd = c1 - c0, _lib.stats["calls"] - c1

@@ -187,6 +187,7 @@ def test_graphed_train_step_equals_the_eager_step(pkg, monkeypatch, seq2seq):
         monkeypatch.setattr(eng, "STEP_GRAPH", graph)
         m.__dict__.pop("_step_graphs", None)
         out = []
+        loss = None                                    # like the Trainer, the previous step's loss is still referenced during the next forward
         for i, (x, y) in enumerate(batches):
             m.zero_grad()
             loss, _ = m(x, y)
@@ -202,6 +203,7 @@ def test_graphed_train_step_equals_the_eager_step(pkg, monkeypatch, seq2seq):
         for k in ge:
             assert ge[k].dtype == gg[k].dtype and rel_err(gg[k], ge[k]) < 2e-5, k
     # stale backward is refused, gradient accumulation falls back to eager semantics
+    m.zero_grad()
     l_a, _ = m(*batches[0]); l_b, _ = m(*batches[1])
     with pytest.raises(RuntimeError, match="later forward"):
         l_a.backward()
