@@ -247,6 +247,214 @@ sincconv_fwd_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// persistent, warp-specialised variant of the kernel above (same math, same operand images)
+// ---------------------------------------------------------------------------------------------------------------
+// One CTA per SM walks the 128-frame tiles (tile = blockIdx.x, + gridDim.x, ...).  14 warps:
+//   warps 0-7   STAGERS   waveform slice -> bf16 hi/lo image, two image slots: tile i+1 is staged while tile i is multiplied
+//   warp  8     MMA       six taps x (5 K-steps x 3 split passes) into one of TWO TMEM accumulators
+//   warp  9     BANK      streams the pre-split filter taps from L2 through a 4-slot TMA ring (tap g of the CTA -> slot g & 3)
+//   warps 10-13 EPILOGUE  tcgen05.ld of accumulator i (abs / max-pool / route stores, or the routed-gradient dot product) while
+//                         the MMAs of tile i+1 run into the other accumulator
+// so per tile the SM pays max(staging, MMA, epilogue) instead of their sum; the MMA phase (78 M128 x N80 x K16 instructions,
+// ~3 300 cycles) is the floor.  All hand-offs are mbarriers (bounded spins: a protocol bug traps instead of hanging).
+constexpr int P_STAGE_WARPS = 8, P_WARPS = 14, P_THREADS = P_WARPS * 32;
+constexpr int P_BANK_SLOTS = 4;
+constexpr uint32_t P_IMG = 2 * X_PART;                                  // one image slot (hi, lo)
+constexpr uint32_t P_BANK = 2 * W_PART;                                 // one bank slot (hi, lo)
+constexpr uint32_t P_TR = 4 * 32 * 17 * 4;                              // epilogue transpose buffers
+constexpr uint32_t P_SMEM = 2 * P_IMG + P_BANK_SLOTS * P_BANK + P_TR;   // 200 064 B
+
+template <bool GRAD>
+__global__ void __launch_bounds__(P_THREADS, 1)
+sincconv_tc_persistent_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wimg, int T, int L0, int L1, int tiles_per_utt,
+                              int n_tiles, float* __restrict__ out, uint8_t* __restrict__ route, const float* __restrict__ gy_in,
+                              double* __restrict__ dsum) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t img_full[2], img_empty[2], acc_full[2], acc_empty[2], bank_full[P_BANK_SLOTS], bank_empty[P_BANK_SLOTS];
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = warp_idx_uniform(), lane = tid & 31;
+  uint8_t* bank_ring = smem + 2 * P_IMG;
+  float* tr_all = reinterpret_cast<float*>(smem + 2 * P_IMG + P_BANK_SLOTS * P_BANK);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&img_full[s], P_STAGE_WARPS); mbar_init(&img_empty[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4);
+    }
+    for (int s = 0; s < P_BANK_SLOTS; ++s) { mbar_init(&bank_full[s], 1); mbar_init(&bank_empty[s], 1); }
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_base, 256);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  const int n_mine = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_img = SLU_NFILT * (int)gridDim.y;                         // rows of the (stacked) bank image; bank = blockIdx.y
+
+  if (warp < P_STAGE_WARPS) {
+    // ---- stagers ------------------------------------------------------------------------------------------------------
+    for (int it = 0; it < n_mine; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x, slot = it & 1;
+      const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TF;
+      if (it >= 2) mbar_wait(&img_empty[slot], (uint32_t)(((it >> 1) - 1) & 1));      // the MMAs of tile it-2 have read this slot
+      uint8_t* hi = smem + slot * P_IMG;
+      stage_wave_image(hi, hi + X_PART, x + (size_t)b * T, t0, T, tid);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&img_full[slot]);
+    }
+  } else if (warp == P_STAGE_WARPS) {
+    // ---- MMA issuer ---------------------------------------------------------------------------------------------------
+    const uint32_t idesc = idesc_bf16(128, SLU_NFILT, false, false);
+    for (int it = 0; it < n_mine; ++it) {
+      const int slot = it & 1;
+      mbar_wait(&img_full[slot], (uint32_t)((it >> 1) & 1));
+      if (it >= 2) mbar_wait(&acc_empty[slot], (uint32_t)(((it >> 1) - 1) & 1));      // the epilogue has drained this accumulator
+      fence_after_sync();
+      const uint32_t x_hi = smem_u32(smem + slot * P_IMG), x_lo = x_hi + X_PART;
+      const uint32_t dacc = tmem + (uint32_t)slot * 128u;
+      for (int tap = 0; tap < 6; ++tap) {
+        const int g = it * 6 + tap, bs = g & (P_BANK_SLOTS - 1);
+        mbar_wait(&bank_full[bs], (uint32_t)((g / P_BANK_SLOTS) & 1));
+        fence_after_sync();
+        if (elect_one()) {
+          const uint32_t w_hi = smem_u32(bank_ring + bs * P_BANK), w_lo = w_hi + W_PART;
+          const uint64_t ah0 = smem_desc(x_hi + tap * 16, LBO_X, 128), al0 = smem_desc(x_lo + tap * 16, LBO_X, 128);
+          const uint64_t bh0 = smem_desc(w_hi, LBO_W, 128), bl0 = smem_desc(w_lo, LBO_W, 128);
+          const int nk = tap == 5 ? 1 : SLU_STRIDE / 16;
+#pragma unroll 1
+          for (int kk = 0; kk < nk; ++kk) {
+            const uint64_t ah = desc_advance(ah0, kk * 2 * LBO_X), al = desc_advance(al0, kk * 2 * LBO_X);
+            const uint64_t bh = desc_advance(bh0, kk * 2 * LBO_W), bl = desc_advance(bl0, kk * 2 * LBO_W);
+            mma_bf16(dacc, ah, bh, idesc, (tap | kk) ? 1u : 0u);
+            mma_bf16(dacc, ah, bl, idesc, 1u);
+            mma_bf16(dacc, al, bh, idesc, 1u);
+          }
+          mma_commit(&bank_empty[bs]);
+          if (tap == 5) { mma_commit(&img_empty[slot]); mma_commit(&acc_full[slot]); }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == P_STAGE_WARPS + 1) {
+    // ---- filter-bank loader (TMA ring) --------------------------------------------------------------------------------
+    for (int g = 0; g < n_mine * 6; ++g) {
+      const int bs = g & (P_BANK_SLOTS - 1), tap = g % 6;
+      if (g >= P_BANK_SLOTS) mbar_wait(&bank_empty[bs], (uint32_t)(((g / P_BANK_SLOTS) - 1) & 1));
+      if (elect_one()) {
+        const int nch = tap == 5 ? 2 : KC;
+        uint8_t* w_hi = bank_ring + bs * P_BANK;
+        mbar_arrive_expect_tx(&bank_full[bs], (uint32_t)(2 * nch * SLU_NFILT * 16));
+        for (int part = 0; part < 2; ++part)
+          for (int kc = 0; kc < nch; ++kc) {
+            const size_t e = ((((size_t)part * 6 + tap) * WKC + kc) * n_img + (size_t)blockIdx.y * SLU_NFILT) * 8;
+            tma_load_1d(w_hi + part * W_PART + kc * LBO_W, wimg + e, SLU_NFILT * 16, &bank_full[bs]);
+          }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue -----------------------------------------------------------------------------------------------------
+    const int q = warp & 3;                                             // TMEM lane quarter of this warp
+    float* tr = tr_all + (warp - P_STAGE_WARPS - 2) * (32 * 17);
+    float gacc[GRAD ? SLU_NFILT : 1];                                   // GRAD: per-thread (= per frame row) sums over its tiles
+#pragma unroll
+    for (int i = 0; i < (GRAD ? SLU_NFILT : 1); ++i) gacc[i] = 0.f;
+    for (int it = 0; it < n_mine; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x, slot = it & 1;
+      const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TF;
+      mbar_wait(&acc_full[slot], (uint32_t)((it >> 1) & 1));
+      fence_after_sync();
+      const uint32_t acc = tmem + (uint32_t)slot * 128u + ((uint32_t)(q * 32) << 16);
+      if (GRAD) {
+        const int t = t0 + q * 32 + lane;
+        const bool t_on = t < L0;
+        const size_t o = ((size_t)b * L1 + (t_on ? (t >> 1) : 0)) * SLU_NFILT;
+#pragma unroll
+        for (int c0 = 0; c0 < SLU_NFILT; c0 += 16) {
+          float v[16];
+          tmem_ld16(acc + c0, v);
+          tmem_ld_wait();
+          uint4 rt = make_uint4(0, 0, 0, 0);
+          float4 g4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t_on) {
+            rt = __ldg(reinterpret_cast<const uint4*>(route + o + c0));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g4[i] = __ldg(reinterpret_cast<const float4*>(gy_in + o + c0) + i);
+          }
+          const uint32_t rw[4] = {rt.x, rt.y, rt.z, rt.w};
+          const float gv[16] = {g4[0].x, g4[0].y, g4[0].z, g4[0].w, g4[1].x, g4[1].y, g4[1].z, g4[1].w,
+                                g4[2].x, g4[2].y, g4[2].z, g4[2].w, g4[3].x, g4[3].y, g4[3].z, g4[3].w};
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t rb = (rw[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            const bool take = t_on && ((rb & 1u) == (uint32_t)(t & 1)) && !(rb & 4u);
+            gacc[c0 + i] += take ? ((rb & 2u) ? -gv[i] : gv[i]) * v[i] : 0.f;
+          }
+        }
+      } else {
+        for (int c0 = 0; c0 < SLU_NFILT; c0 += 16) {
+          float v[16];
+          tmem_ld16(acc + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) tr[lane * 17 + i] = v[i];
+          __syncwarp();
+          const int jp = lane >> 1, cb = (lane & 1) * 8;                // lane -> (frame pair jp of this warp's 16 pairs, 8 of the 16 columns)
+          const int t = t0 + q * 32 + 2 * jp;
+          if (t < L0) {
+            const bool has1 = t + 1 < L0;
+            const size_t o = ((size_t)b * L1 + (t >> 1)) * SLU_NFILT + c0 + cb;
+            float r_out[8]; uint8_t r_rt[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float v0 = tr[(2 * jp) * 17 + cb + i], v1 = tr[(2 * jp + 1) * 17 + cb + i];
+              const float a0 = fabsf(v0), a1 = has1 ? fabsf(v1) : -1.f;
+              const int sel = a1 > a0 ? 1 : 0;
+              const float vs = sel ? v1 : v0;
+              r_out[i] = sel ? a1 : a0;
+              r_rt[i] = (uint8_t)(sel | ((vs < 0.f) ? 2 : 0) | ((vs == 0.f) ? 4 : 0));
+            }
+            *reinterpret_cast<float4*>(out + o) = make_float4(r_out[0], r_out[1], r_out[2], r_out[3]);
+            *reinterpret_cast<float4*>(out + o + 4) = make_float4(r_out[4], r_out[5], r_out[6], r_out[7]);
+            if (route) {
+              uint2 pk;
+              pk.x = r_rt[0] | (r_rt[1] << 8) | (r_rt[2] << 16) | ((uint32_t)r_rt[3] << 24);
+              pk.y = r_rt[4] | (r_rt[5] << 8) | (r_rt[6] << 16) | ((uint32_t)r_rt[7] << 24);
+              *reinterpret_cast<uint2*>(route + o) = pk;
+            }
+          }
+          __syncwarp();
+        }
+      }
+      fence_before_sync();                                              // this thread's tcgen05.ld are done (wait::ld above)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[slot]);
+    }
+    if (GRAD) {
+      // per-filter sums over this warp's 32 frame rows, then one fp64 atomic per filter per warp
+      for (int c0 = 0; c0 < SLU_NFILT; c0 += 16) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) tr[lane * 17 + i] = gacc[c0 + i];
+        __syncwarp();
+        if (lane < 16) {
+          double s2 = 0.0;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) s2 += (double)tr[r * 17 + lane];
+          atomicAdd(dsum + blockIdx.y * SLU_NFILT + c0 + lane, s2);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // backward (filter gradient)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t SBO_G = TF * 16 + 16;                   // 2064: stride between 8-filter chunks of the routed-gradient image
@@ -377,6 +585,19 @@ sincconv_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ gy
 
 int slu_presplit_rows_cm(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream);
 
+// 1 (default): the persistent warp-specialised kernel; 0: one CTA per tile (the round-1 kernel, kept for A/B measurements).
+static int g_sinc_persistent = 1;
+extern "C" int slu_set_sinc_persistent(int on) { g_sinc_persistent = on ? 1 : 0; return 0; }
+static int sinc_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 // Forward: out[B][L1][80] = maxpool2(|conv1d(x, W, stride 80, pad 200)|), route bits for the backward pass.
 // `img` = scratch for the pre-split bank: 2*6*80*96 bf16 values.
 extern "C" int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T, float* out, uint8_t* route, void* img, void* stream) {
@@ -384,6 +605,17 @@ extern "C" int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T,
   const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
   int e = slu_presplit_rows_cm(W, SLU_NTAPS, 1, SLU_STRIDE, 6, SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // bank[c][80a + k], 0 beyond tap 400
   if (e) return e;
+  if (g_sinc_persistent) {
+    SLU_SMEM_ONCE(sincconv_tc_persistent_kernel<false>, P_SMEM);
+    const int tiles_per_utt = (L0 + TF - 1) / TF;
+    const long n_tiles = (long)B * tiles_per_utt;
+    if (n_tiles >= (1L << 31)) return SLU_ERR_TOO_LARGE;
+    const int grid = (int)(n_tiles < sinc_sm_count() ? n_tiles : sinc_sm_count());
+    sincconv_tc_persistent_kernel<false><<<grid, P_THREADS, P_SMEM, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)img, T, L0, L1, tiles_per_utt,
+                                                                                          (int)n_tiles, out, route, nullptr, nullptr);
+    SLU_CHECK_LAUNCH();
+    return 0;
+  }
   SLU_SMEM_ONCE(sincconv_fwd_tc_kernel<false>, FWD_SMEM);
   dim3 grid((L0 + TF - 1) / TF, B);
   sincconv_fwd_tc_kernel<false><<<grid, THREADS, FWD_SMEM, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)img, T, L0, L1, out, route,
@@ -401,6 +633,18 @@ extern "C" int slu_sincconv_bwd_jac_tc(const float* x, const float* gy, const ui
   const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
   int e = slu_presplit_rows_cm(J, SLU_NTAPS, 1, SLU_STRIDE, 6, 2 * SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // both banks: 160 image rows
   if (e) return e;
+  if (g_sinc_persistent) {
+    SLU_SMEM_ONCE(sincconv_tc_persistent_kernel<true>, P_SMEM);
+    const int tiles_per_utt = (L0 + TF - 1) / TF;
+    const long n_tiles = (long)B * tiles_per_utt;
+    if (n_tiles >= (1L << 31)) return SLU_ERR_TOO_LARGE;
+    const int half = sinc_sm_count() / 2;                                // the two Jacobian banks share the SMs
+    const int gx = (int)(n_tiles < half ? n_tiles : half);
+    sincconv_tc_persistent_kernel<true><<<dim3(gx, 2), P_THREADS, P_SMEM, (cudaStream_t)stream>>>(
+        x, (const __nv_bfloat16*)img, T, L0, L1, tiles_per_utt, (int)n_tiles, nullptr, const_cast<uint8_t*>(route), gy, d);
+    SLU_CHECK_LAUNCH();
+    return 0;
+  }
   SLU_SMEM_ONCE(sincconv_fwd_tc_kernel<true>, FWD_SMEM);
   dim3 grid((L0 + TF - 1) / TF, B, 2);
   sincconv_fwd_tc_kernel<true><<<grid, THREADS, FWD_SMEM, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)img, T, L0, L1, nullptr,

@@ -51,6 +51,10 @@ int slu_sincconv_bwd_tc(const float* x, const float* gy, const uint8_t* route, i
  * (slu_sinc_filters_jac) -- same tcgen05 kernel as the forward, two stacked banks, reducing epilogue.  The cancellation between
  * the direct and the max-normalisation term happens analytically inside J, so bf16 hi/lo operands keep fp32-class accuracy
  * (the dW route loses ~3 digits there).  `img` = scratch for the pre-split banks (2*6*160*96 bf16 values). */
+/* Both run as ONE persistent CTA per SM walking the 128-frame tiles with stager / MMA / filter-bank TMA / epilogue warps and two
+ * TMEM accumulators (staging of tile i+1 and the epilogue of tile i-1 overlap the MMAs of tile i); slu_set_sinc_persistent(0)
+ * selects the one-CTA-per-tile kernel instead (A/B measurements). */
+int slu_set_sinc_persistent(int on);
 int slu_sincconv_bwd_jac_tc(const float* x, const float* gy, const uint8_t* route, const float* J, int B, int T, double* d,
                             void* img, void* stream);
 

@@ -446,3 +446,35 @@ def test_canonical_dropout_mask_statistics(pkg):
     m2 = torch.empty_like(m)
     pkg._lib.call("slu_dropout_mask_gru", m2.data_ptr(), B, T, p, 43, pkg._lib.stream())
     assert abs(((m2 > 0).float() * keep).mean().item() - 0.25) < 0.01              # different seeds: independent masks
+
+
+@pytest.mark.parametrize("B,T", [(3, 12345), (300, 16000), (1, 81), (7, 64000)])
+def test_sinc_persistent_kernel_equals_the_per_tile_kernel(pkg, B, T):
+    """The persistent warp-specialised SincConv kernel (default) and the one-CTA-per-tile kernel issue the same MMAs in the same
+    order on the same operand images: outputs and route bits must be identical, the reduced cut-off gradients equal to rounding
+    (different summation order of the fp64 atomics); (300, 16000) gives every CTA several tiles and a ragged last wave."""
+    p = R.synthetic_params()
+    x = R.synthetic_batch(B, T, seed=T)[0].cuda()
+    b1 = p[R.P + "phoneme_layers.0.filt_b1"].cuda(); band = p[R.P + "phoneme_layers.0.filt_band"].cuda()
+    W = pkg.ops.sinc_filters(b1, band)
+    L1 = (((T - 1) // 80 + 1) + 1) // 2
+    gy = torch.randn(B, L1, 80, device="cuda")
+    J = torch.empty(2, 80, 401, device="cuda")
+    st = pkg._lib.stream()
+    pkg._lib.call("slu_sinc_filters_jac", b1.data_ptr(), band.data_ptr(), J.data_ptr(), st)
+    res = []
+    try:
+        for on in (1, 0):
+            pkg._lib.load().slu_set_sinc_persistent(on)
+            out = torch.empty(B, L1, 80, device="cuda"); route = torch.empty(B, L1, 80, device="cuda", dtype=torch.uint8)
+            img = torch.empty(2 * 6 * 160 * 96, device="cuda", dtype=torch.bfloat16)
+            d = torch.zeros(160, device="cuda", dtype=torch.float64)
+            pkg._lib.call("slu_sincconv_fwd_tc", x.data_ptr(), W.data_ptr(), B, T, out.data_ptr(), route.data_ptr(), img.data_ptr(), st)
+            pkg._lib.call("slu_sincconv_bwd_jac_tc", x.data_ptr(), gy.data_ptr(), route.data_ptr(), J.data_ptr(), B, T, d.data_ptr(),
+                          img.data_ptr(), st)
+            torch.cuda.synchronize()
+            res.append((out, route, d))
+    finally:
+        pkg._lib.load().slu_set_sinc_persistent(1)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert rel_err(res[0][2], res[1][2]) < 1e-6
