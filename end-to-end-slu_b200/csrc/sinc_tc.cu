@@ -257,12 +257,75 @@ sincconv_fwd_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restr
 //                         the MMAs of tile i+1 run into the other accumulator
 // so per tile the SM pays max(staging, MMA, epilogue) instead of their sum; the MMA phase (78 M128 x N80 x K16 instructions,
 // ~3 300 cycles) is the floor.  All hand-offs are mbarriers (bounded spins: a protocol bug traps instead of hanging).
+// The filter taps use their own operand image here: [bank][tap][hi | lo][10 k-chunks][80 filters][8] bf16, i.e. ONE contiguous
+// 25 600-byte block per tap, fetched with ONE bulk copy (the per-tile kernel's image needs 20 copies per tap, and bulk copies
+// are operation-rate limited: 120 per tile made the bank loader the bottleneck of the first persistent version).
 constexpr int P_STAGE_WARPS = 8, P_WARPS = 14, P_THREADS = P_WARPS * 32;
 constexpr int P_BANK_SLOTS = 4;
 constexpr uint32_t P_IMG = 2 * X_PART;                                  // one image slot (hi, lo)
-constexpr uint32_t P_BANK = 2 * W_PART;                                 // one bank slot (hi, lo)
+constexpr uint32_t P_LBO_W = SLU_NFILT * 16;                            // 1280: unpadded chunk stride (TMA writes it, no thread stores)
+constexpr uint32_t P_W_PART = KC * P_LBO_W;                             // 12 800 B
+constexpr uint32_t P_BANK = 2 * P_W_PART;                               // one bank slot = one tap (hi, lo) = one bulk copy
+
+// fp32 bank(s) W[nb][80][401] -> the per-tap image above (taps beyond 400 are zero)
+__global__ void __launch_bounds__(256) sinc_bank_image_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ img) {
+  const int bank = blockIdx.x / 6, tap = blockIdx.x % 6;
+  __nv_bfloat16* dst = img + (size_t)blockIdx.x * (P_BANK / 2);
+  for (int i = threadIdx.x; i < KC * SLU_NFILT * 8; i += 256) {
+    const int e = i & 7, n = (i >> 3) % SLU_NFILT, kc = i / (8 * SLU_NFILT);
+    const int k = SLU_STRIDE * tap + kc * 8 + e;
+    const float v = k < SLU_NTAPS ? W[((size_t)bank * SLU_NFILT + n) * SLU_NTAPS + k] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    dst[i] = h;
+    dst[P_W_PART / 2 + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
 constexpr uint32_t P_TR = 4 * 32 * 17 * 4;                              // epilogue transpose buffers
 constexpr uint32_t P_SMEM = 2 * P_IMG + P_BANK_SLOTS * P_BANK + P_TR;   // 200 064 B
+
+// Staging split in two so that a stager's global loads for tile i+1 are in flight while it waits for the image slot (the MMAs
+// of tile i-1): prefetch = issue the loads of this thread's 6 (frame row, 8-sample chunk) tasks into registers, commit = split
+// into bf16 hi / lo and store the 16-byte operand chunks.  (Loading only after the slot is free exposed one HBM round trip per
+// tile: the first persistent version ran at 2x its MMA floor with the stagers stalled on the loads.)
+constexpr int P_TASKS = (XROWS * KC + P_STAGE_WARPS * 32 - 1) / (P_STAGE_WARPS * 32);     // 6
+
+// Developer tool (tools/sinc_trace.py): when set, CTA (0,0) records clock64() at the hand-off points of its first 16 tiles:
+// trace[tile][0..7] = stager: slot free, image committed | MMA: image ready, accumulator free, last tap issued |
+//                     epilogue (quarter 0): accumulator full, tile drained | bank loader: tap 5 of the tile issued
+__device__ long long* g_sinc_trace = nullptr;
+#define STRACE(tile, ev) do { if (trace && (tile) < 16) trace[(tile) * 8 + (ev)] = clock64(); } while (0)
+
+__device__ __forceinline__ void stage_prefetch(float (&v)[P_TASKS][8], const float* xb, int t0, int T, int tid) {
+#pragma unroll
+  for (int u = 0; u < P_TASKS; ++u) {
+    const int task = u * (P_STAGE_WARPS * 32) + tid;
+    const int r = task / KC, kc = task - r * KC;
+    const int idx0 = SLU_STRIDE * (t0 + r) + kc * 8 - SLU_PAD;
+    const float* p = xb + idx0;
+    const bool on = task < XROWS * KC;
+    if (on && idx0 >= 0 && idx0 + 8 <= T && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[u][i] = (on && idx0 + i >= 0 && idx0 + i < T) ? __ldg(p + i) : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void stage_commit(uint8_t* hi, uint8_t* lo, const float (&v)[P_TASKS][8], int tid) {
+#pragma unroll
+  for (int u = 0; u < P_TASKS; ++u) {
+    const int task = u * (P_STAGE_WARPS * 32) + tid;
+    if (task < XROWS * KC) {
+      const int r = task / KC, kc = task - r * KC;
+      uint4 h, l; split8(v[u], h, l);
+      const uint32_t off = (uint32_t)kc * LBO_X + (uint32_t)r * 16;
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(lo + off) = l;
+    }
+  }
+}
 
 template <bool GRAD>
 __global__ void __launch_bounds__(P_THREADS, 1)
@@ -289,27 +352,41 @@ sincconv_tc_persistent_kernel(const float* __restrict__ x, const __nv_bfloat16* 
   fence_after_sync();
   const uint32_t tmem = tmem_base;
   const int n_mine = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int n_img = SLU_NFILT * (int)gridDim.y;                         // rows of the (stacked) bank image; bank = blockIdx.y
+  long long* trace = (g_sinc_trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? g_sinc_trace : nullptr;
 
   if (warp < P_STAGE_WARPS) {
     // ---- stagers ------------------------------------------------------------------------------------------------------
-    for (int it = 0; it < n_mine; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x, slot = it & 1;
+    float v[P_TASKS][8];
+    auto prefetch = [&](int it) {
+      const int tile = blockIdx.x + it * gridDim.x;
       const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TF;
+      stage_prefetch(v, x + (size_t)b * T, t0, T, tid);
+    };
+    if (n_mine > 0) prefetch(0);
+    for (int it = 0; it < n_mine; ++it) {
+      const int slot = it & 1;
       if (it >= 2) mbar_wait(&img_empty[slot], (uint32_t)(((it >> 1) - 1) & 1));      // the MMAs of tile it-2 have read this slot
+      if (warp == 0) STRACE(it, 0);
       uint8_t* hi = smem + slot * P_IMG;
-      stage_wave_image(hi, hi + X_PART, x + (size_t)b * T, t0, T, tid);
+      stage_commit(hi, hi + X_PART, v, tid);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&img_full[slot]);
+      if (warp == 0) STRACE(it, 1);
+      if (it + 1 < n_mine) prefetch(it + 1);                                          // in flight across the next slot wait
     }
   } else if (warp == P_STAGE_WARPS) {
     // ---- MMA issuer ---------------------------------------------------------------------------------------------------
+    // Measured (tools/sinc_trace.py): the 78 MMAs of a tile take ~4 900 cycles = 63 cycles each although an M128 x N80 x K16
+    // MMA is ~42 cycles of tensor work: both operands come from shared memory (4 KB + 2.5 KB per MMA) and 128 B/cycle of
+    // shared-memory bandwidth is the limit (507 KB per tile).  Splitting N into 64 + 16 made it worse (A is read twice as often).
     const uint32_t idesc = idesc_bf16(128, SLU_NFILT, false, false);
     for (int it = 0; it < n_mine; ++it) {
       const int slot = it & 1;
       mbar_wait(&img_full[slot], (uint32_t)((it >> 1) & 1));
+      STRACE(it, 2);
       if (it >= 2) mbar_wait(&acc_empty[slot], (uint32_t)(((it >> 1) - 1) & 1));      // the epilogue has drained this accumulator
+      STRACE(it, 3);
       fence_after_sync();
       const uint32_t x_hi = smem_u32(smem + slot * P_IMG), x_lo = x_hi + X_PART;
       const uint32_t dacc = tmem + (uint32_t)slot * 128u;
@@ -318,14 +395,14 @@ sincconv_tc_persistent_kernel(const float* __restrict__ x, const __nv_bfloat16* 
         mbar_wait(&bank_full[bs], (uint32_t)((g / P_BANK_SLOTS) & 1));
         fence_after_sync();
         if (elect_one()) {
-          const uint32_t w_hi = smem_u32(bank_ring + bs * P_BANK), w_lo = w_hi + W_PART;
+          const uint32_t w_hi = smem_u32(bank_ring + bs * P_BANK), w_lo = w_hi + P_W_PART;
           const uint64_t ah0 = smem_desc(x_hi + tap * 16, LBO_X, 128), al0 = smem_desc(x_lo + tap * 16, LBO_X, 128);
-          const uint64_t bh0 = smem_desc(w_hi, LBO_W, 128), bl0 = smem_desc(w_lo, LBO_W, 128);
+          const uint64_t bh0 = smem_desc(w_hi, P_LBO_W, 128), bl0 = smem_desc(w_lo, P_LBO_W, 128);
           const int nk = tap == 5 ? 1 : SLU_STRIDE / 16;
 #pragma unroll 1
           for (int kk = 0; kk < nk; ++kk) {
             const uint64_t ah = desc_advance(ah0, kk * 2 * LBO_X), al = desc_advance(al0, kk * 2 * LBO_X);
-            const uint64_t bh = desc_advance(bh0, kk * 2 * LBO_W), bl = desc_advance(bl0, kk * 2 * LBO_W);
+            const uint64_t bh = desc_advance(bh0, kk * 2 * P_LBO_W), bl = desc_advance(bl0, kk * 2 * P_LBO_W);
             mma_bf16(dacc, ah, bh, idesc, (tap | kk) ? 1u : 0u);
             mma_bf16(dacc, ah, bl, idesc, 1u);
             mma_bf16(dacc, al, bh, idesc, 1u);
@@ -335,22 +412,18 @@ sincconv_tc_persistent_kernel(const float* __restrict__ x, const __nv_bfloat16* 
         }
         __syncwarp();
       }
+      STRACE(it, 4);
     }
   } else if (warp == P_STAGE_WARPS + 1) {
     // ---- filter-bank loader (TMA ring) --------------------------------------------------------------------------------
     for (int g = 0; g < n_mine * 6; ++g) {
       const int bs = g & (P_BANK_SLOTS - 1), tap = g % 6;
       if (g >= P_BANK_SLOTS) mbar_wait(&bank_empty[bs], (uint32_t)(((g / P_BANK_SLOTS) - 1) & 1));
-      if (elect_one()) {
-        const int nch = tap == 5 ? 2 : KC;
-        uint8_t* w_hi = bank_ring + bs * P_BANK;
-        mbar_arrive_expect_tx(&bank_full[bs], (uint32_t)(2 * nch * SLU_NFILT * 16));
-        for (int part = 0; part < 2; ++part)
-          for (int kc = 0; kc < nch; ++kc) {
-            const size_t e = ((((size_t)part * 6 + tap) * WKC + kc) * n_img + (size_t)blockIdx.y * SLU_NFILT) * 8;
-            tma_load_1d(w_hi + part * W_PART + kc * LBO_W, wimg + e, SLU_NFILT * 16, &bank_full[bs]);
-          }
+      if (elect_one()) {                                                // one tap = one contiguous block of the per-tap image
+        mbar_arrive_expect_tx(&bank_full[bs], P_BANK);
+        tma_load_1d(bank_ring + bs * P_BANK, wimg + ((size_t)blockIdx.y * 6 + tap) * (P_BANK / 2), P_BANK, &bank_full[bs]);
       }
+      if (tap == 5) STRACE(g / 6, 7);
       __syncwarp();
     }
   } else {
@@ -364,6 +437,7 @@ sincconv_tc_persistent_kernel(const float* __restrict__ x, const __nv_bfloat16* 
       const int tile = blockIdx.x + it * gridDim.x, slot = it & 1;
       const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TF;
       mbar_wait(&acc_full[slot], (uint32_t)((it >> 1) & 1));
+      if (q == 0) STRACE(it, 5);
       fence_after_sync();
       const uint32_t acc = tmem + (uint32_t)slot * 128u + ((uint32_t)(q * 32) << 16);
       if (GRAD) {
@@ -432,6 +506,7 @@ sincconv_tc_persistent_kernel(const float* __restrict__ x, const __nv_bfloat16* 
       fence_before_sync();                                              // this thread's tcgen05.ld are done (wait::ld above)
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[slot]);
+      if (q == 0) STRACE(it, 6);
     }
     if (GRAD) {
       // per-filter sums over this warp's 32 frame rows, then one fp64 atomic per filter per warp
@@ -586,6 +661,9 @@ sincconv_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ gy
 int slu_presplit_rows_cm(const float* W, long sn, long sk, long stap, int taps, int N, int K, int row_len, void* img, void* stream);
 
 // 1 (default): the persistent warp-specialised kernel; 0: one CTA per tile (the round-1 kernel, kept for A/B measurements).
+extern "C" int slu_debug_sinc_trace(long long* buf) {   // developer tool; buf = 128 zeroed int64 on the device, or NULL
+  return (int)cudaMemcpyToSymbol(g_sinc_trace, &buf, sizeof(buf));
+}
 static int g_sinc_persistent = 1;
 extern "C" int slu_set_sinc_persistent(int on) { g_sinc_persistent = on ? 1 : 0; return 0; }
 static int sinc_sm_count() {
@@ -603,9 +681,8 @@ static int sinc_sm_count() {
 extern "C" int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T, float* out, uint8_t* route, void* img, void* stream) {
   if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
   const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
-  int e = slu_presplit_rows_cm(W, SLU_NTAPS, 1, SLU_STRIDE, 6, SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // bank[c][80a + k], 0 beyond tap 400
-  if (e) return e;
   if (g_sinc_persistent) {
+    sinc_bank_image_kernel<<<6, 256, 0, (cudaStream_t)stream>>>(W, (__nv_bfloat16*)img);
     SLU_SMEM_ONCE(sincconv_tc_persistent_kernel<false>, P_SMEM);
     const int tiles_per_utt = (L0 + TF - 1) / TF;
     const long n_tiles = (long)B * tiles_per_utt;
@@ -616,6 +693,8 @@ extern "C" int slu_sincconv_fwd_tc(const float* x, const float* W, int B, int T,
     SLU_CHECK_LAUNCH();
     return 0;
   }
+  int e = slu_presplit_rows_cm(W, SLU_NTAPS, 1, SLU_STRIDE, 6, SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // bank[c][80a + k], 0 beyond tap 400
+  if (e) return e;
   SLU_SMEM_ONCE(sincconv_fwd_tc_kernel<false>, FWD_SMEM);
   dim3 grid((L0 + TF - 1) / TF, B);
   sincconv_fwd_tc_kernel<false><<<grid, THREADS, FWD_SMEM, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)img, T, L0, L1, out, route,
@@ -631,9 +710,8 @@ extern "C" int slu_sincconv_bwd_jac_tc(const float* x, const float* gy, const ui
                                        void* img, void* stream) {
   if (B <= 0 || T <= 0) return (int)cudaErrorInvalidValue;
   const int L0 = (T - 1) / SLU_STRIDE + 1, L1 = (L0 + 1) / 2;
-  int e = slu_presplit_rows_cm(J, SLU_NTAPS, 1, SLU_STRIDE, 6, 2 * SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // both banks: 160 image rows
-  if (e) return e;
   if (g_sinc_persistent) {
+    sinc_bank_image_kernel<<<12, 256, 0, (cudaStream_t)stream>>>(J, (__nv_bfloat16*)img);
     SLU_SMEM_ONCE(sincconv_tc_persistent_kernel<true>, P_SMEM);
     const int tiles_per_utt = (L0 + TF - 1) / TF;
     const long n_tiles = (long)B * tiles_per_utt;
@@ -645,6 +723,8 @@ extern "C" int slu_sincconv_bwd_jac_tc(const float* x, const float* gy, const ui
     SLU_CHECK_LAUNCH();
     return 0;
   }
+  int e = slu_presplit_rows_cm(J, SLU_NTAPS, 1, SLU_STRIDE, 6, 2 * SLU_NFILT, SLU_STRIDE, SLU_NTAPS, img, stream);   // both banks: 160 image rows
+  if (e) return e;
   SLU_SMEM_ONCE(sincconv_fwd_tc_kernel<true>, FWD_SMEM);
   dim3 grid((L0 + TF - 1) / TF, B, 2);
   sincconv_fwd_tc_kernel<true><<<grid, THREADS, FWD_SMEM, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)img, T, L0, L1, nullptr,

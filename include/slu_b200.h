@@ -55,6 +55,8 @@ int slu_sincconv_bwd_tc(const float* x, const float* gy, const uint8_t* route, i
  * TMEM accumulators (staging of tile i+1 and the epilogue of tile i-1 overlap the MMAs of tile i); slu_set_sinc_persistent(0)
  * selects the one-CTA-per-tile kernel instead (A/B measurements). */
 int slu_set_sinc_persistent(int on);
+/* Developer tool: CTA (0,0) of the persistent kernel records clock64() at its hand-off points into buf[16 tiles][8] (or NULL: off). */
+int slu_debug_sinc_trace(long long* buf);
 int slu_sincconv_bwd_jac_tc(const float* x, const float* gy, const uint8_t* route, const float* J, int B, int T, double* d,
                             void* img, void* stream);
 
