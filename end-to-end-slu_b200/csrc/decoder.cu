@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_THREADS = 256;      // 8 warps: 3-4 encoder frames per warp at T = 25
 constexpr int ATT_MAXT = 256;        // encoder frames per utterance (4 s -> 25, 15 s -> 94)
 
 __device__ __forceinline__ float block_sum_128(float v, float* red) {
@@ -26,7 +26,9 @@ __device__ __forceinline__ float block_sum_128(float v, float* red) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  const float r = (red[0] + red[1]) + (red[2] + red[3]);
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < ATT_THREADS / 32; ++i) r += red[i];
   __syncthreads();
   return r;
 }
@@ -35,7 +37,9 @@ __device__ __forceinline__ float block_max_128(float v, float* red) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  const float r = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < ATT_THREADS / 32; ++i) r = fmaxf(r, red[i]);
   __syncthreads();
   return r;
 }
@@ -44,7 +48,7 @@ __device__ __forceinline__ float block_max_128(float v, float* red) {
 __global__ void __launch_bounds__(ATT_THREADS) attn_step_fwd_kernel(const float* __restrict__ q, long ldq, const float* __restrict__ keys,
                                                                     const float* __restrict__ values, int T, int K, int V,
                                                                     float inv_scale, float* __restrict__ w, float* __restrict__ ctx) {
-  __shared__ float qs[512], sc[ATT_MAXT], red[4];
+  __shared__ float qs[512], sc[ATT_MAXT], red[ATT_THREADS / 32];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int k = tid; k < K; k += ATT_THREADS) qs[k] = q[(long)b * ldq + k];
   __syncthreads();
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_step_bwd_kernel(const float*
                                                                     const float* __restrict__ values, int T, int K, int V,
                                                                     float inv_scale, float* __restrict__ dq, long lddq,
                                                                     float* __restrict__ dkeys, float* __restrict__ dvalues) {
-  __shared__ float dc[512], qs[512], ws[ATT_MAXT], ds[ATT_MAXT], red[4];
+  __shared__ float dc[512], qs[512], ws[ATT_MAXT], ds[ATT_MAXT], red[ATT_THREADS / 32];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int v = tid; v < V; v += ATT_THREADS) dc[v] = dctx[(long)b * V + v];
   for (int k = tid; k < K; k += ATT_THREADS) qs[k] = q[(long)b * ldq + k];
@@ -239,24 +243,36 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restric
   for (int k0 = 0; k0 < K; k0 += SK_KC) {
     const int kc = min(SK_KC, K - k0);                                  // K % 4 == 0 -> kc % 4 == 0
     __syncthreads();
-    for (int i = tid; i < SK_M * (SK_KC / 4); i += 256) {               // activation chunk: float4 along k
-      const int r = i / (SK_KC / 4), k4 = (i - r * (SK_KC / 4)) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < M && k4 < kc) v = *reinterpret_cast<const float4*>(A + (long)r * lda + k0 + k4);
-      *reinterpret_cast<float4*>(&As[r][k4]) = v;
+    // all loads of the chunk are issued before the first store (8 + 1 (or 4) independent requests per thread in flight: a
+    // load -> store loop would pay one L2 round trip per iteration)
+    float4 va[SK_M * (SK_KC / 4) / 256];
+#pragma unroll
+    for (int u = 0; u < SK_M * (SK_KC / 4) / 256; ++u) {               // activation chunk: float4 along k
+      const int i = u * 256 + tid, r = i / (SK_KC / 4), k4 = (i - r * (SK_KC / 4)) * 4;
+      va[u] = (r < M && k4 < kc) ? __ldg(reinterpret_cast<const float4*>(A + (long)r * lda + k0 + k4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (sk == 1) {                                                      // weight rows contiguous along k
-      for (int i = tid; i < SK_N * (SK_KC / 4); i += 256) {
-        const int r = i / (SK_KC / 4), k4 = (i - r * (SK_KC / 4)) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n0 + r < N && k4 < kc) v = *reinterpret_cast<const float4*>(W + (long)(n0 + r) * sn + k0 + k4);
-        *reinterpret_cast<float4*>(&Ws[r][k4]) = v;
+    if (sk == 1) {                                                      // weight rows contiguous along k: 8 x 32 float4 = 1 per thread
+      const int r = tid / (SK_KC / 4), k4 = (tid - r * (SK_KC / 4)) * 4;
+      const float4 vw = (n0 + r < N && k4 < kc) ? __ldg(reinterpret_cast<const float4*>(W + (long)(n0 + r) * sn + k0 + k4))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(&Ws[r][k4]) = vw;
+    } else {                                                            // transposed view: contiguous along n, 4 scalars per thread
+      float vw[SK_N * SK_KC / 256];
+#pragma unroll
+      for (int u = 0; u < SK_N * SK_KC / 256; ++u) {
+        const int i = u * 256 + tid, k = i / SK_N, r = i - k * SK_N;
+        vw[u] = (n0 + r < N && k < kc) ? __ldg(W + (long)(n0 + r) * sn + (long)(k0 + k) * sk) : 0.f;
       }
-    } else {                                                            // transposed view: contiguous along n
-      for (int i = tid; i < SK_N * SK_KC; i += 256) {
-        const int k = i / SK_N, r = i - k * SK_N;
-        Ws[r][k] = (n0 + r < N && k < kc) ? W[(long)(n0 + r) * sn + (long)(k0 + k) * sk] : 0.f;
+#pragma unroll
+      for (int u = 0; u < SK_N * SK_KC / 256; ++u) {
+        const int i = u * 256 + tid, k = i / SK_N, r = i - k * SK_N;
+        Ws[r][k] = vw[u];
       }
+    }
+#pragma unroll
+    for (int u = 0; u < SK_M * (SK_KC / 4) / 256; ++u) {
+      const int i = u * 256 + tid, r = i / (SK_KC / 4), k4 = (i - r * (SK_KC / 4)) * 4;
+      *reinterpret_cast<float4*>(&As[r][k4]) = va[u];
     }
     __syncthreads();
     const float4* a4 = reinterpret_cast<const float4*>(&As[m][0]);
