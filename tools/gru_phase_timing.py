@@ -16,7 +16,7 @@ for prec in ("bf16x3", "fp16"):
         buf = torch.zeros(16, dtype=torch.int64, device="cuda")
         lib.slu_debug_gru_phase_clocks(buf.data_ptr())
         xx = x.clone().requires_grad_(train)
-        y = pkg.ops.bigru(xx, gru, None, 2)
+        y = pkg.ops.bigru(xx, gru, (0.5, 77) if train else None, 2)
         torch.cuda.synchronize()
         lib.slu_debug_gru_phase_clocks(None)
         v = buf.cpu().view(2, 8).double() / T
