@@ -60,6 +60,18 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
+// ---- TMA tiled tensor copy (3-D tensor map) global -> shared: one instruction moves a [box2][box1][box0] box; coordinates outside
+// the tensor read zeros (SASS: UTMALDG).  `tmap` = address of a CUtensorMap in kernel-parameter (__grid_constant__) space;
+// dst 128-byte aligned; the mbarrier receives the full box bytes.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst_smem),
+               "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // ---- Ampere-style 16-byte async copy global -> shared (SASS: LDGSTS), zero-filling beyond src_bytes, and its
 // completion hook: the mbarrier receives one of its expected arrivals once all prior cp.async of this thread have landed.
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem, uint32_t src_bytes) {

@@ -192,3 +192,58 @@ def teacher_forced_log_likelihood(dec, encoder_outputs, y, training):
     mean_nll, _, row_nll = ops.LinearCE.apply(states.reshape(U * B, D), dec.linear.weight, dec.linear.bias, targets)
     total = -float(U) * mean_nll                                                               # = mean_b log p(y_b | x_b)
     return -row_nll.view(U, B).sum(0) + (total - total.detach())
+
+
+# ---- one decoding step for beam search (Seq2SeqDecoder.infer, reference models.py:558-651): forward only ----------------------
+class StepCache:
+    """What does not change over the symbols of one `infer` call: keys / values of the encoder states and the weights in the
+    operand forms of the step projections (the reference re-projects the encoder states in every step of every hypothesis)."""
+
+    def __init__(self, dec, encoder_outputs):
+        att, cell0, cell1 = dec.attention, dec.rnn.layers[0], dec.rnn.layers[2]
+        B = encoder_outputs.shape[0]
+        self.keys = ops.LinearNT.apply(encoder_outputs, att.key_linear.weight, att.key_linear.bias).contiguous()
+        self.values = ops.LinearNT.apply(encoder_outputs, att.value_linear.weight, att.value_linear.bias).contiguous()
+        S = dec.embed.weight.shape[1]
+        self.pad = (-S) % 4
+        c = lambda t: t.detach().contiguous()
+        self.w_embed = _W(c(torch.nn.functional.pad(dec.embed.weight.detach(), (0, self.pad))), False, B)
+        self.w_q, self.w_ih0, self.w_hh0 = _W(c(att.query_linear.weight), False, B), _W(c(cell0.weight_ih), False, B), _W(c(cell0.weight_hh), False, B)
+        self.w_ih1, self.w_hh1, self.w_out = _W(c(cell1.weight_ih), False, B), _W(c(cell1.weight_hh), False, B), _W(c(dec.linear.weight), False, B)
+        self.b = [c(t) for t in (dec.embed.bias, att.query_linear.bias, cell0.bias_ih, cell0.bias_hh, cell1.bias_ih, cell1.bias_hh, dec.linear.bias)]
+
+
+def beam_step(dec, cache, y_prev, state):
+    """Seq2SeqDecoder._step on the library's kernels: attention over the cached keys / values, the two GRUCells, the output
+    projection; returns (new state [B, 2, D], log-probabilities [B, |S|]).  No dropout (beam search runs in eval mode)."""
+    if dec.rnn.num_layers != 2:
+        raise NotImplementedError("slu_b200 CUDA path: the seq2seq decoder kernels take num_intent_decoder_layers = 2")
+    B = y_prev.shape[0]
+    D = dec.rnn.layers[0].hidden_size
+    K, V, T = cache.keys.shape[2], cache.values.shape[2], cache.keys.shape[1]
+    dev = y_prev.device
+    st = _lib.stream()
+    f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    b_emb, b_q, b_ih0, b_hh0, b_ih1, b_hh1, b_out = cache.b
+    s0, s1 = state[:, 0].contiguous(), state[:, 1].contiguous()
+    yp = torch.nn.functional.pad(y_prev.float(), (0, cache.pad)).contiguous()
+    x0 = f(B, D + V)                                   # cell-0 input: embedding | context (models.py:540 torch.cat)
+    emb, q, ctx, w = f(B, D), f(B, K), f(B, V), f(B, T)
+    cache.w_embed.nt(yp, B, emb, b_emb)
+    cache.w_q.nt(s1, B, q, b_q)
+    _lib.call("slu_attn_step_fwd", q.data_ptr(), K, cache.keys.data_ptr(), cache.values.data_ptr(), B, T, K, V, 1.0 / math.sqrt(float(K)),
+              w.data_ptr(), ctx.data_ptr(), st)
+    x0[:, :D].copy_(emb); x0[:, D:].copy_(ctx)
+    gi, gh, n0, n1 = f(B, 3 * D), f(B, 3 * D), f(B, D), f(B, D)
+    cache.w_ih0.nt(x0, B, gi, b_ih0)
+    cache.w_hh0.nt(s0, B, gh, b_hh0)
+    _lib.call("slu_grucell_fwd", gi.data_ptr(), 3 * D, None, 0, gh.data_ptr(), 3 * D, s0.data_ptr(), None, B, D, 0.0, 0, None, 0,
+              n0.data_ptr(), None, None, st)
+    cache.w_ih1.nt(n0, B, gi, b_ih1)
+    cache.w_hh1.nt(s1, B, gh, b_hh1)
+    _lib.call("slu_grucell_fwd", gi.data_ptr(), 3 * D, None, 0, gh.data_ptr(), 3 * D, s1.data_ptr(), None, B, D, 0.0, 0, None, 0,
+              n1.data_ptr(), None, None, st)
+    S = dec.linear.weight.shape[0]
+    logits = f(B, S)
+    cache.w_out.nt(n1, B, logits, b_out)
+    return torch.stack([n0, n1], dim=1), torch.log_softmax(logits, dim=1)

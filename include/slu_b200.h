@@ -184,6 +184,10 @@ int slu_wgrad2_tc(const float* G0, long ldg0, int m_split, const float* G1, long
                   int T, int taps, int shift0, float* out, long s_m, long s_n, long s_tap, void* stream);
 int slu_wgrad_tc(const float* G, long ldg, int M, const float* X, long ldx, int N, int B, int T, int taps, int shift0, float* out,
                  long s_m, long s_n, long s_tap, void* stream);
+/* Developer tool (tools/wgrad_only.py): bit 0 skips the MMAs, bit 1 the operand conversion, bit 2 the flush; 0 = normal. */
+int slu_debug_wgrad_mode(int mode);
+/* Developer tool: CTA (0,0,0) records clock64() at its hand-off points into buf[64 tiles][8] (NULL: off). */
+int slu_debug_wgrad_trace(long long* buf);
 
 /* tcgen05 self-test: C[128][N] = A[128][K] . B[N][K]^T (3-pass bf16 split, fp32 accumulate in TMEM). */
 /* ---- ASR heads: frame-wise cross-entropy without materialising [B*T', V] logits (reference models.py:308-314, 321-329:

@@ -5,8 +5,10 @@ Seq2SeqDecoder.forward / infer).  SURVEY.md section 8 keeps the decoder OUT of t
 the encoder kernels"): on a CUDA device the encoder's bidirectional GRU runs on the sm_100a persistent-GRU kernel and the teacher-forced
 decoder (`Seq2SeqDecoder.forward`, the training path) on the library's decoder kernels (end-to-end-slu_b200/decoder.py:
 batched tcgen05 GEMMs outside the recurrence, fused attention / GRUCell step kernels inside it, hand-written backward
-through time).  The CPU path and beam search (`infer`, evaluation prints only) are plain torch ops, written batched
-(gather/scatter instead of the reference's per-element python loops) with identical results.  Parameter names match the reference so its seq2seq
+through time); beam search (`infer`) runs its per-symbol step on the same kernels (decoder.beam_step: keys / values projected
+once per call, attention, both GRUCells and the output projection) and keeps only the hypothesis bookkeeping (top-k, sort,
+gather) in torch, written batched (gather/scatter instead of the reference's per-element python loops) with identical
+results.  The CPU path is plain torch ops.  Parameter names match the reference so its seq2seq
 checkpoints (`encoder.layers.0.*`, `decoder.{initial_state, embed, attention.*, rnn.layers.{0,2,..}, linear}`) load strictly.
 """
 import torch
@@ -104,7 +106,10 @@ class Seq2SeqDecoder(torch.nn.Module):
         self.log_softmax = torch.nn.LogSoftmax(dim=1)
         self.SOS = SOS
 
-    def _step(self, encoder_outputs, y_prev, state):
+    def _step(self, encoder_outputs, y_prev, state, cache=None):
+        if cache is not None:             # CUDA: attention / GRUCells / projections on the library's kernels (decoder.beam_step)
+            import importlib
+            return importlib.import_module("end-to-end-slu_b200").decoder.beam_step(self, cache, y_prev, state)
         context = self.attention(encoder_outputs, state[:, -1])
         state = self.rnn(torch.cat([self.embed(y_prev), context], dim=1), state)
         return state, self.log_softmax(self.linear(state[:, -1]))
@@ -135,6 +140,10 @@ class Seq2SeqDecoder(torch.nn.Module):
         batch, S = encoder_outputs.shape[0], len(Sy)
         U = 200 if y_lengths is None else max(y_lengths)
         L, D = self.initial_state.shape
+        cache = None
+        if dev.type == "cuda":
+            import importlib
+            cache = importlib.import_module("end-to-end-slu_b200").decoder.StepCache(self, encoder_outputs)
         beam = torch.zeros(B, batch, U, S, device=dev)
         scores = torch.zeros(B, batch, device=dev)
         states = torch.zeros(B, batch, L, D, device=dev)
@@ -148,7 +157,7 @@ class Seq2SeqDecoder(torch.nn.Module):
                     y_prev = torch.zeros(batch, S, device=dev)
                 else:
                     state, y_prev = states[b], beam[b, :, u - 1, :]
-                state, out = self._step(encoder_outputs, y_prev, state)
+                state, out = self._step(encoder_outputs, y_prev, state, cache)
                 new_states.append(state)
                 top_s, top_i = out.topk(B)                                   # (batch, B)
                 cand_scores.append(top_s.t() + scores[b])                    # (B, batch)
