@@ -40,6 +40,7 @@ struct GemmParams {
   int T;                             // frames per utterance (row boundary for shifted A rows); 0 = none
   int act;                           // 0 none, 1 LeakyReLU(slope)
   float slope;
+  int zero;                          // 0 at run time, opaque to the compiler (see the converters' slot release)
 };
 
 constexpr int BM = 128, BK = 32;
@@ -172,7 +173,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           va[u][0] = x0.x; va[u][1] = x0.y; va[u][2] = x0.z; va[u][3] = x0.w;      // zero-filled by the loaders where invalid
           va[u][4] = x1.x; va[u][5] = x1.y; va[u][6] = x1.z; va[u][7] = x1.w;
         }
-        mbar_arrive(&stg_empty[slot]);                              // values are in registers: the loader may refill the slot
+        // values are in registers: the loader may refill the slot.  The arrive must not overtake the loads above (an mbarrier
+        // arrive does not wait for outstanding shared-memory loads): its address is made data-dependent on each of them.
+        uint32_t dep = 0;
+#pragma unroll
+        for (int u = 0; u < A_CH; ++u) dep ^= __float_as_uint(va[u][0]) ^ __float_as_uint(va[u][4]);
+        mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&stg_empty[slot]) + (dep & (uint32_t)p.zero)));
         if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((it / STAGES) - 1) & 1));
         uint8_t* a_hi = smem + s * S::STAGE;
         uint8_t* a_lo = a_hi + S::A_PART;
@@ -438,7 +444,7 @@ extern "C" int slu_gemm_tc(const float* A, long lda, const void* w_img, const fl
   if (M <= 0 || N <= 0 || K <= 0 || taps <= 0 || !w_img) return (int)cudaErrorInvalidValue;
   GemmParams p;
   p.A = A; p.lda = lda; p.Wimg = (const __nv_bfloat16*)w_img; p.Kp = (K + 31) / 32 * 32; p.bias = bias;
-  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.taps = taps; p.tap_pad = tap_pad; p.T = T; p.act = act; p.slope = slope;
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.taps = taps; p.tap_pad = tap_pad; p.T = T; p.act = act; p.slope = slope; p.zero = 0;
   // TMA source alignment: 16-byte aligned operands, row pitch and K in whole 16-byte units
   if ((reinterpret_cast<uintptr_t>(w_img) & 15) != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0 || (lda & 3) != 0 || (K & 3) != 0)
     return (int)cudaErrorInvalidValue;

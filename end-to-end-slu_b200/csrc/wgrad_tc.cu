@@ -47,6 +47,7 @@ struct WgradParams {
   int B, T, shift0, tiles_per_utt;
   float* out; long s_m, s_n, s_tap;     // out[m*s_m + n*s_n + tap*s_tap] += D_tap[m][n]
   long long* trace;
+  int zero;                              // 0 at run time, opaque to the compiler (see the converters' slot release)
   int dbg;                               // developer switch (slu_debug_wgrad_mode): 1 = no MMAs, 2 = no conversion, 4 = no flush
 };
 int g_dbg = 0;
@@ -76,13 +77,14 @@ struct Cfg {
   static constexpr uint32_t PIPE = NOPS * OP_STAGE;
   static constexpr uint32_t FLUSH = 8 * 32 * 17 * 4;                              // transposers of the final flush (alias PIPE)
   static constexpr uint32_t STG_OFF = (cmax(PIPE, FLUSH) + 127u) & ~127u;
-  static constexpr int NSTG = (int)cmin(NSTG_MAX, (SMEM_BUDGET - STG_OFF) / STG_SLOT);
+  static constexpr int NSTG = (int)cmin(NSTG_MAX, (SMEM_BUDGET - STG_OFF) / STG_SLOT) & ~1;    // even: a slot always meets the same converter group
+
   static constexpr uint32_t TOTAL = STG_OFF + NSTG * STG_SLOT + 128;              // + slack to align the base to 128 bytes
   static constexpr int ACC = MT * NTAPS * N;
   static constexpr uint32_t TCOLS = ACC <= 32 ? 32 : (ACC <= 64 ? 64 : (ACC <= 128 ? 128 : (ACC <= 256 ? 256 : 512)));
   static_assert(N % 16 == 0 && N <= 256 && ACC <= 512, "accumulators must fit the 512 TMEM columns");
   static_assert(N % XB == 0 && (X_BLK % 128) == 0 && (G_BLK % 128) == 0, "TMA boxes land on 128-byte boundaries");
-  static_assert(NSTG >= 3, "at least three staging slots");
+  static_assert(NSTG >= 4, "at least four staging slots");
 };
 
 // two fp32 -> packed bf16 hi pair and lo (residual) pair; four of them = one 8-column chunk of one frame
@@ -95,10 +97,17 @@ __device__ __forceinline__ Split8 split_chunk(const float4& a, const float4& b) 
 }
 // One conversion task: the 32 bytes (8 columns) at `q` of a dense fp32 row -> 16-byte hi / lo chunks.  Lanes of a quarter-warp
 // sit on 8 consecutive chunks of the same row; reading half `h` = (c >> 2) & 1 first spreads them over all eight 16-byte bank groups.
-__device__ __forceinline__ void convert_chunk(const uint8_t* q, int h, uint8_t* hi, uint8_t* lo) {
-  const float4 u0 = *reinterpret_cast<const float4*>(q + h * 16);
-  const float4 u1 = *reinterpret_cast<const float4*>(q + (h ^ 1) * 16);
-  const Split8 r = split_chunk(u0, u1);                       // r.{h,l}[0..1] = the half read first
+// Split in a load and a store half: a thread first pulls ALL its tasks of a tile into registers (the compiler will not move a
+// shared-memory load above an earlier shared-memory store), hands the staging slot back, and only then converts.
+struct Raw8 { float4 a, b; };
+__device__ __forceinline__ Raw8 load_chunk(const uint8_t* q, int h) {
+  Raw8 r;
+  r.a = *reinterpret_cast<const float4*>(q + h * 16);
+  r.b = *reinterpret_cast<const float4*>(q + (h ^ 1) * 16);
+  return r;
+}
+__device__ __forceinline__ void store_chunk(const Raw8& raw, int h, uint8_t* hi, uint8_t* lo) {
+  const Split8 r = split_chunk(raw.a, raw.b);                 // r.{h,l}[0..1] = the half read first
   *reinterpret_cast<uint4*>(hi) = h ? make_uint4(r.h[2], r.h[3], r.h[0], r.h[1]) : make_uint4(r.h[0], r.h[1], r.h[2], r.h[3]);
   *reinterpret_cast<uint4*>(lo) = h ? make_uint4(r.l[2], r.l[3], r.l[0], r.l[1]) : make_uint4(r.l[0], r.l[1], r.l[2], r.l[3]);
 }
@@ -133,32 +142,37 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++my_tiles;
 
   if (warp == LOAD_WARP) {
-    // ================= loader: one thread, MT + NXB tensor copies per tile =================
+    // ================= loader: one elected thread, MT + NXB tensor copies per tile =================
+    // (the whole warp walks the loop so that the copy instructions sit in warp-uniform control flow: their descriptor and
+    // coordinate operands are uniform registers, and a divergent branch would make the compiler wrap each one in a vote loop)
+    const bool two = p.m_split < p.m_valid;                  // a second G source exists
     if (lane == 0) {
-      const bool two = p.m_split < p.m_valid;                  // a second G source exists
       tma_prefetch_desc(&p.map_g0); tma_prefetch_desc(&p.map_x);
       if (two) tma_prefetch_desc(&p.map_g1);
-      const uint32_t stg0 = smem_u32(stg_base);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int slot = it % NSTG;
-        if (it >= NSTG) mbar_wait(&stg_empty[slot], (uint32_t)(((it / NSTG) - 1) & 1));
+    }
+    const uint32_t stg0 = smem_u32(stg_base);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int slot = it % NSTG;
+      if (it >= NSTG) mbar_wait(&stg_empty[slot], (uint32_t)(((it / NSTG) - 1) & 1));
+      const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TF;
+      const uint32_t dst = stg0 + (uint32_t)slot * C::STG_SLOT;
+      if (elect_one()) {
         const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64;
         if (tr) p.trace[it * 8 + 0] = clock64();
-        const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TF;
-        const uint32_t dst = stg0 + (uint32_t)slot * C::STG_SLOT;
         mbar_arrive_expect_tx(&stg_full[slot], C::STG_SLOT);
 #pragma unroll
         for (int k = 0; k < MT; ++k) {
           const int m = m0 + k * GB;                           // columns beyond the source's width read zeros
-          const bool second = two && m >= p.m_split;
-          tma_load_3d(dst + (uint32_t)k * C::G_BLK, second ? &p.map_g1 : &p.map_g0, second ? m - p.m_split : m, t0, b, &stg_full[slot]);
+          if (two && m >= p.m_split) tma_load_3d(dst + (uint32_t)k * C::G_BLK, &p.map_g1, m - p.m_split, t0, b, &stg_full[slot]);
+          else tma_load_3d(dst + (uint32_t)k * C::G_BLK, &p.map_g0, m, t0, b, &stg_full[slot]);
         }
 #pragma unroll
         for (int j = 0; j < C::NXB; ++j)
           tma_load_3d(dst + C::STG_G + (uint32_t)j * C::X_BLK, &p.map_x, n0 + j * C::XB, t0 + p.shift0, b, &stg_full[slot]);
         if (tr) p.trace[it * 8 + 1] = clock64();
       }
+      __syncwarp();
     }
   } else if (warp < CONV_WARPS) {
     // ================= converters: dense fp32 boxes -> bf16 hi/lo MN-major images =================
@@ -168,29 +182,57 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       mbar_wait(&stg_full[slot], (uint32_t)((it / NSTG) & 1));
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && ctid == 0 && it < 64;
       if (tr) p.trace[it * 8 + 2] = clock64();
-      if (it >= NOPS) mbar_wait(&op_empty[s], (uint32_t)(((it / NOPS) - 1) & 1));
       const uint8_t* src = stg_base + slot * C::STG_SLOT;
-      if (p.dbg & 2) { mbar_arrive(&stg_empty[slot]); mbar_arrive(&op_full[s]); if (tr) p.trace[it * 8 + 3] = clock64(); continue; }
+      if (p.dbg & 2) {
+        if (it >= NOPS) mbar_wait(&op_empty[s], (uint32_t)(((it / NOPS) - 1) & 1));
+        mbar_arrive(&stg_empty[slot]); mbar_arrive(&op_full[s]);
+        if (tr) p.trace[it * 8 + 3] = clock64();
+        continue;
+      }
+      constexpr int GT = MT * 256 / CONV_THREADS;                                   // tasks per thread: G ...
+      constexpr int XTOT = C::NXB * C::XR * C::XCHP, XT = (XTOT + CONV_THREADS - 1) / CONV_THREADS;   // ... and X
+      Raw8 rg[GT], rx[XT];
+#pragma unroll
+      for (int u = 0; u < GT; ++u) {                                               // (block k, frame f, chunk c): 16 chunks per row
+        const int i = ctid + u * CONV_THREADS, c = i & 15, f = (i >> 4) & 15, k = i >> 8;
+        rg[u] = load_chunk(src + k * C::G_BLK + f * (GB * 4) + c * 32, (c >> 2) & 1);
+      }
+      const uint8_t* srcx = src + C::STG_G;
+#pragma unroll
+      for (int u = 0; u < XT; ++u) {
+        const int i = ctid + u * CONV_THREADS, c = i % C::XCHP, r = i / C::XCHP, f = r % C::XR, j = r / C::XR;
+        rx[u].a = rx[u].b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < XTOT && c < C::XCH) rx[u] = load_chunk(srcx + j * C::X_BLK + f * (C::XB * 4) + c * 32, (c >> 2) & 1);
+      }
+      // Hand the slot back once the tile is in registers.  "In registers" has to be enforced: an mbarrier arrive does not wait for
+      // earlier shared-memory loads of the thread to return, and a TMA refill that hits in L2 can overtake them (measured: random
+      // corrupted rows).  The arrive's address is therefore made data-dependent on every load (x & 0 with a run-time 0).
+      uint32_t dep = 0;
+#pragma unroll
+      for (int u = 0; u < GT; ++u) dep ^= __float_as_uint(rg[u].a.x) ^ __float_as_uint(rg[u].b.x);
+#pragma unroll
+      for (int u = 0; u < XT; ++u) dep ^= __float_as_uint(rx[u].a.x) ^ __float_as_uint(rx[u].b.x);
+      if (!(p.dbg & 8)) mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&stg_empty[slot]) + (dep & (uint32_t)p.zero)));
+      if (it >= NOPS) mbar_wait(&op_empty[s], (uint32_t)(((it / NOPS) - 1) & 1));
       uint8_t* a_hi = smem + s * C::OP_STAGE;
       uint8_t* a_lo = a_hi + C::A_PART;
       uint8_t* b_hi = a_hi + 2 * C::A_PART;
       uint8_t* b_lo = b_hi + C::B_PART;
-#pragma unroll 2
-      for (int i = ctid; i < MT * 256; i += CONV_THREADS) {           // (block k, frame f, chunk c): 16 chunks per row
-        const int c = i & 15, f = (i >> 4) & 15, k = i >> 8;
+#pragma unroll
+      for (int u = 0; u < GT; ++u) {
+        const int i = ctid + u * CONV_THREADS, c = i & 15, f = (i >> 4) & 15, k = i >> 8;
         const uint32_t off = (uint32_t)(k * 16 + c) * C::SBO_A + (uint32_t)f * 16;
-        convert_chunk(src + k * C::G_BLK + f * (GB * 4) + c * 32, (c >> 2) & 1, a_hi + off, a_lo + off);
+        store_chunk(rg[u], (c >> 2) & 1, a_hi + off, a_lo + off);
       }
-      const uint8_t* srcx = src + C::STG_G;
-#pragma unroll 2
-      for (int i = ctid; i < C::NXB * C::XR * C::XCHP; i += CONV_THREADS) {
-        const int c = i % C::XCHP, r = i / C::XCHP, f = r % C::XR, j = r / C::XR;
-        if (c < C::XCH) {
+#pragma unroll
+      for (int u = 0; u < XT; ++u) {
+        const int i = ctid + u * CONV_THREADS, c = i % C::XCHP, r = i / C::XCHP, f = r % C::XR, j = r / C::XR;
+        if (i < XTOT && c < C::XCH) {
           const uint32_t off = (uint32_t)(j * C::XCH + c) * C::SBO_B + (uint32_t)f * 16;
-          convert_chunk(srcx + j * C::X_BLK + f * (C::XB * 4) + c * 32, (c >> 2) & 1, b_hi + off, b_lo + off);
+          store_chunk(rx[u], (c >> 2) & 1, b_hi + off, b_lo + off);
         }
       }
-      mbar_arrive(&stg_empty[slot]);            // all reads of the slot are done (the stores above depend on them)
+      if (p.dbg & 8) mbar_arrive(&stg_empty[slot]);
       fence_async_smem();                       // generic-proxy stores -> visible to the tensor core
       mbar_arrive(&op_full[s]);
       if (tr) p.trace[it * 8 + 3] = clock64();
@@ -366,7 +408,7 @@ extern "C" int slu_wgrad2_tc(const float* G0, long ldg0, int m_split, const floa
   if (err) return err;
   p.m_split = two ? m_split : M;
   p.m_valid = M; p.n_valid = N; p.B = B; p.T = T; p.shift0 = shift0;
-  p.tiles_per_utt = (T + TF - 1) / TF; p.out = out; p.s_m = s_m; p.s_n = s_n; p.s_tap = s_tap; p.dbg = g_dbg; p.trace = g_trace;
+  p.tiles_per_utt = (T + TF - 1) / TF; p.out = out; p.s_m = s_m; p.s_n = s_n; p.s_tap = s_tap; p.dbg = g_dbg; p.trace = g_trace; p.zero = 0;
   return run(p, taps, (cudaStream_t)stream);
 }
 
