@@ -27,6 +27,7 @@ SIGNATURES = {
     "slu_set_sinc_persistent": [_I],
     "slu_debug_sinc_trace": [_P],
     "slu_debug_wgrad_mode": [_I],
+    "slu_debug_gemm_mode": [_I],
     "slu_debug_wgrad_trace": [_P],
     "slu_gru_fwd_simt": [_P, _P, _P, _P, _F, _U, _P, _I, _I, _I, _P, _P, _P, _P],
     "slu_gru_bwd_simt": [_P, _P, _F, _U, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
@@ -104,7 +105,7 @@ stats = {"calls": 0}        # number of C-ABI kernel launches issued by this pro
 _prof = None                # name -> [(start_event, end_event)] while profiling
 _prof_detail = None         # [(name, small-int args, start, end)] per launch, when asked for
 _fn = {}
-_HOST_ONLY = ("slu_set_sinc_persistent", "slu_debug_sinc_trace", "slu_debug_wgrad_mode", "slu_debug_wgrad_trace", "slu_gru_rows_per_cta", "slu_h2d_async", "slu_h2d_ready", "slu_h2d_pending", "slu_h2d_wait", "slu_stream_fork", "slu_stream_join", "slu_set_gru_precision", "slu_debug_gru_phase_clocks")
+_HOST_ONLY = ("slu_set_sinc_persistent", "slu_debug_sinc_trace", "slu_debug_wgrad_mode", "slu_debug_gemm_mode", "slu_debug_wgrad_trace", "slu_gru_rows_per_cta", "slu_h2d_async", "slu_h2d_ready", "slu_h2d_pending", "slu_h2d_wait", "slu_stream_fork", "slu_stream_join", "slu_set_gru_precision", "slu_debug_gru_phase_clocks")
 
 
 def call(name, *args):

@@ -41,7 +41,9 @@ struct GemmParams {
   int act;                           // 0 none, 1 LeakyReLU(slope)
   float slope;
   int zero;                          // 0 at run time, opaque to the compiler (see the converters' slot release)
+  int dbg;                           // developer switch (slu_debug_gemm_mode): 1 = no MMAs, 2 = no conversion, 4 = no global stores, 8 = no epilogue
 };
+int g_gemm_dbg = 0;
 
 constexpr int BM = 128, BK = 32;
 
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         for (int u = 0; u < A_CH; ++u) dep ^= __float_as_uint(va[u][0]) ^ __float_as_uint(va[u][4]);
         mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&stg_empty[slot]) + (dep & (uint32_t)p.zero)));
         if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((it / STAGES) - 1) & 1));
+        if (p.dbg & 2) { mbar_arrive(&full_a[s]); continue; }
         uint8_t* a_hi = smem + s * S::STAGE;
         uint8_t* a_lo = a_hi + S::A_PART;
 #pragma unroll
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           uint32_t acc = kb > 0 ? 1u : 0u;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            if (kk < nk16) {
+            if (kk < nk16 && !(p.dbg & 1)) {
               const uint64_t ah = desc_advance(ah0, kk * 2 * S::LBO_A), al = desc_advance(al0, kk * 2 * S::LBO_A);
               const uint64_t bh = desc_advance(bh0, kk * 2 * S::LBO_B), bl = desc_advance(bl0, kk * 2 * S::LBO_B);
               mma_bf16(d_tmem, ah, bh, idesc, acc); acc = 1u;
@@ -282,6 +285,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           fence_before_sync();
           mbar_arrive(&acc_empty[buf]);
         }
+        if (p.dbg & 8) continue;
 #pragma unroll
         for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
         __syncwarp();
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
               x.x = x.x > 0.f ? x.x : x.x * p.slope; x.y = x.y > 0.f ? x.y : x.y * p.slope;
               x.z = x.z > 0.f ? x.z : x.z * p.slope; x.w = x.w > 0.f ? x.w : x.w * p.slope;
             }
-            *reinterpret_cast<float4*>(dst4 + (long)r * p.ldc) = x;
+            if (!(p.dbg & 4)) *reinterpret_cast<float4*>(dst4 + (long)r * p.ldc) = x;
           }
         } else {
           const int n = n0 + c0 + lane;
@@ -444,7 +448,7 @@ extern "C" int slu_gemm_tc(const float* A, long lda, const void* w_img, const fl
   if (M <= 0 || N <= 0 || K <= 0 || taps <= 0 || !w_img) return (int)cudaErrorInvalidValue;
   GemmParams p;
   p.A = A; p.lda = lda; p.Wimg = (const __nv_bfloat16*)w_img; p.Kp = (K + 31) / 32 * 32; p.bias = bias;
-  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.taps = taps; p.tap_pad = tap_pad; p.T = T; p.act = act; p.slope = slope; p.zero = 0;
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.taps = taps; p.tap_pad = tap_pad; p.T = T; p.act = act; p.slope = slope; p.zero = 0; p.dbg = g_gemm_dbg;
   // TMA source alignment: 16-byte aligned operands, row pitch and K in whole 16-byte units
   if ((reinterpret_cast<uintptr_t>(w_img) & 15) != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0 || (lda & 3) != 0 || (K & 3) != 0)
     return (int)cudaErrorInvalidValue;
@@ -464,3 +468,7 @@ extern "C" int slu_gemm_tc(const float* A, long lda, const void* w_img, const fl
   if (best_bn == 128) return launch<128>(p, st);
   return launch<256>(p, st);
 }
+
+// Developer switch for tools/gemm_rate.py: bit 0 skips the MMAs, bit 1 the operand conversion, bit 2 the global stores of the fast
+// epilogue path, bit 3 the whole epilogue after the accumulator read.  Results are meaningless with any bit set.
+extern "C" int slu_debug_gemm_mode(int mode) { g_gemm_dbg = mode; return 0; }

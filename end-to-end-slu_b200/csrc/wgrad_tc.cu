@@ -24,9 +24,9 @@
 // Contract of the tensor copies: operands 16-byte aligned; ldg, ldx, M, N multiples of 4 floats; m_split a multiple of 128 (or = M).
 // (Round 2 measured the previous 16-byte cp.async loader at 3.9-4.3 TB/s with everything else switched off: ~800 issue cycles and
 // a 2 500-cycle latency per 32 KB tile with 3 slots in flight; profiles/r2_wgrad_*.)
-#include <cuda.h>
 #include "common.cuh"
 #include "tc05.cuh"
+#include "tmap.cuh"
 
 namespace {
 using namespace tc05;
@@ -356,31 +356,13 @@ int run(const WgradParams& p, int taps, cudaStream_t st) {
 
 bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point query: no link-time dependency on libcuda.
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
-}
-
 // (column, frame, utterance) view of base[(b*T + t)*ld + c], c < cols, with a [box_rows frames][box_cols columns] box; out-of-range
 // coordinates (frames < 0 or >= T, columns >= cols) read zeros
 int make_map(CUtensorMap* m, const float* base, long ld, int cols, int T, int B, int box_cols, int box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return (int)cudaErrorNotSupported;
   const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
   const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)T * (cuuint64_t)ld * 4};
   const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
-  const cuuint32_t es[3] = {1, 1, 1};
-  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+  return tmap::encode_f32(m, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 int x_box_cols(int N, int taps) {               // Cfg<>::XB of the instantiation run() picks

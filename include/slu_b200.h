@@ -186,6 +186,7 @@ int slu_wgrad_tc(const float* G, long ldg, int M, const float* X, long ldx, int 
                  long s_m, long s_n, long s_tap, void* stream);
 /* Developer tool (tools/wgrad_only.py): bit 0 skips the MMAs, bit 1 the operand conversion, bit 2 the flush; 0 = normal. */
 int slu_debug_wgrad_mode(int mode);
+int slu_debug_gemm_mode(int mode);      /* same for slu_gemm_tc: 1 no MMAs, 2 no conversion, 4 no global stores, 8 no epilogue */
 /* Developer tool: CTA (0,0,0) records clock64() at its hand-off points into buf[64 tiles][8] (NULL: off). */
 int slu_debug_wgrad_trace(long long* buf);
 
