@@ -81,8 +81,9 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=25, query=None):
         self.rows, self.proc, self.index, self.lo, self.hi = [], None, index, 0, None
+        self.interval_ms, self.query = interval_ms, query or self.Q
 
     def __enter__(self):
         self.lo = len(self.rows)             # rows from here on were sampled inside the timed region
@@ -95,8 +96,8 @@ class ClockSampler:
     def start(self):
         """Launch nvidia-smi ahead of the timed region (its start-up takes longer than a short run)."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.query,
+                                          "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=lambda: [self.rows.append(l) for l in self.proc.stdout], daemon=True)
             self.thread.start()
         except Exception:
@@ -236,6 +237,7 @@ def main():
     ap.add_argument("--launch-detail", action="store_true", help="print every launch of one step with its sizes and device time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-structured port on this GPU (cuDNN), N=1 only")
+    ap.add_argument("--sampler-probe", action="store_true", help="developer: time the step under several clock-sampler settings (stderr)")
     ap.add_argument("--eval-dropout", action="store_true", help="disable dropout (debug)")
     args = ap.parse_args()
     _claim_stdout()
@@ -322,11 +324,23 @@ def main():
         if clk.rows or clk.proc is None:
             break
         time.sleep(0.1)
+    for i in range(max(args.warmup, 3)):                     # the GPU idled while nvidia-smi started: warm it again (untimed)
+        step(xs_dev[i % NB], ys_dev[i % NB])
+    torch.cuda.synchronize()
     calls0 = pkg._lib.stats["calls"]
     with clk:
         ms_dev = timed(args.steps, host=None)
     launches = pkg._lib.stats["calls"] - calls0
     clk.stop()
+    if args.sampler_probe and rank == 0:                     # developer: how much does the clock sampler perturb the timed region?
+        for name, kw in [("none", None), ("25 ms full query", {}), ("25 ms, clocks + reasons only", {"query": ClockSampler.Q.replace("power.draw,", "")}),
+                         ("100 ms full query", {"interval_ms": 100}), ("200 ms full query", {"interval_ms": 200}), ("none", None)]:
+            c = ClockSampler(local, **kw).start() if kw is not None else None
+            time.sleep(1.0)
+            runs = [timed(args.steps, host=None) / args.steps for _ in range(5)]
+            if c is not None:
+                c.stop()
+            print("sampler %-30s ms/step: %s" % (name, " ".join("%.3f" % r for r in runs)), file=sys.stderr)
     ms_e2e = timed(args.steps, host="prefetch")
     ms_e2e_serial = timed(args.steps, host="serial")
     per_step = ms_dev / args.steps

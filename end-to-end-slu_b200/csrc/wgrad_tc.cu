@@ -51,6 +51,15 @@ struct WgradParams {
   int dbg;                               // developer switch (slu_debug_wgrad_mode): 1 = no MMAs, 2 = no conversion, 4 = no flush
 };
 int g_dbg = 0;
+// Ablation switches and the hand-off trace exist only in -DSLU_KERNEL_DEBUG builds (SLU_KERNEL_DEBUG=1 python __graft_entry__.py): even
+// switched off they cost measurable time in the GEMM (gemm_tc.cu).  tools/wgrad_{only,rate,trace,check}.py need such a build.
+#ifdef SLU_KERNEL_DEBUG
+#define SLU_DBG(p) ((p).dbg)
+#define SLU_TRACE(p) ((p).trace)
+#else
+#define SLU_DBG(p) 0
+#define SLU_TRACE(p) ((long long*)nullptr)
+#endif
 long long* g_trace = nullptr;      // developer tool: CTA (0,0,0) records clock64() per tile: [tile][0] loader issue start, [1] issue end,
                                    // [2] converter saw the slot full, [3] converter done, [4] MMA warp saw operands, [5] after MMA issue
 
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TF;
       const uint32_t dst = stg0 + (uint32_t)slot * C::STG_SLOT;
       if (elect_one()) {
-        const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64;
+        const bool tr = SLU_TRACE(p) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64;
         if (tr) p.trace[it * 8 + 0] = clock64();
         mbar_arrive_expect_tx(&stg_full[slot], C::STG_SLOT);
 #pragma unroll
@@ -180,10 +189,10 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     for (int it = grp; it < my_tiles; it += CONV_GROUPS) {
       const int slot = it % NSTG, s = it % NOPS;
       mbar_wait(&stg_full[slot], (uint32_t)((it / NSTG) & 1));
-      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && ctid == 0 && it < 64;
+      const bool tr = SLU_TRACE(p) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && ctid == 0 && it < 64;
       if (tr) p.trace[it * 8 + 2] = clock64();
       const uint8_t* src = stg_base + slot * C::STG_SLOT;
-      if (p.dbg & 2) {
+      if (SLU_DBG(p) & 2) {
         if (it >= NOPS) mbar_wait(&op_empty[s], (uint32_t)(((it / NOPS) - 1) & 1));
         mbar_arrive(&stg_empty[slot]); mbar_arrive(&op_full[s]);
         if (tr) p.trace[it * 8 + 3] = clock64();
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       for (int u = 0; u < GT; ++u) dep ^= __float_as_uint(rg[u].a.x) ^ __float_as_uint(rg[u].b.x);
 #pragma unroll
       for (int u = 0; u < XT; ++u) dep ^= __float_as_uint(rx[u].a.x) ^ __float_as_uint(rx[u].b.x);
-      if (!(p.dbg & 8)) mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&stg_empty[slot]) + (dep & (uint32_t)p.zero)));
+      if (!(SLU_DBG(p) & 8)) mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&stg_empty[slot]) + (dep & (uint32_t)p.zero)));
       if (it >= NOPS) mbar_wait(&op_empty[s], (uint32_t)(((it / NOPS) - 1) & 1));
       uint8_t* a_hi = smem + s * C::OP_STAGE;
       uint8_t* a_lo = a_hi + C::A_PART;
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
           store_chunk(rx[u], (c >> 2) & 1, b_hi + off, b_lo + off);
         }
       }
-      if (p.dbg & 8) mbar_arrive(&stg_empty[slot]);
+      if (SLU_DBG(p) & 8) mbar_arrive(&stg_empty[slot]);
       fence_async_smem();                       // generic-proxy stores -> visible to the tensor core
       mbar_arrive(&op_full[s]);
       if (tr) p.trace[it * 8 + 3] = clock64();
@@ -245,14 +254,14 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       mbar_wait(&op_full[s], (uint32_t)((it / NOPS) & 1));
       fence_after_sync();
       if (elect_one()) {
-        const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64;
+        const bool tr = SLU_TRACE(p) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 64;
         if (tr) p.trace[it * 8 + 4] = clock64();
         const uint32_t sa = smem_u32(smem + s * C::OP_STAGE);
         // MN-major, no swizzle: LBO = stride between 8-frame K groups (128 B), SBO = stride between 8-wide MN chunks
         const uint64_t bh0 = smem_desc(sa + 2 * C::A_PART, 128, C::SBO_B), bl0 = smem_desc(sa + 2 * C::A_PART + C::B_PART, 128, C::SBO_B);
         const uint32_t acc = it ? 1u : 0u;
 #pragma unroll
-        for (int mi = 0; mi < ((p.dbg & 1) ? 0 : MT); ++mi) {
+        for (int mi = 0; mi < ((SLU_DBG(p) & 1) ? 0 : MT); ++mi) {
           const uint64_t ah = smem_desc(sa + mi * 16 * C::SBO_A, 128, C::SBO_A), al = smem_desc(sa + C::A_PART + mi * 16 * C::SBO_A, 128, C::SBO_A);
 #pragma unroll
           for (int tap = 0; tap < NTAPS; ++tap) {
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   }
 
   // ================= flush: TMEM -> transposed through shared memory -> fp32 atomics (coalesced when s_n == 1) =================
-  if (my_tiles > 0 && warp < 8 && !(p.dbg & 4)) {
+  if (my_tiles > 0 && warp < 8 && !(SLU_DBG(p) & 4)) {
     mbar_wait(&acc_bar, 0);
     fence_after_sync();
     const int q = warp & 3, half = warp >> 2;          // two warps per TMEM lane quarter alternate 16-column groups
@@ -402,6 +411,13 @@ extern "C" int slu_wgrad_tc(const float* G, long ldg, int M, const float* X, lon
 
 // Developer switch for tools/wgrad_only.py (which pipeline stage bounds the kernel): bit 0 skips the MMAs, bit 1 the conversion,
 // bit 2 the flush.  Results are meaningless with any bit set.
-extern "C" int slu_debug_wgrad_mode(int mode) { g_dbg = mode; return 0; }
+extern "C" int slu_debug_wgrad_mode(int mode) {
+  g_dbg = mode;
+#ifdef SLU_KERNEL_DEBUG
+  return 0;
+#else
+  return mode ? (int)cudaErrorNotSupported : 0;      // built without the switches
+#endif
+}
 // CTA (0,0,0) records clock64() at its hand-off points into buf[64 tiles][8] (NULL: off).
 extern "C" int slu_debug_wgrad_trace(long long* buf) { g_trace = buf; return 0; }

@@ -1,5 +1,6 @@
 """Developer tool: sustained time per slu_gemm_tc launch for the x-projection / input-gradient shapes of the config-3 step, over
-`reps` back-to-back launches, per pipeline-ablation mode (slu_debug_gemm_mode).   python tools/gemm_rate.py [modes] [reps]"""
+`reps` back-to-back launches, per pipeline-ablation mode (slu_debug_gemm_mode).   python tools/gemm_rate.py [modes] [reps]
+Needs a library built with the debug switches: SLU_KERNEL_DEBUG=1 python __graft_entry__.py (the default build has none)."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

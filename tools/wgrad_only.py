@@ -1,6 +1,7 @@
 """Developer tool: the weight-gradient launches of one train step (config 3, B=256 x 4 s) one by one, CUDA-event timed with an
 L2 flush in between, optionally with pipeline stages switched off (slu_debug_wgrad_mode) to see which stage bounds the kernel.
-  python tools/wgrad_only.py [modes, e.g. 0,1,3,7] [reps]"""
+  python tools/wgrad_only.py [modes, e.g. 0,1,3,7] [reps]
+Needs a library built with the debug switches: SLU_KERNEL_DEBUG=1 python __graft_entry__.py (the default build has none)."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,5 +1,6 @@
 """Developer tool: sustained time per weight-gradient launch, measured over `reps` back-to-back launches (no host gaps, data sets
-larger than L2), per pipeline-ablation mode (slu_debug_wgrad_mode).   python tools/wgrad_rate.py [modes] [reps]"""
+larger than L2), per pipeline-ablation mode (slu_debug_wgrad_mode).   python tools/wgrad_rate.py [modes] [reps]
+Needs a library built with the debug switches: SLU_KERNEL_DEBUG=1 python __graft_entry__.py (the default build has none)."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,7 +1,8 @@
 """Developer tool: clock64() hand-off trace of CTA 0 of one weight-gradient launch (slu_debug_wgrad_trace).
   python tools/wgrad_trace.py kind[,kind..] [layer 0..4] [mode] [-v]
 kinds: hh (dW_hh as BiGRU.backward launches it), hh_dense (same from dense sources), ih (dW_ih 768 x I), ih_1g (one dense m-group),
-       conv0 / conv1 (Conv1d weight gradients)"""
+       conv0 / conv1 (Conv1d weight gradients)
+Needs a library built with the debug switches: SLU_KERNEL_DEBUG=1 python __graft_entry__.py (the default build has none)."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
