@@ -28,11 +28,17 @@ constexpr int TC_THREADS = 512;       // 16 compute warps: warp w owns TMEM lane
 __host__ __device__ constexpr int svc_warps(int nr) { return nr == 4 ? 4 : 0; }
 __host__ __device__ constexpr int block_threads(int nr) { return TC_THREADS + 32 * svc_warps(nr); }
 constexpr uint32_t ACC_COL = 384;     // accumulators start after the 384 weight columns
-constexpr int FWD_RING = 4, BWD_RING = 3;
+constexpr int FWD_RING = 4, BWD_RING = 3;      // depth of the TMA input rings (steps in flight)
 // Optional phase timing (developer tool, tools/gru_phase_timing.py): when set, CTA (0,0) accumulates clock64() deltas of the
 // step phases for threads 0 and 128 into this buffer [2][8].
 __device__ long long* g_phase_clk = nullptr;
-#define PHASE(i) do { if (NR == 4 && dbg) { const long long now_ = clock64(); ph_acc[i] += now_ - tprev_; tprev_ = now_; } } while (0)   // depth of the TMA input rings (steps in flight)
+// (phase clocks exist only in -DSLU_KERNEL_DEBUG builds -- SLU_KERNEL_DEBUG=1 python __graft_entry__.py -- which tools/gru_phase_timing.py needs:
+// eight untaken branches and their accumulators in the step loop are not free, see DESIGN.md "debug branches")
+#ifdef SLU_KERNEL_DEBUG
+#define PHASE(i) do { if (NR == 4 && dbg) { const long long now_ = clock64(); ph_acc[i] += now_ - tprev_; tprev_ = now_; } } while (0)
+#else
+#define PHASE(i) do { } while (0)
+#endif
 
 // Load W rows (this thread's lane) into TMEM as split bf16 A-operands.  src: 3 blocks of [128][128] fp32 with
 // element (row j, k) at src[g*block_stride + j*row_stride + k*k_stride].
@@ -216,9 +222,11 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   uint8_t* h_hi_j = h_hi + (uint32_t)(j >> 3) * LBO + (uint32_t)(j & 7) * 2 + c0 * 16;
   uint8_t* h_lo_j = PASSES == 2 ? h_hi_j + NR * 16 : h_hi_j + 16 * LBO;     // stacked: lo rows follow the NR hi rows of the same tile
 
+#ifdef SLU_KERNEL_DEBUG
   long long* dbg = (g_phase_clk && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 128)) ? g_phase_clk + (tid ? 8 : 0) : nullptr;
   long long tprev_ = clock64();
   long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // register accumulators (4-row instantiations only): no memory traffic in the loop
+#endif
   if (SVC && !is_compute) {
     // service warps: one barrier per step like everybody else, then issue -- they are back at the next barrier long
     // before the compute warps have finished their gate math
@@ -335,8 +343,10 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       off[c] += dt * 256;
     }
   }
+#ifdef SLU_KERNEL_DEBUG
   if (NR == 4 && dbg)
     for (int i = 0; i < 8; ++i) dbg[i] += ph_acc[i];
+#endif
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);

@@ -293,7 +293,11 @@ constexpr int P_TASKS = (XROWS * KC + P_STAGE_WARPS * 32 - 1) / (P_STAGE_WARPS *
 // trace[tile][0..7] = stager: slot free, image committed | MMA: image ready, accumulator free, last tap issued |
 //                     epilogue (quarter 0): accumulator full, tile drained | bank loader: tap 5 of the tile issued
 __device__ long long* g_sinc_trace = nullptr;
+#ifdef SLU_KERNEL_DEBUG      // SLU_KERNEL_DEBUG=1 python __graft_entry__.py; the default build carries no trace branches
 #define STRACE(tile, ev) do { if (trace && (tile) < 16) trace[(tile) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define STRACE(tile, ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ void stage_prefetch(float (&v)[P_TASKS][8], const float* xb, int t0, int T, int tid) {
 #pragma unroll

@@ -1,6 +1,7 @@
 """Developer tool: where does a step of the tcgen05 GRU forward kernel spend its cycles?
 Phases (accumulated clock64 deltas for thread 0 [MMA issuer warp] and thread 128): 0 wait MMAs, 1 tcgen05.ld, 2 TMA ring wait,
-3 gate math + operand stores, 4 fences, 5 __syncthreads, 6 MMA issue, 7 global stores + loop tail."""
+3 gate math + operand stores, 4 fences, 5 __syncthreads, 6 MMA issue, 7 global stores + loop tail.
+Needs a library built with the debug switches: SLU_KERNEL_DEBUG=1 python __graft_entry__.py (the default build has none)."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

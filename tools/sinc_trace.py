@@ -1,4 +1,5 @@
-"""Developer tool: hand-off timeline of CTA 0 of the persistent SincConv kernel (cycles since its first event)."""
+"""Developer tool: hand-off timeline of CTA 0 of the persistent SincConv kernel (cycles since its first event).
+Needs a library built with the debug switches: SLU_KERNEL_DEBUG=1 python __graft_entry__.py (the default build has none)."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
