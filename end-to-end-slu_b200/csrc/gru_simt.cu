@@ -9,7 +9,7 @@
 //   gx     [B][T][768]   col = d*384 + g*128 + j      (g: 0=r 1=z 2=n)
 //   y_full [B][T][256]   col = d*128 + j              raw h_t  (kept for backward)
 //   y_out  [B][ceil(T/ds)][256]                       after dropout-mask and avg-downsample
-//   stash  [B][T][1024]  col = d*512 + s*128 + j      s: 0=r 1=z 2=n 3=hn (=W_hn h + b_hn), training only
+//   stash  [B][T][1024]  col = d*512 + 4*j + s        s: 0=r 1=z 2=n 3=hn (=W_hn h + b_hn), training only
 //   mask   [B][T][256]   dropout keep-mask pre-scaled by 1/(1-p), or NULL
 #include "common.cuh"
 #include "philox.cuh"
@@ -107,8 +107,7 @@ gru_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, con
       const size_t bt = (size_t)b * T + t;
       y_full[bt * 256 + d * SLU_H + j] = hnew;
       if (STASH) {
-        float* sp = stash + bt * 1024 + d * 512 + j;
-        sp[0] = r; sp[128] = z; sp[256] = n; sp[384] = hn;
+        *reinterpret_cast<float4*>(stash + bt * 1024 + d * 512 + 4 * j) = make_float4(r, z, n, hn);
       }
       const float val = hnew * mk;
       if (ds == 1) {
@@ -155,8 +154,8 @@ gru_bwd_kernel(const float* __restrict__ dy_out, const float* __restrict__ mask,
     v.r = v.z = v.n = v.hn = v.hp = v.dy = 0.f;
     if (!valid) return;
     const size_t bt = (size_t)b * T + t;
-    const float* sp = stash + bt * 1024 + d * 512 + j;
-    v.r = __ldg(sp); v.z = __ldg(sp + 128); v.n = __ldg(sp + 256); v.hn = __ldg(sp + 384);
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(stash + bt * 1024 + d * 512 + 4 * j));
+    v.r = g4.x; v.z = g4.y; v.n = g4.z; v.hn = g4.w;
     const int tp = d ? t + 1 : t - 1;
     if (tp >= 0 && tp < T) v.hp = __ldg(y_full + ((size_t)b * T + tp) * 256 + d * SLU_H + j);
     float g;

@@ -190,7 +190,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
   }
   float* yf_j = y_full + d * SLU_H + j;
   float* yo_j = y_out + d * SLU_H + j;
-  float* st_j = STASH ? stash + d * 512 + j : nullptr;
+  float* st_j = STASH ? stash + d * 512 + 4 * j : nullptr;      // stash row: [direction][unit][r, z, n, hn] -- one 16-byte store per step
 
   // Step inputs arrive through a TMA ring: one elected thread bulk-copies the NB gx rows (1536 B each) and mask rows
   // (512 B) of step `s` into slot s % FWD_RING, FWD_RING steps ahead of their use.
@@ -335,8 +335,7 @@ gru_fwd_tc_kernel(const float* __restrict__ gx, const float* __restrict__ w_hh, 
       if (ok[c]) {
         yf_j[off[c]] = o_h[c];
         if (STASH) {
-          float* sp = st_j + 4 * (long)off[c];
-          sp[0] = o_r[c]; sp[128] = o_z[c]; sp[256] = o_n[c]; sp[384] = o_hn[c];
+          *reinterpret_cast<float4*>(st_j + 4 * (long)off[c]) = make_float4(o_r[c], o_z[c], o_n[c], o_hn[c]);
         }
         if (!first) yo_j[offo[c] + to] = o_out[c];
       }
@@ -467,7 +466,7 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
     const float dscale = (ds == 2 && !((t & 1) == 0 && t == T - 1)) ? 0.5f : 1.f;
     mbar_wait(&in_bar[s % BWD_RING], (uint32_t)((s / BWD_RING) & 1));
     const float* sl = in_ring + (s % BWD_RING) * SLOT;
-    const float* sts = sl + c0 * 512 + j;
+    const float4* sts = reinterpret_cast<const float4*>(sl + c0 * 512) + j;      // [unit][r, z, n, hn]: one 16-byte read per step
     const float* hps = sl + NR * 512 + c0 * 128 + j;
     const float* dys = sl + NR * 640 + c0 * 128 + j;
     const float* mks = sl + NR * 768 + c0 * 128 + j;
@@ -480,12 +479,13 @@ gru_bwd_tc_kernel(const float* __restrict__ dy_out, const float* __restrict__ ma
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const float mkv = mask ? mks[c * 128] : (rng ? (slu_gru_mask_draw16(rnd[c], t) < drop_thr ? drop_scale : 0.f) : 1.f);
-      const float r = sts[c * 512], z = sts[c * 512 + 128], n = sts[c * 512 + 256];
+      const float4 g4 = sts[c * 128];
+      const float r = g4.x, z = g4.y, n = g4.z;
       base[c] = dh_direct[c] + dys[c * 128] * (dscale * mkv);            // dL/dh without the recurrent part
       zc[c] = z; rc[c] = r;
       f_n[c] = (1.f - z) * (1.f - n * n);                                // dn_pre = dh * f_n
       f_z[c] = (hps[c * 128] * hp_on - n) * z * (1.f - z);               // dz_pre = dh * f_z
-      f_r[c] = sts[c * 512 + 384] * r * (1.f - r);                       // dr_pre = dn_pre * f_r
+      f_r[c] = g4.w * r * (1.f - r);                                     // dr_pre = dn_pre * f_r
     }
     float rec[NC];
     if (s == 0) {

@@ -72,7 +72,8 @@ int slu_sincconv_bwd_jac_tc(const float* x, const float* gy, const uint8_t* rout
  *             graph freezes its by-value arguments, slu_seed_advance(word) as the graph's first node gives every replay new masks.
  *   ds    1 = Downsample("none",1), 2 = Downsample("avg",2) (ceil mode: an odd tail frame is kept as is)
  *   y_full [B][T][256] raw hidden states (col = d*128 + j);  y_out [B][ceil(T/ds)][256]
- *   stash [B][T][1024] (r, z, n, W_hn h + b_hn per direction) for the backward pass, or NULL for inference. */
+ *   stash [B][T][1024] (col = d*512 + 4*j + s: r, z, n, W_hn h + b_hn of unit j, direction d, adjacent) for the backward pass, or NULL
+ *         for inference. */
 int slu_gru_fwd_simt(const float* gx, const float* w_hh, const float* b_hh, const float* drop_mask, float drop_p,
                      unsigned long long drop_seed, const unsigned long long* drop_seed_dev, int B, int T, int ds, float* y_full,
                      float* y_out, float* stash, void* stream);
