@@ -283,6 +283,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 #pragma unroll 1
       for (int ch = 0; ch < nchunks; ++ch) {
         const int c0 = ch * 32;
+        // fast path: 16-byte stores, a warp instruction writes 4 rows x 128 B.  Its bias vector is requested BEFORE the accumulator
+        // read: fetched where it is used it exposes an L2 round trip per chunk (tools/gemm_rate.py: -50 % on the x-projection's epilogue)
+        const bool fast = rows == 32 && c0 + 32 <= ncols && vec_ok && ((n0 + c0) & 3) == 0;
+        const int cq = (lane & 7) * 4, r0 = lane >> 3;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fast && p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + cq));
         float v[32];
         tmem_ld16(t_acc + c0, v);
         tmem_ld16(t_acc + c0 + 16, v + 16);
@@ -295,11 +301,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
         __syncwarp();
-        if (rows == 32 && c0 + 32 <= ncols && vec_ok && ((n0 + c0) & 3) == 0) {
-          // fast path: 16-byte stores, a warp instruction writes 4 rows x 128 B
-          const int cq = (lane & 7) * 4, r0 = lane >> 3;
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + cq));
+        if (fast) {
           float* dst4 = p.C + (long)(m0 + q * 32) * p.ldc + n0 + c0 + cq;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
