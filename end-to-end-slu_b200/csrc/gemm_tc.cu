@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         // Values are on their way to registers: the loader may refill the slot.  An mbarrier arrive does not wait for the thread's
         // outstanding shared-memory loads (measured in wgrad_tc.cu, whose TMA refill overtook them), but here the refill is made of
         // cp.async instructions that enter the SM's load/store queue behind these loads and write shared memory a global-memory
-        // latency later.  Making the arrive data-dependent on the loads (as wgrad_tc.cu must) costs 7 % of this kernel's time.
+        // latency later; two rounds of parity tests and sanitizer runs never saw a stale row here.
         mbar_arrive(&stg_empty[slot]);
         if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((it / STAGES) - 1) & 1));
         if (SLU_DBG(p) & 2) { mbar_arrive(&full_a[s]); continue; }
